@@ -1,0 +1,60 @@
+"""Container-only: pin the oracle against the live reference (skipped where /root/reference is absent)."""
+import pytest
+import torch
+
+from oracle import nerf_oracle as O
+from oracle import ref_loader
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return ref_loader.load("cpu")
+
+
+def test_sample_pdf_random_shapes(ref):
+    h = ref["helpers"]
+    for seed, (R, S, N) in enumerate([(1, 8, 5), (7, 64, 64), (5, 128, 256), (3, 3, 9)]):
+        g = torch.Generator().manual_seed(seed)
+        z = torch.sort(torch.rand(R, S, generator=g) * 5 + 1, -1)[0]
+        bins = .5 * (z[:, 1:] + z[:, :-1])
+        w = torch.rand(R, S - 2, generator=g)
+        assert torch.equal(h.sample_pdf(bins, w, N, det=True), O.sample_pdf(bins, w, N))
+        torch.manual_seed(seed)
+        a = h.sample_pdf(bins, w, N, det=False)
+        torch.manual_seed(seed)
+        u = torch.rand(R, N)
+        assert torch.equal(a, O.sample_pdf(bins, w, N, u))
+        cdf = O.build_cdf(w)
+        assert torch.equal(torch.searchsorted(cdf, u, right=True), O.upper_bound(cdf, u))
+
+
+def test_rays_and_ndc(ref):
+    h = ref["helpers"]
+    c2w = O.synthetic_c2w()
+    c2w[:3, :3] = torch.linalg.qr(torch.randn(3, 3, generator=torch.Generator().manual_seed(4)))[0]
+    o_r, d_r = h.get_rays(20, 30, 25.0, c2w)
+    o_m, d_m = O.get_rays(20, 30, 25.0, c2w)
+    assert torch.equal(o_r, o_m) and torch.equal(d_r, d_m)
+    a, b = h.ndc_rays(20, 30, 25.0, 1., o_r, d_r)
+    c, d = O.ndc_rays(20, 30, 25.0, 1., o_m, d_m)
+    assert torch.equal(a, c) and torch.equal(b, d)
+
+
+def test_stratified_and_render_rays_lin(ref, tmp_path):
+    """non-lindisp, no white background, N_importance=0 and a different S — branches the goldens do not cover."""
+    args = ref_loader.default_args(tmp_path, lindisp=False, white_bkgd=False, N_samples=24, N_importance=0)
+    torch.manual_seed(0)
+    kw_train, kw_test, *_ = ref["create_nerf"](args)
+    kw_test.update(near=O.NEAR, far=O.FAR)
+    pc = O.init_params(0)
+    rays = O.synthetic_rays(19, seed=9)
+    with torch.no_grad():
+        rgb, disp, acc, depth, ex = ref["render"](O.H_FULL, O.W_FULL, O.FOCAL, chunk=8,
+                                                  rays=torch.stack([rays[:, :3], rays[:, 3:6]]), **kw_test)
+        r = O.render(rays, chunk=8, p_coarse=pc, p_fine=None, n_samples=24, n_importance=0)
+    for a, b in ((rgb, r["rgb_map"]), (disp, r["disp_map"]), (acc, r["acc_map"]), (depth, r["depth_map"]),
+                 (ex["weights"], r["weights"]), (ex["z_vals"], r["z_vals"])):
+        torch.testing.assert_close(a, b, rtol=2e-5, atol=2e-6, equal_nan=True)
+    assert set(ex) == set(k for k in r if k not in ("rgb_map", "disp_map", "acc_map", "depth_map"))
