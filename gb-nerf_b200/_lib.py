@@ -1,0 +1,66 @@
+"""ctypes binding of libgbnerf.so — the reference-side stub of INTEGRATION.md, verbatim.
+
+The library is the product: if it is missing or a call fails this module raises; nothing here (or anywhere in
+the package) falls back to PyTorch or to the CPU oracle.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgbnerf.so")
+
+PRECISION = {"bf16": 0, "tf32": 1}
+
+_p, _i64, _i, _f, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/gbnerf.h one to one
+SIGNATURES = {
+    "gbn_version": (_i, []),
+    "gbn_last_error_string": (C.c_char_p, []),
+    "gbn_zvals_stratified": (_i, [_p, _p, _i64, _i64, _i, _i, _p, _p, _p]),
+    "gbn_encode_points": (_i, [_p, _p, _p, _i64, _p, _i64, _i, _p, _p]),
+    "gbn_composite_forward": (_i, [_p, _p, _p, _i64, _p, _i64, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "gbn_composite_backward": (_i, [_p, _p, _p, _i64, _p, _i64, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "gbn_sample_pdf": (_i, [_p, _p, _p, _i64, _i, _i, _p, _p]),
+    "gbn_searchsorted_right": (_i, [_p, _p, _i64, _i, _i, _p, _p]),
+    "gbn_sample_pdf_merge": (_i, [_p, _p, _p, _i64, _i, _i, _p, _p, _p, _p]),
+    "gbn_mlp_packed_bytes": (_sz, [_i]),
+    "gbn_mlp_prepack_weights": (_i, [C.POINTER(_p), _p, _i, _p]),
+    "gbn_mlp_workspace_bytes": (_sz, [_i64]),
+    "gbn_mlp_forward": (_i, [_p, _i, _p, _p, _p, _i64, _p, _p, _i64, _i, _p, _p, _p]),
+    "gbn_mlp_forward_embedded": (_i, [_p, _i, _p, _i64, _p, _p, _p]),
+    "gbn_loss_seed": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _f, _p, _p, _p, _p, _p]),
+}
+
+_lib = None
+
+
+class GbnError(RuntimeError):
+    pass
+
+
+def load():
+    """Load (once) and type the shared library; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GbnError(f"{LIB_PATH} is missing: build it with `python gb-nerf_b200/csrc/build.py` "
+                       "(or __graft_entry__.build()); there is no fallback path")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the ABI and the header ever drift apart
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point and raise on a non-zero code."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.gbn_last_error_string().decode(errors="replace")
+        if rc == 1:
+            raise ValueError(f"{name}: {msg}")
+        raise GbnError(f"{name} failed (code {rc}): {msg}")

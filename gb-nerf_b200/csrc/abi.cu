@@ -1,0 +1,26 @@
+// Error reporting and version of the C ABI (include/gbnerf.h).
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace gbn {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+  return GBN_ECUDA;
+}
+
+}  // namespace gbn
+
+extern "C" int gbn_version(void) { return 100; }  // 0.1.0
+
+extern "C" const char* gbn_last_error_string(void) { return gbn::g_err; }

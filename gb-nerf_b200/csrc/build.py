@@ -1,0 +1,63 @@
+"""Build libgbnerf.so in-tree with plain nvcc for sm_100a (no torch headers, no JIT cache).
+
+    python gb-nerf_b200/csrc/build.py [--force] [--verbose]
+
+The shared library lands next to the package (gb-nerf_b200/libgbnerf.so); it is git-ignored but travels to
+the GPU box with the gpurun snapshot.
+"""
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.dirname(HERE)
+OUT = os.path.join(PKG, "libgbnerf.so")
+STAMP = os.path.join(PKG, ".libgbnerf.stamp")
+SOURCES = ["abi.cu", "render_ops.cu", "mlp_tc.cu", "mlp_aux.cu"]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+         "-Xcompiler", "-fPIC,-O2,-Wall", "--expt-relaxed-constexpr"]
+
+
+def _digest():
+    h = hashlib.sha256(" ".join(FLAGS).encode())
+    names = sorted(f for f in os.listdir(HERE) if f.endswith((".cu", ".cuh", ".h")))
+    for n in names + ["../../include/gbnerf.h"]:
+        with open(os.path.join(HERE, n), "rb") as fh:
+            h.update(n.encode() + b"\0" + fh.read())
+    return h.hexdigest()
+
+
+def build(force=False, verbose=False):
+    srcs = [s for s in SOURCES if os.path.exists(os.path.join(HERE, s))]
+    dig = _digest()
+    if not force and os.path.exists(OUT) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
+        return OUT
+    objs = []
+    procs = []
+    for s in srcs:
+        o = os.path.join(HERE, s.replace(".cu", ".o"))
+        cmd = [NVCC, *FLAGS, "-c", os.path.join(HERE, s), "-o", o]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(o)
+    failed = False
+    for s, p in procs:
+        out, _ = p.communicate()
+        if out.strip() and (verbose or p.returncode != 0):
+            print(f"--- {s}\n{out}", file=sys.stderr)
+        failed |= p.returncode != 0
+    if failed:
+        raise RuntimeError("nvcc failed")
+    subprocess.check_call([NVCC, "-shared", "-o", OUT, *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+    for o in objs:
+        os.remove(o)
+    with open(STAMP, "w") as fh:
+        fh.write(dig)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,162 @@
+// Companions of the tcgen05 MLP kernel: the weight pre-packer (nn.Linear fp32 -> UMMA shared-memory images)
+// and the per-ray view-direction bias of views_linears.0 (run_nerf_helpers.py:117-121).
+#include <mutex>
+
+#include "common.cuh"
+#include "mlp_layout.h"
+#include "tc_ptx.cuh"
+
+namespace gbn {
+
+const MlpPlan& mlp_plan(int precision);  // mlp_tc.cu
+
+__constant__ PackJob c_pack[2][kMaxJobs];
+
+struct ParamPtrs {
+  const float* w[GBN_NUM_LINEAR];
+  const float* b[GBN_NUM_LINEAR];
+};
+
+struct PackHeader {
+  uint32_t magic, precision, off_bias, off_wdir, off_bdir, total_bytes, njobs, pad;
+};
+
+// one block per weight chunk: [rows x KB] slice of a linear's weight -> K-major, 128-byte-swizzled image
+template <int PREC>
+__global__ void __launch_bounds__(256) prepack_kernel(ParamPtrs pp, uint8_t* __restrict__ out, int njobs,
+                                                      PackHeader hdr) {
+  constexpr int ESZ = PREC == GBN_PRECISION_BF16 ? 2 : 4;
+  constexpr int KB = 128 / ESZ;
+  if ((int)blockIdx.x < njobs) {
+    const PackJob q = c_pack[PREC][blockIdx.x];
+    const float* W = pp.w[q.layer];
+    for (int i = threadIdx.x; i < q.rows * KB; i += blockDim.x) {
+      const int n = i / KB, k = i - n * KB;
+      float v = 0.f;
+      if (n < q.rows_valid && k < q.cols_valid) v = __ldg(W + (size_t)(q.row0 + n) * q.ld + q.col0 + k);
+      const uint32_t byte = (uint32_t)k * ESZ;
+      uint8_t* dst = out + q.w_off + tc::sw128_offset((uint32_t)n, byte >> 4) + (byte & 15);
+      if constexpr (PREC == GBN_PRECISION_BF16) {
+        *reinterpret_cast<uint16_t*>(dst) = (uint16_t)(tc::pack_bf16(v, 0.f) & 0xffff);
+      } else {
+        *reinterpret_cast<uint32_t*>(dst) = tc::to_tf32(v);
+      }
+    }
+    return;
+  }
+  // trailing block: header, biases, direction part of views_linears.0
+  if (threadIdx.x == 0) *reinterpret_cast<PackHeader*>(out) = hdr;
+  float* bias = reinterpret_cast<float*>(out + hdr.off_bias);
+  for (int i = threadIdx.x; i < kBiasFloats; i += blockDim.x) {
+    float v = 0.f;
+    if (i < kBiasFeat) v = pp.b[i >> 8][i & 255];
+    else if (i < kBiasAlpha) v = pp.b[LIN_FEATURE][i - kBiasFeat];
+    else if (i == kBiasAlpha) v = pp.b[LIN_ALPHA][0];
+    else if (i >= kBiasRgb && i < kBiasRgb + 3) v = pp.b[LIN_RGB][i - kBiasRgb];
+    bias[i] = v;
+  }
+  float* wdir = reinterpret_cast<float*>(out + hdr.off_wdir);
+  for (int i = threadIdx.x; i < 128 * 27; i += blockDim.x) {
+    const int j = i / 27, c = i - j * 27;
+    wdir[i] = pp.w[LIN_VIEWS][(size_t)j * 283 + 256 + c];
+  }
+  float* bdir = reinterpret_cast<float*>(out + hdr.off_bdir);
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) bdir[i] = pp.b[LIN_VIEWS][i];
+}
+
+// out[r, j] = b_views[j] + sum_c W_views[j, 256 + c] * enc4(viewdir_r)[c]   (fp32, exact direction term)
+constexpr int kVbRays = 16;
+__global__ void __launch_bounds__(128) view_bias_kernel(const float* __restrict__ wdir, const float* __restrict__ bdir,
+                                                        const float* __restrict__ vd, int64_t stride,
+                                                        const float* __restrict__ emb, int64_t n,
+                                                        float* __restrict__ out) {
+  __shared__ float w[27][128];
+  __shared__ float enc[kVbRays][28];
+  for (int i = threadIdx.x; i < 128 * 27; i += blockDim.x) w[i % 27][i / 27] = __ldg(wdir + i);
+  const float bj = __ldg(bdir + threadIdx.x);
+  const int64_t ngroups = (n + kVbRays - 1) / kVbRays;
+  for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    __syncthreads();
+    const int64_t r0 = g * kVbRays;
+    if (emb != nullptr) {
+      for (int i = threadIdx.x; i < kVbRays * 27; i += blockDim.x) {
+        const int rr = i / 27, c = i - rr * 27;
+        enc[rr][c] = (r0 + rr < n) ? __ldg(emb + (r0 + rr) * GBN_EMB_CH + GBN_PTS_CH + c) : 0.f;
+      }
+    } else if (threadIdx.x < kVbRays * 3) {
+      const int rr = threadIdx.x / 3, ax = threadIdx.x - rr * 3;
+      const float x = (r0 + rr < n) ? __ldg(vd + (r0 + rr) * stride + ax) : 0.f;
+      float sc[8];
+      posenc_axis<4>(x, sc);
+      enc[rr][ax] = x;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { enc[rr][3 + 6 * k + ax] = sc[2 * k]; enc[rr][6 + 6 * k + ax] = sc[2 * k + 1]; }
+    }
+    __syncthreads();
+    float acc[kVbRays];
+#pragma unroll
+    for (int rr = 0; rr < kVbRays; ++rr) acc[rr] = bj;
+#pragma unroll
+    for (int c = 0; c < 27; ++c) {
+      const float wc = w[c][threadIdx.x];
+#pragma unroll
+      for (int rr = 0; rr < kVbRays; ++rr) acc[rr] = fmaf(wc, enc[rr][c], acc[rr]);
+    }
+#pragma unroll
+    for (int rr = 0; rr < kVbRays; ++rr)
+      if (r0 + rr < n) out[(r0 + rr) * 128 + threadIdx.x] = acc[rr];
+  }
+}
+
+int launch_view_bias(const uint8_t* packed, const MlpPlan& p, const float* viewdirs, int64_t stride,
+                     const float* emb, int64_t n, float* out, cudaStream_t stream) {
+  const int64_t groups = (n + kVbRays - 1) / kVbRays;
+  const int grid = (int)(groups < kNumSMs * 8 ? groups : kNumSMs * 8);
+  view_bias_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const float*>(packed + p.off_wdir),
+                                             reinterpret_cast<const float*>(packed + p.off_bdir), viewdirs, stride, emb,
+                                             n, out);
+  return check_launch("view_bias_kernel");
+}
+
+static bool g_pack_init[64];
+static std::mutex g_pack_mutex;
+
+}  // namespace gbn
+
+using namespace gbn;
+
+extern "C" int gbn_mlp_prepack_weights(const void* const* params, void* packed, int precision, void* stream) {
+  GBN_REQUIRE(precision == GBN_PRECISION_BF16 || precision == GBN_PRECISION_TF32, "prepack: unknown precision %d", precision);
+  GBN_REQUIRE(params && packed, "prepack: null pointer");
+  GBN_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 255) == 0, "prepack: packed buffer must be 256-byte aligned");
+  ParamPtrs pp;
+  for (int i = 0; i < GBN_NUM_LINEAR; ++i) {
+    GBN_REQUIRE(params[2 * i] && params[2 * i + 1], "prepack: params[%d] is null", 2 * i);
+    pp.w[i] = static_cast<const float*>(params[2 * i]);
+    pp.b[i] = static_cast<const float*>(params[2 * i + 1]);
+  }
+  const MlpPlan& p = mlp_plan(precision);
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0;
+  GBN_CUDA(cudaGetDevice(&dev));
+  GBN_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
+  {
+    std::lock_guard<std::mutex> lk(g_pack_mutex);
+    if (!g_pack_init[dev]) {
+      for (int pr = 0; pr < 2; ++pr) {
+        const MlpPlan& q = mlp_plan(pr);
+        GBN_CUDA(cudaMemcpyToSymbolAsync(c_pack, q.pack.data(), q.pack.size() * sizeof(PackJob),
+                                         pr * kMaxJobs * sizeof(PackJob), cudaMemcpyHostToDevice, st));
+      }
+      g_pack_init[dev] = true;
+    }
+  }
+  PackHeader hdr{0x4e42476bu, (uint32_t)precision, p.off_bias, p.off_wdir, p.off_bdir, p.total_bytes,
+                 (uint32_t)p.jobs.size(), 0};
+  const int njobs = (int)p.jobs.size();
+  if (precision == GBN_PRECISION_BF16)
+    prepack_kernel<GBN_PRECISION_BF16><<<njobs + 1, 256, 0, st>>>(pp, static_cast<uint8_t*>(packed), njobs, hdr);
+  else
+    prepack_kernel<GBN_PRECISION_TF32><<<njobs + 1, 256, 0, st>>>(pp, static_cast<uint8_t*>(packed), njobs, hdr);
+  return check_launch("prepack_kernel");
+}

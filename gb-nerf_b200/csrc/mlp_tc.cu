@@ -1,0 +1,459 @@
+// The 8x256 NeRF MLP (run_nerf_helpers.py:75-129) as ONE persistent, warp-specialised tcgen05 kernel, fused
+// with ray-point generation and the sin/cos positional encoding (run.py:2317, run_nerf_helpers.py:23-53,
+// run.py:1637-1653).
+//
+// One CTA per SM, 128 points (rows) per tile, the whole network per tile without touching HBM in between:
+//   warp 0      weight producer : streams the pre-packed weight chunks (16 KB, UMMA K-major/128B-swizzle
+//                                 images) L2 -> smem ring with bulk TMA (cp.async.bulk + mbarrier tx-count)
+//   warp 1      MMA issuer      : one thread issues tcgen05.mma (M=128, N=128/16, K=32 B per step) with the
+//                                 activation tile as A (smem), the weight chunk as B (smem), fp32
+//                                 accumulators in TMEM; tcgen05.commit releases ring slots / signals layers
+//   warp 2      TMEM allocator
+//   warps 4-7   encoders        : next tile's points o + d*z, 63-channel encoding -> A operand of layer 0/5
+//   warps 8-15  epilogue        : TMEM -> registers (tcgen05.ld) -> +bias, ReLU -> bf16/tf32 -> swizzled smem
+//                                 = the next layer's A operand, handed over per 128-byte K-block so the next
+//                                 layer's MMAs start while the rest of the tile is still being converted
+// Accumulators ping-pong between two 256-column TMEM regions (X, Y), so layer l+1 runs on the tensor pipe
+// while layer l's accumulator is drained.  The last epilogue writes (r,g,b,sigma_raw) as one float4 per row.
+#include <mutex>
+
+#include "common.cuh"
+#include "mlp_layout.h"
+#include "tc_ptx.cuh"
+
+namespace gbn {
+
+using namespace tc;
+
+__constant__ MlpJob c_jobs[2][kMaxJobs];
+__constant__ int c_unit_begin[2][kNumUnits + 1];
+
+template <int PREC>
+struct Cfg;
+template <>
+struct Cfg<GBN_PRECISION_BF16> {
+  static constexpr int ESZ = 2, KB = 64, NBLK = 4, ENCB = 1, NST = 8;
+  static constexpr uint32_t FMT = 1;
+};
+template <>
+struct Cfg<GBN_PRECISION_TF32> {
+  static constexpr int ESZ = 4, KB = 32, NBLK = 8, ENCB = 2, NST = 3;
+  static constexpr uint32_t FMT = 2;
+};
+
+constexpr int kThreadsMlp = 512;
+constexpr int kStageBytes = 16384;
+
+template <int PREC>
+struct Smem {
+  using C = Cfg<PREC>;
+  static constexpr uint32_t act = 0;
+  static constexpr uint32_t enc = act + C::NBLK * kBlkBytes;
+  static constexpr uint32_t ring = enc + C::ENCB * kBlkBytes;
+  static constexpr uint32_t bias = ring + C::NST * kStageBytes;
+  static constexpr uint32_t bars = bias + kBiasFloats * 4;
+  // barrier slots (8 B each)
+  static constexpr uint32_t w_full = bars;
+  static constexpr uint32_t w_empty = w_full + 8 * C::NST;
+  static constexpr uint32_t acc_full = w_empty + 8 * C::NST;
+  static constexpr uint32_t act_ready = acc_full + 8 * kNumUnits;
+  static constexpr uint32_t enc_full = act_ready + 8 * C::NBLK;
+  static constexpr uint32_t enc_empty = enc_full + 8;
+  static constexpr uint32_t tmem_ptr = enc_empty + 8;
+  static constexpr uint32_t abort_flag = tmem_ptr + 4;
+  static constexpr uint32_t total = abort_flag + 4;
+  static constexpr uint32_t alloc = total + 1024;  // slack for the 1024-byte alignment of the base
+};
+
+struct MlpArgs {
+  const uint8_t* packed;
+  const float* ro; const float* rd;   // ray origins / directions, pitch `stride` floats
+  const float* z;                     // [R,S]
+  const float* pts;                   // optional dense [P,3]
+  const float* emb;                   // optional dense [P,90] (pre-embedded rows)
+  const float* view_bias;             // [P / S, 128] fp32
+  float* raw;                         // [P,4]
+  int* err;
+  int64_t stride;
+  int64_t P;
+  int S;
+};
+
+// bounded mbarrier wait that also honours the CTA-wide abort flag (set by whoever times out first)
+__device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity, uint32_t abort_addr, int* err, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    uint32_t ab;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(ab) : "r"(abort_addr));
+    if (ab) return;
+    if (clock64() - t0 > kWatchdogCycles) {
+      atomicCAS(err, 0, code);
+      asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(abort_addr), "r"(1u));
+      return;
+    }
+  }
+}
+
+template <int PREC>
+__device__ __forceinline__ void store_group32(uint32_t row_addr, int row, int chunk0, const float (&f)[32], bool relu) {
+  // 32 consecutive output channels of one row -> bf16: 4 chunks of 16 B, tf32: 8 chunks
+  if constexpr (PREC == GBN_PRECISION_BF16) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        w[i] = relu ? pack_bf16_relu(f[c * 8 + 2 * i], f[c * 8 + 2 * i + 1]) : pack_bf16(f[c * 8 + 2 * i], f[c * 8 + 2 * i + 1]);
+      st_smem16(row_addr + (((chunk0 + c) ^ (row & 7)) << 4), w[0], w[1], w[2], w[3]);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uint32_t w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w[i] = to_tf32(relu ? fmaxf(f[c * 4 + i], 0.f) : f[c * 4 + i]);
+      st_smem16(row_addr + (((chunk0 + c) ^ (row & 7)) << 4), w[0], w[1], w[2], w[3]);
+    }
+  }
+}
+
+template <int PREC>
+__global__ void __launch_bounds__(kThreadsMlp, 1) nerf_mlp_kernel(const MlpArgs a) {
+  using C = Cfg<PREC>;
+  using L = Smem<PREC>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* const gen = smem_raw + (base - smem_u32(smem_raw));  // generic pointer to the aligned base
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ntiles = (a.P + kTileRows - 1) / kTileRows;
+  const int my_tiles = (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  const uint32_t abort_addr = base + L::abort_flag;
+  const MlpJob* jobs = c_jobs[PREC];
+  const int* ub = c_unit_begin[PREC];
+
+  // ---- one-time setup ------------------------------------------------------------------------------------
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C::NST; ++i) { mbar_init(base + L::w_full + 8 * i, 1); mbar_init(base + L::w_empty + 8 * i, 1); }
+    for (int i = 0; i < kNumUnits; ++i) mbar_init(base + L::acc_full + 8 * i, 1);
+    for (int i = 0; i < C::NBLK; ++i) mbar_init(base + L::act_ready + 8 * i, 128);
+    mbar_init(base + L::enc_full, 128);
+    mbar_init(base + L::enc_empty, 1);
+    *reinterpret_cast<volatile uint32_t*>(gen + L::abort_flag) = 0;
+    mbar_init_fence();
+  }
+  if (warp == 2) tmem_alloc(base + L::tmem_ptr, kTmemCols);
+  {  // biases -> smem
+    const float* gb = reinterpret_cast<const float*>(a.packed + reinterpret_cast<const uint32_t*>(a.packed)[2]);
+    float* sb = reinterpret_cast<float*>(gen + L::bias);
+    for (int i = threadIdx.x; i < kBiasFloats; i += blockDim.x) sb[i] = __ldg(gb + i);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + L::tmem_ptr);
+
+  if (warp == 0) {
+    // =============================== weight producer (one thread) ========================================
+    if (lane == 0) {
+      uint32_t cnt = 0;
+      auto emit = [&](int u) {
+        for (int j = ub[u]; j < ub[u + 1]; ++j) {
+          const uint32_t s = cnt % C::NST, par = (cnt / C::NST) & 1;
+          wait_bar(base + L::w_empty + 8 * s, par ^ 1, abort_addr, a.err, 0x10000000 | j);
+          const uint32_t bytes = (uint32_t)jobs[j].w_bytes16 * 16;
+          mbar_expect_tx(base + L::w_full + 8 * s, bytes);
+          tma_bulk_g2s(base + L::ring + s * kStageBytes, a.packed + jobs[j].w_off, bytes, base + L::w_full + 8 * s);
+          ++cnt;
+        }
+      };
+      if (my_tiles > 0) emit(0);
+      for (int t = 0; t < my_tiles; ++t) {
+        for (int u = 1; u <= 9; ++u) emit(u);
+        if (t + 1 < my_tiles) emit(0);
+        emit(10);
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer (one thread) =============================================
+    if (lane == 0) {
+      uint32_t cnt = 0, act_par = 0;
+      auto issue = [&](int u, int t) {
+        for (int j = ub[u]; j < ub[u + 1]; ++j) {
+          const MlpJob jb = jobs[j];
+          if (jb.flags & JF_WAIT_ENC) wait_bar(base + L::enc_full, t & 1, abort_addr, a.err, 0x20000000 | j);
+          if (jb.flags & JF_WAIT_ACT) {
+            wait_bar(base + L::act_ready + 8 * jb.a_blk, (act_par >> jb.a_blk) & 1, abort_addr, a.err, 0x21000000 | j);
+            act_par ^= 1u << jb.a_blk;
+          }
+          const uint32_t s = cnt % C::NST, par = (cnt / C::NST) & 1;
+          wait_bar(base + L::w_full + 8 * s, par, abort_addr, a.err, 0x22000000 | j);
+          tc_fence_after_sync();
+          const uint32_t a_addr = (jb.a_blk & kEncBlkFlag) ? base + L::enc + (jb.a_blk & 0x7f) * kBlkBytes
+                                                           : base + L::act + jb.a_blk * kBlkBytes;
+          const uint64_t adesc = smem_desc_sw128(a_addr);
+          const uint64_t bdesc = smem_desc_sw128(base + L::ring + s * kStageBytes);
+          const uint32_t idesc = make_idesc(C::FMT, 128, (uint32_t)jb.n8 * 8);
+          const uint32_t d = tmem + jb.d_col;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t accum = ((jb.flags & JF_FIRST) && k == 0) ? 0u : 1u;
+            if constexpr (PREC == GBN_PRECISION_BF16) umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+            else umma_tf32(d, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+          }
+          umma_commit(base + L::w_empty + 8 * s);
+          if (jb.flags & JF_COMMIT_ENC) umma_commit(base + L::enc_empty);
+          if (jb.flags & JF_COMMIT_ACC) umma_commit(base + L::acc_full + 8 * jb.unit);
+          ++cnt;
+        }
+      };
+      if (my_tiles > 0) issue(0, 0);
+      for (int t = 0; t < my_tiles; ++t) {
+        for (int u = 1; u <= 9; ++u) issue(u, t);
+        if (t + 1 < my_tiles) issue(0, t + 1);
+        issue(10, t);
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // =============================== encoders: thread == row of the next tile ============================
+    const int row = threadIdx.x - 128;
+    const uint32_t row_off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int64_t tile = blockIdx.x + (int64_t)t * gridDim.x;
+      const int64_t p = tile * kTileRows + row;
+      float e[64];
+      if (p < a.P) {
+        if (a.emb != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 63; ++i) e[i] = __ldg(a.emb + p * GBN_EMB_CH + i);
+        } else {
+          float x[3];
+          if (a.pts != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) x[i] = __ldg(a.pts + p * 3 + i);
+          } else {
+            const int64_t r = p / a.S;
+            const float zz = __ldg(a.z + p);
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+              x[i] = __fadd_rn(__ldg(a.ro + r * a.stride + i), __fmul_rn(__ldg(a.rd + r * a.stride + i), zz));
+          }
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            float sc[20];
+            posenc_axis<10>(x[i], sc);
+            e[i] = x[i];
+#pragma unroll
+            for (int k = 0; k < 10; ++k) { e[3 + 6 * k + i] = sc[2 * k]; e[6 + 6 * k + i] = sc[2 * k + 1]; }
+          }
+        }
+        e[63] = 0.f;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) e[i] = 0.f;
+      }
+      if (t > 0) wait_bar(base + L::enc_empty, (t - 1) & 1, abort_addr, a.err, 0x30000000 | t);
+      // 64 channels: bf16 -> one K-block (8 chunks); tf32 -> two K-blocks (8 chunks each)
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = e[g * 32 + i];
+        if constexpr (PREC == GBN_PRECISION_BF16)
+          store_group32<PREC>(base + L::enc + row_off, row, g * 4, f, false);
+        else
+          store_group32<PREC>(base + L::enc + g * kBlkBytes + row_off, row, 0, f, false);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(base + L::enc_full);
+    }
+  } else if (warp >= 8) {
+    // =============================== epilogue: thread == row, two warpgroups split the K-blocks ==========
+    const int wg = (warp - 8) >> 2;                 // 0 or 1
+    const int row = ((warp & 3) << 5) | lane;       // TMEM lane == tile row; warp%4 selects the lane quadrant
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) << 5) << 16);
+    const uint32_t row_off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
+    const float* sbias = reinterpret_cast<const float*>(gen + L::bias);
+    constexpr int GPB = C::KB / 32;                 // 32-column groups per K-block (bf16 2, tf32 1)
+    for (int t = 0; t < my_tiles; ++t) {
+      const int64_t tile = blockIdx.x + (int64_t)t * gridDim.x;
+      const int64_t p = tile * kTileRows + row;
+      const uint32_t par = t & 1;
+      float sigma_acc = 0.f;
+      for (int u = 0; u <= 9; ++u) {
+        wait_bar(base + L::acc_full + 8 * u, par, abort_addr, a.err, 0x40000000 | (u << 8) | wg);
+        tc_fence_after_sync();
+        const uint32_t col0 = (u & 1) ? kColY : kColX;
+        const int nb = (u == 9) ? (128 / C::KB) : C::NBLK;
+        const bool relu = (u != 8);
+        const float* vb = nullptr;
+        if (u == 9) {
+          const int64_t pr = p < a.P ? p : a.P - 1;
+          vb = a.view_bias + (pr / a.S) * 128;
+          if (wg == 0) {  // sigma accumulator finished together with the feature layer
+            uint32_t sv;
+            tmem_ld1(lane_addr + kColAlpha, sv);
+            tmem_ld_wait();
+            sigma_acc = __uint_as_float(sv);
+          }
+        }
+        for (int b = wg; b < nb; b += 2) {
+          uint32_t v[GPB][32];
+#pragma unroll
+          for (int g = 0; g < GPB; ++g) tmem_ld32(lane_addr + col0 + b * C::KB + g * 32, v[g]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < GPB; ++g) {
+            float f[32];
+            const int c0 = b * C::KB + g * 32;
+            if (u == 9) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(vb + c0 + i));
+                f[i] = __uint_as_float(v[g][i]) + bb.x; f[i + 1] = __uint_as_float(v[g][i + 1]) + bb.y;
+                f[i + 2] = __uint_as_float(v[g][i + 2]) + bb.z; f[i + 3] = __uint_as_float(v[g][i + 3]) + bb.w;
+              }
+            } else {
+              const float4* bp = reinterpret_cast<const float4*>(sbias + (u == 8 ? kBiasFeat : u * 256) + c0);
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 bb = bp[i >> 2];
+                f[i] = __uint_as_float(v[g][i]) + bb.x; f[i + 1] = __uint_as_float(v[g][i + 1]) + bb.y;
+                f[i + 2] = __uint_as_float(v[g][i + 2]) + bb.z; f[i + 3] = __uint_as_float(v[g][i + 3]) + bb.w;
+              }
+            }
+            store_group32<PREC>(base + L::act + b * kBlkBytes + row_off, row, g * (GPB == 2 ? 4 : 0), f, relu);
+          }
+          fence_proxy_async_smem();
+          tc_fence_before_sync();
+          mbar_arrive(base + L::act_ready + 8 * b);
+        }
+      }
+      // ---- unit 10: rgb accumulator + sigma -> raw[p] ------------------------------------------------------
+      wait_bar(base + L::acc_full + 8 * 10, par, abort_addr, a.err, 0x40000000 | (10 << 8) | wg);
+      tc_fence_after_sync();
+      if (wg == 0) {
+        uint32_t c[4];
+        tmem_ld4(lane_addr + kColRgb, c);
+        tmem_ld_wait();
+        if (p < a.P) {
+          float4 o;
+          o.x = __uint_as_float(c[0]) + sbias[kBiasRgb + 0];
+          o.y = __uint_as_float(c[1]) + sbias[kBiasRgb + 1];
+          o.z = __uint_as_float(c[2]) + sbias[kBiasRgb + 2];
+          o.w = sigma_acc + sbias[kBiasAlpha];
+          st_stream4(reinterpret_cast<float4*>(a.raw) + p, o);
+        }
+      }
+      tc_fence_before_sync();
+    }
+  }
+
+  // ---- teardown ------------------------------------------------------------------------------------------
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, kTmemCols);
+}
+
+// =========================================================================================================
+// host side
+// =========================================================================================================
+static std::once_flag g_plan_once;
+static MlpPlan g_plan[2];
+static bool g_dev_init[64];
+static std::mutex g_dev_mutex;
+
+static const MlpPlan& plan(int precision) {
+  std::call_once(g_plan_once, [] {
+    g_plan[0] = make_plan(GBN_PRECISION_BF16);
+    g_plan[1] = make_plan(GBN_PRECISION_TF32);
+  });
+  return g_plan[precision];
+}
+
+const MlpPlan& mlp_plan(int precision) { return plan(precision); }
+
+// per-device one-time setup: job tables -> constant memory, opt-in shared memory size
+static int ensure_device(cudaStream_t stream) {
+  int dev = 0;
+  GBN_CUDA(cudaGetDevice(&dev));
+  GBN_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
+  std::lock_guard<std::mutex> lk(g_dev_mutex);
+  if (g_dev_init[dev]) return GBN_OK;
+  for (int pr = 0; pr < 2; ++pr) {
+    const MlpPlan& p = plan(pr);
+    GBN_REQUIRE((int)p.jobs.size() <= kMaxJobs, "job table overflow");
+    GBN_CUDA(cudaMemcpyToSymbolAsync(c_jobs, p.jobs.data(), p.jobs.size() * sizeof(MlpJob),
+                                     pr * kMaxJobs * sizeof(MlpJob), cudaMemcpyHostToDevice, stream));
+    GBN_CUDA(cudaMemcpyToSymbolAsync(c_unit_begin, p.unit_begin, sizeof(p.unit_begin),
+                                     pr * sizeof(p.unit_begin), cudaMemcpyHostToDevice, stream));
+  }
+  GBN_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<GBN_PRECISION_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)Smem<GBN_PRECISION_BF16>::alloc));
+  GBN_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<GBN_PRECISION_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)Smem<GBN_PRECISION_TF32>::alloc));
+  g_dev_init[dev] = true;
+  return GBN_OK;
+}
+
+int launch_view_bias(const uint8_t* packed, const MlpPlan& p, const float* viewdirs, int64_t stride,
+                     const float* emb, int64_t n, float* out, cudaStream_t stream);  // mlp_aux.cu
+
+static int run_mlp(const void* packed, int precision, const float* ro, const float* rd, const float* vd,
+                   int64_t stride, const float* z, const float* pts, const float* emb, int64_t R, int S, float* raw,
+                   void* workspace, cudaStream_t stream) {
+  GBN_REQUIRE(precision == GBN_PRECISION_BF16 || precision == GBN_PRECISION_TF32, "mlp: unknown precision %d", precision);
+  GBN_REQUIRE(R >= 0 && S >= 1, "mlp: bad sizes R=%lld S=%d", (long long)R, S);
+  if (R == 0) return GBN_OK;
+  GBN_REQUIRE(packed && raw && workspace, "mlp: null pointer");
+  GBN_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 255) == 0, "mlp: packed weights must be 256-byte aligned");
+  GBN_REQUIRE(((reinterpret_cast<uintptr_t>(raw) | reinterpret_cast<uintptr_t>(workspace)) & 15) == 0,
+              "mlp: raw / workspace must be 16-byte aligned");
+  int rc = ensure_device(stream);
+  if (rc != GBN_OK) return rc;
+  const MlpPlan& p = plan(precision);
+  int* err = reinterpret_cast<int*>(workspace);
+  float* vbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + 256);
+  GBN_CUDA(cudaMemsetAsync(err, 0, 256, stream));
+  rc = launch_view_bias(reinterpret_cast<const uint8_t*>(packed), p, vd, stride, emb, R, vbias, stream);
+  if (rc != GBN_OK) return rc;
+  MlpArgs a{};
+  a.packed = reinterpret_cast<const uint8_t*>(packed);
+  a.ro = ro; a.rd = rd; a.z = z; a.pts = pts; a.emb = emb;
+  a.view_bias = vbias; a.raw = raw; a.err = err;
+  a.stride = stride; a.P = R * S; a.S = S;
+  const int64_t ntiles = (a.P + kTileRows - 1) / kTileRows;
+  const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
+  if (precision == GBN_PRECISION_BF16)
+    nerf_mlp_kernel<GBN_PRECISION_BF16><<<grid, kThreadsMlp, Smem<GBN_PRECISION_BF16>::alloc, stream>>>(a);
+  else
+    nerf_mlp_kernel<GBN_PRECISION_TF32><<<grid, kThreadsMlp, Smem<GBN_PRECISION_TF32>::alloc, stream>>>(a);
+  return check_launch("nerf_mlp_kernel");
+}
+
+}  // namespace gbn
+
+using namespace gbn;
+
+extern "C" size_t gbn_mlp_packed_bytes(int precision) {
+  if (precision != GBN_PRECISION_BF16 && precision != GBN_PRECISION_TF32) return 0;
+  return mlp_plan(precision).total_bytes;
+}
+
+extern "C" size_t gbn_mlp_workspace_bytes(int64_t R) { return 256 + (size_t)(R < 0 ? 0 : R) * 128 * sizeof(float); }
+
+extern "C" int gbn_mlp_forward(const void* packed, int precision, const float* rays_o, const float* rays_d,
+                               const float* viewdirs, int64_t ray_stride, const float* z, const float* pts,
+                               int64_t R, int S, float* raw, void* workspace, void* stream) {
+  GBN_REQUIRE(viewdirs, "mlp_forward: viewdirs is required");
+  GBN_REQUIRE(pts || (rays_o && rays_d && z), "mlp_forward: need pts or (rays_o, rays_d, z)");
+  return run_mlp(packed, precision, rays_o, rays_d, viewdirs, ray_stride, z, pts, nullptr, R, S, raw, workspace,
+                 (cudaStream_t)stream);
+}
+
+extern "C" int gbn_mlp_forward_embedded(const void* packed, int precision, const float* emb, int64_t P, float* raw,
+                                        void* workspace, void* stream) {
+  GBN_REQUIRE(emb, "mlp_forward_embedded: null pointer");
+  return run_mlp(packed, precision, nullptr, nullptr, nullptr, 0, nullptr, nullptr, emb, P, 1, raw, workspace,
+                 (cudaStream_t)stream);
+}

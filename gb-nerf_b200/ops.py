@@ -1,0 +1,339 @@
+"""Tensor-level operators over the C ABI (include/gbnerf.h) + their autograd wiring.
+
+PyTorch is plumbing here: it owns device memory and the current stream; every operator below enqueues exactly
+one (or two) kernels of libgbnerf.so on that stream.  Inputs must be CUDA fp32 tensors — anything else raises
+(ValueError for shape/dtype/device problems, in the spirit of the reference extension's AT_ASSERTM checks,
+torchsearchsorted/src/cuda/searchsorted_cuda_wrapper.cpp:5-7).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import PRECISION
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t, name, dim=None, allow_none=False):
+    if t is None:
+        if allow_none:
+            return None
+        raise ValueError(f"{name} is required")
+    if not isinstance(t, torch.Tensor):
+        raise ValueError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise ValueError(f"{name} must live on a CUDA device (no CPU path exists)")
+    if t.dtype != torch.float32:
+        raise ValueError(f"{name} must be float32, got {t.dtype}")
+    if dim is not None and t.dim() != dim:
+        raise ValueError(f"{name} must have {dim} dims, got shape {tuple(t.shape)}")
+    return t
+
+
+def _dense(t, name, dim=None, allow_none=False):
+    t = _chk(t, name, dim, allow_none)
+    if t is None:
+        return None
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _ray_views(*cols):
+    """[R,k] column views of one packed ray batch (run.py:1726-1736) share a row pitch and are passed as they
+    are; anything else (different pitches, broadcast strides, a single ray) is copied to dense [R,k]."""
+    cols = [_chk(c, "ray tensor", 2) for c in cols]
+    R, k = cols[0].shape
+    if any(tuple(c.shape) != (R, k) for c in cols):
+        raise ValueError("ray tensors disagree in shape")
+    pitch = cols[0].stride(0)
+    if R > 1 and pitch >= k and all(c.stride(1) == 1 and c.stride(0) == pitch for c in cols):
+        return cols, int(pitch)
+    return [c.contiguous() for c in cols], int(k)
+
+
+# --------------------------------------------------------------------------------------------------------- #
+def zvals_stratified(near, far, n_samples, lindisp=False, t_rand=None):
+    """near, far: [R] or [R,1] (column views of the ray batch are fine) -> z [R,S].  run.py:2291-2315."""
+    near = near.reshape(near.shape[0], -1)[:, :1] if near.dim() != 2 else near[:, :1]
+    far = far.reshape(far.shape[0], -1)[:, :1] if far.dim() != 2 else far[:, :1]
+    (near, far), pitch = _ray_views(near, far)
+    R = near.shape[0]
+    t_rand = _dense(t_rand, "t_rand", 2, allow_none=True)
+    if t_rand is not None and tuple(t_rand.shape) != (R, n_samples):
+        raise ValueError("t_rand must be [R, N_samples]")
+    z = torch.empty(R, n_samples, device=near.device, dtype=torch.float32)
+    _lib.call("gbn_zvals_stratified", _ptr(near), _ptr(far), pitch, R, int(n_samples), int(bool(lindisp)),
+              _ptr(t_rand), _ptr(z), _stream())
+    return z
+
+
+def encode_points(rays_o, rays_d, viewdirs, z):
+    """Materialised [R*S, 90] embedding of o + d*z and the ray's view direction (test / measurement only)."""
+    (rays_o, rays_d, viewdirs), pitch = _ray_views(rays_o, rays_d, viewdirs)
+    z = _dense(z, "z", 2)
+    R, S = z.shape
+    out = torch.empty(R * S, 90, device=z.device, dtype=torch.float32)
+    _lib.call("gbn_encode_points", _ptr(rays_o), _ptr(rays_d), _ptr(viewdirs), pitch, _ptr(z), R, S, _ptr(out),
+              _stream())
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------- #
+class _Composite(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, raw, z, rays_d, noise, white_bkgd, detach_weights, need_alpha):
+        raw = _dense(raw, "raw", 3)
+        z = _dense(z, "z_vals", 2)
+        noise = _dense(noise, "noise", 2, allow_none=True)
+        (rays_d,), pitch = _ray_views(rays_d)
+        R, S = z.shape
+        if tuple(raw.shape) != (R, S, 4) or rays_d.shape[0] != R:
+            raise ValueError(f"raw {tuple(raw.shape)} / z_vals {tuple(z.shape)} / rays_d {tuple(rays_d.shape)} mismatch")
+        dev = raw.device
+        rgb = torch.empty(R, 3, device=dev); disp = torch.empty(R, device=dev); acc = torch.empty(R, device=dev)
+        depth = torch.empty(R, device=dev); weights = torch.empty(R, S, device=dev)
+        alpha = torch.empty(R, S, device=dev) if need_alpha else None
+        _lib.call("gbn_composite_forward", _ptr(raw), _ptr(z), _ptr(rays_d), pitch, _ptr(noise), R, S,
+                  int(bool(white_bkgd)), _ptr(rgb), _ptr(disp), _ptr(acc), _ptr(depth), _ptr(weights), _ptr(alpha),
+                  _stream())
+        ctx.save_for_backward(raw, z, rays_d, noise if noise is not None else torch.empty(0, device=dev))
+        ctx.cfg = (pitch, bool(white_bkgd), bool(detach_weights), noise is not None)
+        if alpha is None:
+            alpha = torch.empty(0, device=dev)
+        ctx.mark_non_differentiable(alpha)
+        return rgb, disp, acc, weights, depth, alpha
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_disp, g_acc, g_weights, g_depth, _g_alpha):
+        raw, z, rays_d, noise = ctx.saved_tensors
+        pitch, white, detach_w, has_noise = ctx.cfg
+        R, S = z.shape
+        g_raw = torch.empty_like(raw)
+        c = lambda g: g.contiguous().float() if g is not None else None
+        g_rgb, g_disp, g_acc, g_weights, g_depth = map(c, (g_rgb, g_disp, g_acc, g_weights, g_depth))
+        _lib.call("gbn_composite_backward", _ptr(raw), _ptr(z), _ptr(rays_d), pitch,
+                  _ptr(noise if has_noise else None), R, S, int(white), int(detach_w), _ptr(g_rgb), _ptr(g_disp),
+                  _ptr(g_acc), _ptr(g_depth), _ptr(g_weights), _ptr(g_raw), _stream())
+        return g_raw, None, None, None, None, None, None
+
+
+def composite(raw, z_vals, rays_d, noise=None, white_bkgd=False, detach_weights=False, need_alpha=False):
+    """raw2outputs on the device: returns (rgb, disp, acc, weights, depth, alpha-or-None)."""
+    rgb, disp, acc, weights, depth, alpha = _Composite.apply(raw, z_vals, rays_d, noise, white_bkgd, detach_weights,
+                                                             need_alpha)
+    return rgb, disp, acc, weights, depth, (alpha if need_alpha else None)
+
+
+# --------------------------------------------------------------------------------------------------------- #
+def searchsorted_right(cdf, u):
+    """int64 indices == torch.searchsorted(cdf, u, right=True)."""
+    cdf, u = _dense(cdf, "cdf", 2), _dense(u, "u", 2)
+    if cdf.shape[0] != u.shape[0]:
+        raise ValueError("cdf and u disagree on the number of rows")
+    inds = torch.empty(u.shape, device=u.device, dtype=torch.int64)
+    _lib.call("gbn_searchsorted_right", _ptr(cdf), _ptr(u), u.shape[0], cdf.shape[1], u.shape[1], _ptr(inds), _stream())
+    return inds
+
+
+def sample_pdf(bins, weights, n_samples, u=None):
+    """bins [R,B], weights [R,B-1] -> samples [R,N]; u=None is the deterministic linspace branch."""
+    bins, weights = _dense(bins.detach(), "bins", 2), _dense(weights.detach(), "weights", 2)
+    u = _dense(u, "u", 2, allow_none=True)
+    R, B = bins.shape
+    if tuple(weights.shape) != (R, B - 1):
+        raise ValueError(f"weights must be [R, B-1] = {(R, B - 1)}, got {tuple(weights.shape)}")
+    if u is not None and tuple(u.shape) != (R, n_samples):
+        raise ValueError("u must be [R, N_samples]")
+    out = torch.empty(R, n_samples, device=bins.device, dtype=torch.float32)
+    _lib.call("gbn_sample_pdf", _ptr(bins), _ptr(weights), _ptr(u), R, B, int(n_samples), _ptr(out), _stream())
+    return out
+
+
+def sample_pdf_merge(z_vals, weights, n_importance, u=None, want_samples=False):
+    """Fused run.py:2343-2348 + :2370.  Returns (z_merged [R,S+N], z_std [R], z_samples [R,N] or None)."""
+    z_vals, weights = _dense(z_vals.detach(), "z_vals", 2), _dense(weights.detach(), "weights", 2)
+    u = _dense(u, "u", 2, allow_none=True)
+    R, S = z_vals.shape
+    if tuple(weights.shape) != (R, S):
+        raise ValueError("weights must match z_vals")
+    N = int(n_importance)
+    dev = z_vals.device
+    merged = torch.empty(R, S + N, device=dev); std = torch.empty(R, device=dev)
+    samples = torch.empty(R, N, device=dev) if want_samples else None
+    _lib.call("gbn_sample_pdf_merge", _ptr(z_vals), _ptr(weights), _ptr(u), R, S, N, _ptr(samples), _ptr(merged),
+              _ptr(std), _stream())
+    return merged, std, samples
+
+
+# --------------------------------------------------------------------------------------------------------- #
+PARAM_ORDER = tuple([f"pts_linears.{i}" for i in range(8)] + ["feature_linear", "alpha_linear", "views_linears.0",
+                                                               "rgb_linear"])
+PARAM_SHAPES = {"pts_linears.0": (256, 63), "pts_linears.5": (256, 319), "feature_linear": (256, 256),
+                "alpha_linear": (1, 256), "views_linears.0": (128, 283), "rgb_linear": (3, 128)}
+
+
+def prepack_weights(params, precision="bf16", out=None):
+    """params: 24 tensors (weight, bias) x PARAM_ORDER -> packed uint8 buffer in the kernel's smem layout."""
+    prec = PRECISION[precision]
+    if len(params) != 24:
+        raise ValueError("expected 24 parameter tensors")
+    keep = []
+    for i, p in enumerate(params):
+        p = _chk(p.detach(), f"params[{i}]")
+        keep.append(p if p.is_contiguous() else p.contiguous())
+    for i, name in enumerate(PARAM_ORDER):
+        want = PARAM_SHAPES.get(name, (256, 256))
+        if tuple(keep[2 * i].shape) != want or tuple(keep[2 * i + 1].shape) != (want[0],):
+            raise ValueError(f"{name}: expected weight {want}, got {tuple(keep[2 * i].shape)}")
+    nbytes = _lib.load().gbn_mlp_packed_bytes(prec)
+    if out is None:
+        out = torch.empty(nbytes, device=keep[0].device, dtype=torch.uint8)
+    arr = (C.c_void_p * 24)(*[p.data_ptr() for p in keep])
+    _lib.call("gbn_mlp_prepack_weights", arr, _ptr(out), prec, _stream())
+    return out
+
+
+def _workspace(R, device):
+    return torch.empty(_lib.load().gbn_mlp_workspace_bytes(int(R)), device=device, dtype=torch.uint8)
+
+
+def mlp_forward_raw(packed, precision, viewdirs, R, S, rays_o=None, rays_d=None, z=None, pts=None):
+    """Kernel launch only (no autograd): raw [R,S,4]."""
+    if pts is not None:
+        pts = _dense(pts, "pts").reshape(-1, 3)
+        (viewdirs,), pitch = _ray_views(viewdirs)
+        rays_o = rays_d = None
+    else:
+        (rays_o, rays_d, viewdirs), pitch = _ray_views(rays_o, rays_d, viewdirs)
+        z = _dense(z, "z", 2)
+    raw = torch.empty(R, S, 4, device=viewdirs.device, dtype=torch.float32)
+    ws = _workspace(R, viewdirs.device)
+    _lib.call("gbn_mlp_forward", _ptr(packed), PRECISION[precision], _ptr(rays_o), _ptr(rays_d), _ptr(viewdirs), pitch,
+              _ptr(z), _ptr(pts), R, S, _ptr(raw), _ptr(ws), _stream())
+    return raw, ws
+
+
+def mlp_forward_embedded_raw(packed, precision, emb):
+    emb = _dense(emb, "embedded", 2)
+    if emb.shape[1] != 90:
+        raise ValueError(f"embedded input must be [P, 90], got {tuple(emb.shape)}")
+    P = emb.shape[0]
+    raw = torch.empty(P, 4, device=emb.device, dtype=torch.float32)
+    ws = _workspace(P, emb.device)
+    _lib.call("gbn_mlp_forward_embedded", _ptr(packed), PRECISION[precision], _ptr(emb), P, _ptr(raw), _ptr(ws), _stream())
+    return raw, ws
+
+
+def mlp_error_code(ws):
+    """Watchdog word of the last launch that used this workspace (0 = clean); synchronises."""
+    return int(ws[:4].view(torch.int32).item())
+
+
+def torch_posenc(x, n_freqs):
+    parts = [x]
+    for k in range(n_freqs):
+        parts += [torch.sin(x * float(2 ** k)), torch.cos(x * float(2 ** k))]
+    return torch.cat(parts, -1)
+
+
+def _torch_mlp(params, emb):
+    """Differentiable restatement used ONLY to obtain parameter gradients in backward (cuBLAS GEMMs)."""
+    W = lambda i: params[2 * i]
+    b = lambda i: params[2 * i + 1]
+    x_pts, x_dir = emb[:, :63], emb[:, 63:]
+    h = x_pts
+    for i in range(8):
+        h = torch.relu(torch.addmm(b(i), h, W(i).t()))
+        if i == 4:
+            h = torch.cat([x_pts, h], -1)
+    sigma = torch.addmm(b(9), h, W(9).t())
+    feat = torch.addmm(b(8), h, W(8).t())
+    hv = torch.relu(torch.addmm(b(10), torch.cat([feat, x_dir], -1), W(10).t()))
+    return torch.cat([torch.addmm(b(11), hv, W(11).t()), sigma], -1)
+
+
+class _Mlp(torch.autograd.Function):
+    """raw = NeRF(embed(o + d z), embed(viewdir)).  Forward: the fused tcgen05 kernel.
+
+    Backward (interim, round 1): parameter gradients by recomputation through cuBLAS GEMMs on the device —
+    library code, to be replaced by the tcgen05 dgrad/wgrad kernels.  Inputs carry no gradient, exactly as in
+    the reference where z_samples is detached and rays are data (run.py:2346).
+    """
+
+    @staticmethod
+    def forward(ctx, module, mode, a0, a1, a2, a3, *params):
+        packed = module.packed_weights()
+        if mode == "rays":
+            rays_o, rays_d, viewdirs, z = a0, a1, a2, a3
+            R, S = z.shape
+            raw, ws = mlp_forward_raw(packed, module.precision, viewdirs, R, S, rays_o=rays_o, rays_d=rays_d, z=z)
+        elif mode == "pts":
+            pts, viewdirs = a0, a1
+            R, S = pts.shape[0], pts.shape[1]
+            raw, ws = mlp_forward_raw(packed, module.precision, viewdirs, R, S, pts=pts.contiguous())
+        else:
+            raw, ws = mlp_forward_embedded_raw(packed, module.precision, a0)
+        module.last_workspace = ws
+        ctx.mode = mode
+        ctx.save_for_backward(*[t for t in (a0, a1, a2, a3) if t is not None], *params)
+        ctx.n_in = sum(t is not None for t in (a0, a1, a2, a3))
+        return raw
+
+    @staticmethod
+    def backward(ctx, g_raw):
+        saved = ctx.saved_tensors
+        ins, params = saved[:ctx.n_in], saved[ctx.n_in:]
+        with torch.enable_grad():
+            ps = [p.detach().requires_grad_(True) for p in params]
+            if ctx.mode == "rays":
+                o, d, vd, z = ins
+                pts = o[:, None, :] + d[:, None, :] * z[:, :, None]
+                emb = torch.cat([torch_posenc(pts.reshape(-1, 3), 10),
+                                 torch_posenc(vd[:, None, :].expand(pts.shape).reshape(-1, 3), 4)], -1)
+            elif ctx.mode == "pts":
+                pts, vd = ins
+                emb = torch.cat([torch_posenc(pts.reshape(-1, 3), 10),
+                                 torch_posenc(vd[:, None, :].expand(pts.shape).reshape(-1, 3), 4)], -1)
+            else:
+                (emb,) = ins
+            out = _torch_mlp(ps, emb)
+            grads = torch.autograd.grad(out, ps, g_raw.reshape(out.shape))
+        return (None, None, None, None, None, None, *grads)
+
+
+def mlp_rays(module, rays_o, rays_d, viewdirs, z):
+    return _Mlp.apply(module, "rays", rays_o, rays_d, viewdirs, z, *module.param_list())
+
+
+def mlp_points(module, pts, viewdirs):
+    return _Mlp.apply(module, "pts", pts, viewdirs, None, None, *module.param_list())
+
+
+def mlp_embedded(module, emb):
+    return _Mlp.apply(module, "emb", emb, None, None, None, *module.param_list())
+
+
+# --------------------------------------------------------------------------------------------------------- #
+def loss_seed(rgb, rgb0, disp, target_rgb, target_disp, depth_lambda=0.1, global_rays=None):
+    """Fused img2mse terms: returns (loss[1], g_rgb, g_rgb0, g_disp) with means over the GLOBAL ray count."""
+    rgb, target_rgb = _dense(rgb, "rgb", 2), _dense(target_rgb, "target_rgb", 2)
+    rgb0 = _dense(rgb0, "rgb0", 2, allow_none=True)
+    disp = _dense(disp, "disp", 1, allow_none=True)
+    target_disp = _dense(target_disp, "target_disp", 1, allow_none=True)
+    R = rgb.shape[0]
+    dev = rgb.device
+    g_rgb = torch.empty_like(rgb)
+    g_rgb0 = torch.empty_like(rgb0) if rgb0 is not None else None
+    g_disp = torch.empty_like(disp) if disp is not None else None
+    loss = torch.zeros(1, device=dev)
+    _lib.call("gbn_loss_seed", _ptr(rgb), _ptr(rgb0), _ptr(disp), _ptr(target_rgb), _ptr(target_disp), R,
+              int(global_rays or R), float(depth_lambda), _ptr(g_rgb), _ptr(g_rgb0), _ptr(g_disp), _ptr(loss), _stream())
+    return loss, g_rgb, g_rgb0, g_disp

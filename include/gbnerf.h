@@ -1,0 +1,127 @@
+/*
+ * gbnerf.h — C ABI of libgbnerf.so, the B200 (sm_100a) implementation of GB-NeRF's DS_NeRF
+ * volumetric-rendering hot path.
+ *
+ * This is the drop-in boundary: everything the reference computes with ATen ops inside
+ * run.py:render_rays / DS_NeRF/run_nerf_helpers.py is one of the entry points below.  The reference has no
+ * FFI of its own for this path (it is pure PyTorch); the binding a maintainer adds is the ctypes stub shown
+ * in INTEGRATION.md, and `gb-nerf_b200/_lib.py` is exactly that stub.
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers, int64 sizes, scalar flags, a cudaStream_t passed as void*.
+ *   - the caller owns every buffer (inputs, outputs, workspaces); the library only borrows them for the
+ *     duration of the enqueued work.  Nothing is allocated, freed or synchronised inside.
+ *   - all work is enqueued on `stream`; no default-stream use, no hidden syncs.
+ *   - every function returns 0 on success, else a GBN_E* code; gbn_last_error_string() describes the last
+ *     failure on the calling thread.  Nothing throws, nothing calls exit().
+ *   - fp32 tensors are dense row-major unless a stride argument says otherwise.  "ray_stride" is the row
+ *     pitch, in floats, of the reference's packed ray batch (run.py:1726-1736: [o(3) d(3) near far (depth)
+ *     viewdir(3)] -> 11 or 12), so views into that batch can be passed without a copy.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns GBN_ECUDA.
+ */
+#ifndef GBNERF_H_
+#define GBNERF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GBN_OK 0
+#define GBN_EINVAL 1       /* bad argument (null pointer, size, alignment, unsupported shape) */
+#define GBN_ECUDA 2        /* a CUDA runtime call / kernel launch failed */
+#define GBN_EUNSUPPORTED 3 /* valid request this build cannot serve */
+
+#define GBN_PRECISION_BF16 0 /* bf16 operands, fp32 accumulate (tcgen05 kind::f16)  */
+#define GBN_PRECISION_TF32 1 /* tf32 operands, fp32 accumulate (tcgen05 kind::tf32) */
+
+/* Network geometry fixed by the reference (run_nerf_helpers.py:75-104 with D=8, W=256, skips=[4],
+ * multires=10, multires_views=4, use_viewdirs=True). */
+#define GBN_PTS_CH 63
+#define GBN_DIR_CH 27
+#define GBN_EMB_CH 90
+#define GBN_WIDTH 256
+#define GBN_NUM_LINEAR 12 /* pts_linears.0-7, feature_linear, alpha_linear, views_linears.0, rgb_linear */
+#define GBN_PARAM_COUNT 595844
+
+int gbn_version(void);
+const char* gbn_last_error_string(void);
+
+/* ---- stratified depths: run.py:2291-2315 ---------------------------------------------------------------
+ * near/far: [R] with pitch ray_stride (floats).  t_rand: [R,S] uniform [0,1) or NULL (perturb == 0).
+ * z out: [R,S].  lindisp != 0 samples linearly in inverse depth. */
+int gbn_zvals_stratified(const float* near, const float* far, int64_t ray_stride, int64_t R, int S,
+                         int lindisp, const float* t_rand, float* z, void* stream);
+
+/* ---- standalone positional encoding: Embedder.embed (run_nerf_helpers.py:23-53) + run_network's
+ * concatenation (run.py:1640-1647).  pts = o + d*z per sample, dirs broadcast along the ray.
+ * out: [R*S, 90] fp32 = [pts(3) sin/cos x10 | dir(3) sin/cos x4].  Measurement / test entry point — the
+ * MLP kernel fuses this stage and never materialises the tensor. */
+int gbn_encode_points(const float* rays_o, const float* rays_d, const float* viewdirs, int64_t ray_stride,
+                      const float* z, int64_t R, int S, float* out, void* stream);
+
+/* ---- alpha compositing: raw2outputs (run_nerf_helpers.py:352-406) ---------------------------------------
+ * raw [R,S,4], z [R,S], rays_d [R] x3 with pitch ray_stride, noise [R,S] (already scaled by raw_noise_std) or
+ * NULL.  Outputs rgb [R,3], disp [R], acc [R], depth [R], weights [R,S], alpha [R,S] or NULL. */
+int gbn_composite_forward(const float* raw, const float* z, const float* rays_d, int64_t ray_stride,
+                          const float* noise, int64_t R, int S, int white_bkgd, float* rgb, float* disp,
+                          float* acc, float* depth, float* weights, float* alpha, void* stream);
+
+/* Backward of the above.  g_weights [R,S] may be NULL.  The forward is recomputed
+ * from raw/z, nothing else is read.  g_raw out: [R,S,4]. */
+int gbn_composite_backward(const float* raw, const float* z, const float* rays_d, int64_t ray_stride,
+                           const float* noise, int64_t R, int S, int white_bkgd, int detach_weights,
+                           const float* g_rgb, const float* g_disp, const float* g_acc, const float* g_depth,
+                           const float* g_weights, float* g_raw, void* stream);
+
+/* ---- inverse-CDF sampling: sample_pdf (run_nerf_helpers.py:306-349) --------------------------------------
+ * bins [R,B], weights [R,B-1], u [R,N] or NULL (deterministic linspace(0,1,N)).  samples out [R,N]. */
+int gbn_sample_pdf(const float* bins, const float* weights, const float* u, int64_t R, int B, int N,
+                   float* samples, void* stream);
+
+/* The search on its own, for the bit-exact index test: inds[r,n] = #{j : cdf[r,j] <= u[r,n]}
+ * == torch.searchsorted(cdf, u, right=True) (run_nerf_helpers.py:333).  inds out: int64 [R,N]. */
+int gbn_searchsorted_right(const float* cdf, const float* u, int64_t R, int B, int N, int64_t* inds,
+                           void* stream);
+
+/* Fused hierarchical step of render_rays (run.py:2343-2348, 2370): z_mid, sample_pdf on weights[:,1:-1],
+ * sort-merge with the coarse depths, std of the new samples.
+ * z_vals [R,S] ascending, weights [R,S], u [R,N] or NULL.  Outputs: z_samples [R,N] (may be NULL),
+ * z_merged [R,S+N] ascending, z_std [R] (may be NULL). */
+int gbn_sample_pdf_merge(const float* z_vals, const float* weights, const float* u, int64_t R, int S, int N,
+                         float* z_samples, float* z_merged, float* z_std, void* stream);
+
+/* ---- the 8x256 NeRF MLP: NeRF.forward (run_nerf_helpers.py:106-129) --------------------------------------
+ * Weights are re-laid-out once per optimiser step into the kernel's shared-memory image
+ * (UMMA K-major, 128-byte swizzle, K padded to 64) — `params` is a HOST array of 24 DEVICE pointers in the
+ * order weight,bias of: pts_linears.0 … pts_linears.7, feature_linear, alpha_linear, views_linears.0,
+ * rgb_linear (nn.Linear layout: weight [out,in] row-major fp32). */
+size_t gbn_mlp_packed_bytes(int precision);
+int gbn_mlp_prepack_weights(const void* const* params, void* packed, int precision, void* stream);
+
+/* Fused point generation + positional encoding + MLP.  Row p = r*S + s evaluates the point
+ * o_r + d_r * z[r,s] with view direction viewdirs_r.  If `pts` is non-NULL it is a dense [R*S,3] tensor
+ * used instead of o + d*z (network_query_fn's general form, run.py:2059-2062).  raw out: [R*S,4] fp32 =
+ * (r,g,b,sigma_raw).  workspace: gbn_mlp_workspace_bytes(R) bytes. */
+size_t gbn_mlp_workspace_bytes(int64_t R);
+int gbn_mlp_forward(const void* packed, int precision, const float* rays_o, const float* rays_d,
+                    const float* viewdirs, int64_t ray_stride, const float* z, const float* pts, int64_t R,
+                    int S, float* raw, void* workspace, void* stream);
+
+/* Same network on pre-embedded rows (NeRF.forward's own signature): emb [P,90] fp32 -> raw [P,4]. */
+int gbn_mlp_forward_embedded(const void* packed, int precision, const float* emb, int64_t P, float* raw,
+                             void* workspace, void* stream);
+
+/* ---- loss seed: img2mse terms of the training step (run.py:1483,1502,1513-1515) --------------------------
+ * loss = mean((rgb-t)^2) + mean((rgb0-t)^2) + depth_lambda*mean((disp-td)^2), means over R_global*3 / R_global.
+ * Writes the gradients wrt rgb, rgb0, disp and atomically accumulates the scalar loss into *loss. */
+int gbn_loss_seed(const float* rgb, const float* rgb0, const float* disp, const float* target_rgb,
+                  const float* target_disp, int64_t R, int64_t R_global, float depth_lambda, float* g_rgb,
+                  float* g_rgb0, float* g_disp, float* loss, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GBNERF_H_ */

@@ -1,0 +1,96 @@
+"""CPU: the C-ABI library builds, loads and exports exactly what include/gbnerf.h declares; host-side logic that
+needs no GPU (layout plan, argument validation, the no-fallback rule)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "gbnerf.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    ge._load_builder().build()
+    from gbnerf_b200 import _lib
+    return _lib
+
+
+def header_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gbn_\w+)\s*\(", src)))
+
+
+def test_header_and_binding_agree(lib):
+    names = header_functions()
+    assert len(names) >= 15
+    assert sorted(lib.SIGNATURES) == names
+    so = ctypes.CDLL(lib.LIB_PATH)
+    for n in names:
+        assert hasattr(so, n), f"{n} declared in gbnerf.h but not exported"
+
+
+def test_exports_are_plain_c(lib):
+    out = subprocess.check_output(["nm", "-D", "--defined-only", lib.LIB_PATH], text=True)
+    exported = [l.split()[-1] for l in out.splitlines() if " T " in l]
+    gbn = [e for e in exported if e.startswith("gbn_")]
+    assert sorted(gbn) == header_functions()
+
+
+def test_version_and_sizes(lib):
+    l = lib.load()
+    assert l.gbn_version() == 100
+    bf16, tf32 = l.gbn_mlp_packed_bytes(0), l.gbn_mlp_packed_bytes(1)
+    # 593,408 weights padded to the UMMA tiling: K 63->64, 319->64+256, alpha/rgb N->16, views K 283->256 (+fp32 dir part)
+    assert 1_190_000 < bf16 < 1_300_000 and 2_380_000 < tf32 < 2_600_000
+    assert bf16 % 256 == 0 and tf32 % 256 == 0
+    assert l.gbn_mlp_packed_bytes(7) == 0
+    assert l.gbn_mlp_workspace_bytes(10) == 256 + 10 * 128 * 4
+
+
+def test_sm100a_tensor_core_sass(lib):
+    """The MLP kernel must be a tcgen05 kernel: UTC*MMA + LDTM + UBLKCP in the SASS, no legacy HMMA."""
+    sass = subprocess.check_output(["cuobjdump", "-sass", lib.LIB_PATH], text=True)
+    assert "sm_100a" in sass
+    assert re.search(r"\bUTCHMMA\b", sass), "no tcgen05.mma (UTCHMMA) in SASS"
+    assert re.search(r"\bLDTM\b", sass), "no tcgen05.ld (LDTM) in SASS"
+    assert re.search(r"\bUBLKCP\b", sass), "no bulk TMA (UBLKCP) in SASS"
+    assert not re.search(r"\bHMMA\b", sass)
+
+
+def test_no_cpu_fallback(lib):
+    """Operators refuse CPU tensors; without a GPU compute entry points report a CUDA error, never a result."""
+    from gbnerf_b200 import ops
+    with pytest.raises(ValueError):
+        ops.composite(torch.zeros(2, 4, 4), torch.zeros(2, 4), torch.zeros(2, 3))
+    with pytest.raises(ValueError):
+        ops.sample_pdf(torch.zeros(2, 5), torch.zeros(2, 4), 8)
+    if not torch.cuda.is_available():
+        buf = (ctypes.c_float * 64)()
+        p = ctypes.cast(buf, ctypes.c_void_p)
+        with pytest.raises(lib.GbnError):
+            lib.call("gbn_zvals_stratified", p, p, 1, 4, 4, 0, None, p, None)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "gb-nerf_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "nerf_oracle" not in src, f
+
+
+def test_argument_validation(lib):
+    l = lib.load()
+    assert l.gbn_zvals_stratified(None, None, 1, 4, 4, 0, None, None, None) == 1   # GBN_EINVAL
+    assert b"null" in l.gbn_last_error_string()
+    assert l.gbn_sample_pdf_merge(None, None, None, 4, 2, 4, None, None, None, None) == 1
+    assert l.gbn_mlp_forward(None, 5, None, None, None, 3, None, None, 4, 4, None, None, None) == 1
+    assert l.gbn_composite_forward(None, None, None, 3, None, 0, 64, 1, None, None, None, None, None, None, None) == 0
