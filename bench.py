@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""Benchmark of the DS_NeRF render hot path (BASELINE.json: rays/s, coarse 64 + fine 64 samples).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|tf32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A step = one full-frame inference render (1008x756 SPIn-NeRF images_4 shape = 762,048 rays, chunk 32,768,
+coarse 64 + fine 64 samples, aconfig_1 test kwargs) per GPU through `gbnerf_b200.render`.  With N ranks each
+rank renders its own contiguous block of an N-frame ray set (weak scaling: rays are independent) and
+the 24 B/ray image outputs are gathered on rank 0 inside the timed region.
+
+One JSON line is printed by rank 0; see DESIGN.md §Measurement for every key.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, FOCAL, NEAR, FAR = 756, 1008, 815.0, 1.2, 8.0
+N_SAMPLES, N_IMPORTANCE, CHUNK = 64, 64, 32768
+FLOP_PER_POINT = 1186816                      # 593,408 MAC per point, unpadded
+POINTS_PER_RAY = N_SAMPLES + (N_SAMPLES + N_IMPORTANCE)
+METRIC = "rays/sec (coarse64+fine64) full-frame inference render"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], None, set(), []
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1]); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------------- #
+def synthetic_frame_rays(n_frames_offset=0):
+    """SURVEY §8d synthetic LLFF-shaped frame: get_rays(756, 1008, 815, [I | t]); returns host [2, R, 3]."""
+    c2w = torch.zeros(3, 4)
+    c2w[:, :3] = torch.eye(3)
+    c2w[:, 3] = torch.tensor([0.1 + 0.01 * n_frames_offset, -0.05, 0.2])
+    i = torch.linspace(0, W - 1, W)[None, :].expand(H, W)
+    j = torch.linspace(0, H - 1, H)[:, None].expand(H, W)
+    dirs = torch.stack([(i - W * .5) / FOCAL, -(j - H * .5) / FOCAL, -torch.ones_like(i)], -1)
+    rays_d = torch.sum(dirs[..., None, :] * c2w[:3, :3], -1).reshape(-1, 3)
+    rays_o = c2w[:3, -1].expand(rays_d.shape)
+    return torch.stack([rays_o, rays_d], 0).contiguous()
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    import gbnerf_b200 as G
+    from gbnerf_b200 import _lib, ops
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    pk = peaks()
+
+    # model: random-init 8x256 coarse + fine nets in the reference's construction order (seed 0)
+    torch.manual_seed(0)
+    nets = []
+    for _ in range(2):
+        nets.append(G.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True,
+                           precision=args.precision).to(dev))
+    e10, _ = G.get_embedder(10, 0)
+    e4, _ = G.get_embedder(4, 0)
+    kw = dict(network_query_fn=G.NetworkQuery(e10, e4, 65536), perturb=False, N_importance=N_IMPORTANCE,
+              network_fine=nets[1], N_samples=N_SAMPLES, network_fn=nets[0], use_viewdirs=True, white_bkgd=True,
+              raw_noise_std=0., ndc=False, lindisp=True, near=NEAR, far=FAR)
+
+    rays_host = synthetic_frame_rays(rank).pin_memory()          # this rank's frame: [2, R, 3]
+    R = rays_host.shape[1]
+    if args.rays:
+        R = min(R, args.rays)
+        rays_host = rays_host[:, :R].contiguous().pin_memory()
+    rays_dev = rays_host.to(dev)
+    out_host = torch.empty(R, 6, pin_memory=True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def step_resident():
+        with torch.no_grad():
+            rgb, disp, acc, depth, _ = G.render(H, W, FOCAL, chunk=CHUNK, rays=rays_dev, **kw)
+            packed = torch.cat([rgb, disp[:, None], acc[:, None], depth[:, None]], 1)
+            if world > 1:
+                return G.dist.gather_rows(packed, R * world, dst=0)
+            return packed
+
+    def step_e2e():
+        with torch.no_grad():
+            r = rays_host.to(dev, non_blocking=True)
+            rgb, disp, acc, depth, _ = G.render(H, W, FOCAL, chunk=CHUNK, rays=r, **kw)
+            packed = torch.cat([rgb, disp[:, None], acc[:, None], depth[:, None]], 1)
+            out_host.copy_(packed, non_blocking=True)
+            return packed
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sample_clocks=False, kernel_events=False):
+        for _ in range(warmup):
+            fn()
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        barrier()
+        if sampler:
+            sampler.start()
+        if kernel_events:
+            ops.KERNEL_EVENTS = []
+        _lib.LAUNCHES = 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            flush.zero_()
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = _lib.LAUNCHES
+        events = ops.KERNEL_EVENTS
+        ops.KERNEL_EVENTS = None
+        clocks = sampler.stop() if sampler else None
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, launches, events, clocks
+
+    ms, launches, events, clocks = timed(step_resident, args.steps, args.warmup, sample_clocks=True, kernel_events=True)
+    rays_total = R * world * args.steps
+    value = rays_total / (ms * 1e-3)
+
+    # dominant kernel: the fused encode+MLP kernel, timed per launch with CUDA events inside the timed region
+    mlp_ms = [a.elapsed_time(b) for (name, a, b, pts) in events if name == "mlp"]
+    mlp_pts = sum(pts for (name, a, b, pts) in events if name == "mlp")
+    achieved = mlp_pts * FLOP_PER_POINT / (sum(mlp_ms) * 1e-3) / 1e12 if mlp_ms else None
+    peak = pk["bf16_tflops_sustained"]
+    roofline = {"kernel": f"nerf_mlp_kernel<{args.precision}> (fused point generation + posenc + 8x256 MLP)",
+                "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak if achieved else None, "peak_source": pk["source"] + " bf16 sustained",
+                "traffic": None, "launches_timed": len(mlp_ms), "avg_launch_ms": sum(mlp_ms) / max(1, len(mlp_ms)),
+                "share_of_step": sum(mlp_ms) / ms if mlp_ms else None,
+                "flop_per_launch": mlp_pts * FLOP_PER_POINT / max(1, len(mlp_ms))}
+
+    e2e_steps = max(2, min(args.steps, 5))
+    ms_e2e, _, _, _ = timed(step_e2e, e2e_steps, 1)
+    e2e = {"value": R * world * e2e_steps / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": R * 6 * 4,
+           "d2h_bytes_per_step": R * 6 * 4, "api": "gbnerf_b200.render(H, W, focal, chunk, rays=<pinned host>)"}
+
+    cpu = cpu_baseline(bounded_s=20.0) if rank == 0 and world == 1 and not args.no_cpu else None
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+                "config": {"workload": "full-frame inference render 1008x756 (762,048 rays/GPU), coarse 64 + fine 64, "
+                                       "chunk 32768, lindisp, white_bkgd, viewdirs, random-init 8x256 MLPs (seed 0)",
+                           "rays_per_gpu": R, "parallelism": f"ray-sharded x{world}",
+                           "l2": "256 MiB memset between steps (inside the timed region)"},
+                "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------------- #
+def cpu_render(n_rays, threads=None):
+    """The oracle port of the reference render_rays on the host cores; returns seconds for one pass."""
+    from oracle import nerf_oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    rays2 = synthetic_frame_rays(0)
+    g = torch.Generator().manual_seed(1)
+    idx = torch.randint(0, H * W, (n_rays,), generator=g)
+    o, d = rays2[0, idx], rays2[1, idx]
+    rays = O.pack_rays(o, d, NEAR, FAR)
+    torch.manual_seed(0)
+    pc, pf = O.init_params(0), O.init_params(None)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        O.render(rays, chunk=CHUNK, p_coarse=pc, p_fine=pf, n_samples=N_SAMPLES, n_importance=N_IMPORTANCE,
+                 lindisp=True, white_bkgd=True)
+        return time.perf_counter() - t0
+
+
+def cpu_baseline(bounded_s=20.0, n_rays=1024):
+    threads = torch.get_num_threads()
+    cpu_render(256)                      # warm-up
+    best, spent = None, 0.0
+    for _ in range(3):
+        dt = cpu_render(n_rays)
+        spent += dt
+        best = dt if best is None else min(best, dt)
+        if spent > bounded_s:
+            break
+    return {"value": n_rays / best, "unit": "rays/s", "cores": threads, "kind": "port",
+            "sample": f"{n_rays} random pixels of the same frame, same kwargs, oracle/nerf_oracle.py (torch CPU fp32), "
+                      f"best of 3", "host_cpu_count": os.cpu_count()}
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path (its PyTorch code cannot travel to the GPU box, so the
+    oracle port — pinned to it by tests/golden — is what runs), all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    n_rays = 1024
+    threads = torch.get_num_threads()
+    for _ in range(args.warmup):
+        cpu_render(n_rays)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_render(n_rays)
+    dt = time.perf_counter() - t0
+    v = n_rays * args.steps / dt
+    sample = f"{n_rays} random pixels of the 1008x756 frame per step (bounded sample of the same workload)"
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "full-frame inference render 1008x756, coarse 64 + fine 64 (bounded sample)",
+                       "rays_per_step": n_rays},
+            "cpu_baseline": {"value": v, "unit": "rays/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"])
+    ap.add_argument("--rays", type=int, default=0, help="debug: cap rays per GPU")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -32,6 +32,10 @@ SIGNATURES = {
     "gbn_loss_seed": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _f, _p, _p, _p, _p, _p]),
 }
 
+# kernels each entry point enqueues (bench.py reports the sum over its timed region as gpu_launches)
+KERNELS_PER_CALL = {"gbn_mlp_forward": 2, "gbn_mlp_forward_embedded": 2}
+LAUNCHES = 0
+
 _lib = None
 
 
@@ -57,8 +61,10 @@ def load():
 
 def call(name, *args):
     """Invoke an int-returning entry point and raise on a non-zero code."""
+    global LAUNCHES
     lib = load()
     rc = getattr(lib, name)(*args)
+    LAUNCHES += KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         msg = lib.gbn_last_error_string().decode(errors="replace")
         if rc == 1:

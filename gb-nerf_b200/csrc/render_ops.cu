@@ -593,6 +593,11 @@ extern "C" int gbn_searchsorted_right(const float* cdf, const float* u, int64_t 
   GBN_REQUIRE(cdf && u && inds, "searchsorted_right: null pointer");
   GBN_REQUIRE(R >= 0 && B >= 1 && N >= 1 && B <= 4096, "searchsorted_right: bad sizes B=%d N=%d", B, N);
   const size_t smem = (size_t)kWarpsPerBlock * B * sizeof(float);
+  static bool attr_set = false;  // immutable kernel attribute, set once
+  if (!attr_set) {
+    GBN_CUDA(cudaFuncSetAttribute(searchsorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
   searchsorted_kernel<<<persistent_grid(R, 4), kThreads, smem, (cudaStream_t)stream>>>(cdf, u, R, B, N, inds);
   return check_launch("searchsorted_kernel");
 }
@@ -603,6 +608,11 @@ extern "C" int gbn_sample_pdf(const float* bins, const float* weights, const flo
   GBN_REQUIRE(bins && weights && samples, "sample_pdf: null pointer");
   GBN_REQUIRE(R >= 0 && B >= 2 && N >= 1 && B <= 2048, "sample_pdf: bad sizes B=%d N=%d", B, N);
   const size_t smem = (size_t)kWarpsPerBlock * 2 * B * sizeof(float);
+  static bool attr_set = false;  // immutable kernel attribute, set once
+  if (!attr_set) {
+    GBN_CUDA(cudaFuncSetAttribute(sample_pdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
   sample_pdf_kernel<<<persistent_grid(R, 4), kThreads, smem, (cudaStream_t)stream>>>(bins, weights, u, R, B, N, samples);
   return check_launch("sample_pdf_kernel");
 }

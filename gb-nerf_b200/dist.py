@@ -107,7 +107,7 @@ def gather_rows(local, total_rows, dst=0):
 
 
 def render_sharded(render_fn, rays_flat, gather_keys=("rgb_map", "disp_map", "acc_map", "depth_map"), dst=0, **kw):
-    """Render this rank's block of ``rays_flat`` with ``render_fn`` (= render.batchify_rays) and gather the
+    """Render this rank's block of ``rays_flat`` with ``render_fn`` (= run.batchify_rays) and gather the
     image outputs packed as one [R, 6] tensor (24 B/ray: rgb(3), disp, acc, depth) on ``dst``."""
     rank, ws = world()
     mine = shard_rays(rays_flat, rank, ws)

@@ -13,6 +13,28 @@ from . import _lib
 from ._lib import PRECISION
 
 
+# bench.py sets this to a list to collect (name, start_event, end_event, points) per MLP launch, recorded on
+# the launching stream; None (the default) records nothing
+KERNEL_EVENTS = None
+
+
+class _timed_launch:
+    def __init__(self, name, units):
+        self.name, self.units = name, units
+
+    def __enter__(self):
+        if KERNEL_EVENTS is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record(torch.cuda.current_stream())
+
+    def __exit__(self, *exc):
+        if KERNEL_EVENTS is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record(torch.cuda.current_stream())
+            KERNEL_EVENTS.append((self.name, self.e0, e1, self.units))
+        return False
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -216,8 +238,9 @@ def mlp_forward_raw(packed, precision, viewdirs, R, S, rays_o=None, rays_d=None,
         z = _dense(z, "z", 2)
     raw = torch.empty(R, S, 4, device=viewdirs.device, dtype=torch.float32)
     ws = _workspace(R, viewdirs.device)
-    _lib.call("gbn_mlp_forward", _ptr(packed), PRECISION[precision], _ptr(rays_o), _ptr(rays_d), _ptr(viewdirs), pitch,
-              _ptr(z), _ptr(pts), R, S, _ptr(raw), _ptr(ws), _stream())
+    with _timed_launch("mlp", R * S):
+        _lib.call("gbn_mlp_forward", _ptr(packed), PRECISION[precision], _ptr(rays_o), _ptr(rays_d), _ptr(viewdirs),
+                  pitch, _ptr(z), _ptr(pts), R, S, _ptr(raw), _ptr(ws), _stream())
     return raw, ws
 
 
