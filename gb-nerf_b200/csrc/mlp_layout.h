@@ -1,5 +1,6 @@
 // Layout shared by the weight pre-packer and the tcgen05 MLP kernel: the per-tile list of tensor-core jobs
-// (one K-block of one layer against one 128-row half of its weight matrix) and the packed weight image.
+// (one K-block of one layer against an N-row slab of its weight matrix: all 256 rows in bf16, 128-row halves in
+// tf32 where a 256-row slab would not leave room for a ring) and the packed weight image.
 //
 // Network (run_nerf_helpers.py:75-129, D=8 W=256 skips=[4] use_viewdirs):
 //   unit 0..7  pts_linears.i   (unit 5 reads [pts-encoding | h], the skip concat of helpers:111-112)
@@ -32,7 +33,7 @@ struct MlpJob {         // consumed by the TMA producer and the MMA issuer
   uint8_t a_blk;        // activation K-block index, or kEncBlkFlag | encoding K-block index
   uint8_t flags;
   uint16_t d_col;       // TMEM column of the accumulator
-  uint8_t n8;           // N >> 3
+  uint8_t n16;          // N >> 4
   uint8_t unit;
   uint32_t pad;
 };
@@ -60,7 +61,7 @@ constexpr int kBiasFloats = 2312;
 
 struct MlpPlan {
   int precision;
-  int esz, kb, nblk, encb;           // element bytes, K-block elements, act K-blocks, enc K-blocks
+  int esz, kb, nblk, encb, nj;       // element bytes, K-block elements, act K-blocks, enc K-blocks, N per job
   std::vector<MlpJob> jobs;
   std::vector<PackJob> pack;
   int unit_begin[kNumUnits + 1];
@@ -74,6 +75,8 @@ inline MlpPlan make_plan(int precision) {
   p.kb = 128 / p.esz;
   p.nblk = 256 / p.kb;
   p.encb = 64 / p.kb;
+  p.nj = precision == 0 ? 256 : 128;
+  const int nh = 256 / p.nj;
   uint32_t off = 256;  // header
   auto add = [&](int unit, int layer, int ld, int row0, int rows_valid, int rows, int col0, int cols_valid,
                  uint8_t a_blk, uint8_t flags, uint32_t d_col) {
@@ -83,7 +86,7 @@ inline MlpPlan make_plan(int precision) {
     j.a_blk = a_blk;
     j.flags = flags;
     j.d_col = (uint16_t)d_col;
-    j.n8 = (uint8_t)(rows / 8);
+    j.n16 = (uint8_t)(rows / 16);
     j.unit = (uint8_t)unit;
     p.jobs.push_back(j);
     PackJob q{};
@@ -104,25 +107,26 @@ inline MlpPlan make_plan(int precision) {
     const uint32_t dX = (u % 2 == 0) ? kColX : kColY;
     if (u == 0) {
       for (int e = 0; e < p.encb; ++e)
-        for (int h = 0; h < 2; ++h)
-          add(u, 0, 63, h * 128, 128, 128, e * p.kb, clampc(e * p.kb, 63), kEncBlkFlag | e,
-              (uint8_t)((e == 0 && h == 0 ? JF_WAIT_ENC : 0) | (e == 0 ? JF_FIRST : 0)), dX + h * 128);
+        for (int h = 0; h < nh; ++h)
+          add(u, 0, 63, h * p.nj, p.nj, p.nj, e * p.kb, clampc(e * p.kb, 63), kEncBlkFlag | e,
+              (uint8_t)((e == 0 && h == 0 ? JF_WAIT_ENC : 0) | (e == 0 ? JF_FIRST : 0)), dX + h * p.nj);
     } else if (u <= 7) {
       const int ld = (u == 5) ? 319 : 256, hoff = (u == 5) ? 63 : 0;
       if (u == 5)
         for (int e = 0; e < p.encb; ++e)
-          for (int h = 0; h < 2; ++h)
-            add(u, u, ld, h * 128, 128, 128, e * p.kb, clampc(e * p.kb, 63), kEncBlkFlag | e,
-                (uint8_t)((e == 0 ? JF_FIRST : 0) | (e == p.encb - 1 && h == 1 ? JF_COMMIT_ENC : 0)), dX + h * 128);
+          for (int h = 0; h < nh; ++h)
+            add(u, u, ld, h * p.nj, p.nj, p.nj, e * p.kb, clampc(e * p.kb, 63), kEncBlkFlag | e,
+                (uint8_t)((e == 0 ? JF_FIRST : 0) | (e == p.encb - 1 && h == nh - 1 ? JF_COMMIT_ENC : 0)),
+                dX + h * p.nj);
       for (int k = 0; k < p.nblk; ++k)
-        for (int h = 0; h < 2; ++h)
-          add(u, u, ld, h * 128, 128, 128, hoff + k * p.kb, p.kb, (uint8_t)k,
-              (uint8_t)((h == 0 ? JF_WAIT_ACT : 0) | ((k == 0 && u != 5) ? JF_FIRST : 0)), dX + h * 128);
+        for (int h = 0; h < nh; ++h)
+          add(u, u, ld, h * p.nj, p.nj, p.nj, hoff + k * p.kb, p.kb, (uint8_t)k,
+              (uint8_t)((h == 0 ? JF_WAIT_ACT : 0) | ((k == 0 && u != 5) ? JF_FIRST : 0)), dX + h * p.nj);
     } else if (u == 8) {
       for (int k = 0; k < p.nblk; ++k)
-        for (int h = 0; h < 2; ++h)
-          add(u, LIN_FEATURE, 256, h * 128, 128, 128, k * p.kb, p.kb, (uint8_t)k,
-              (uint8_t)((h == 0 ? JF_WAIT_ACT : 0) | (k == 0 ? JF_FIRST : 0)), kColX + h * 128);
+        for (int h = 0; h < nh; ++h)
+          add(u, LIN_FEATURE, 256, h * p.nj, p.nj, p.nj, k * p.kb, p.kb, (uint8_t)k,
+              (uint8_t)((h == 0 ? JF_WAIT_ACT : 0) | (k == 0 ? JF_FIRST : 0)), kColX + h * p.nj);
       for (int k = 0; k < p.nblk; ++k)
         add(u, LIN_ALPHA, 256, 0, 1, 16, k * p.kb, p.kb, (uint8_t)k, (uint8_t)(k == 0 ? JF_FIRST : 0), kColAlpha);
     } else if (u == 9) {

@@ -32,17 +32,16 @@ template <int PREC>
 struct Cfg;
 template <>
 struct Cfg<GBN_PRECISION_BF16> {
-  static constexpr int ESZ = 2, KB = 64, NBLK = 4, ENCB = 1, NST = 8;
+  static constexpr int ESZ = 2, KB = 64, NBLK = 4, ENCB = 1, NST = 4, STAGE = 32768;
   static constexpr uint32_t FMT = 1;
 };
 template <>
 struct Cfg<GBN_PRECISION_TF32> {
-  static constexpr int ESZ = 4, KB = 32, NBLK = 8, ENCB = 2, NST = 3;
+  static constexpr int ESZ = 4, KB = 32, NBLK = 8, ENCB = 2, NST = 3, STAGE = 16384;
   static constexpr uint32_t FMT = 2;
 };
 
 constexpr int kThreadsMlp = 512;
-constexpr int kStageBytes = 16384;
 
 template <int PREC>
 struct Smem {
@@ -50,7 +49,7 @@ struct Smem {
   static constexpr uint32_t act = 0;
   static constexpr uint32_t enc = act + C::NBLK * kBlkBytes;
   static constexpr uint32_t ring = enc + C::ENCB * kBlkBytes;
-  static constexpr uint32_t bias = ring + C::NST * kStageBytes;
+  static constexpr uint32_t bias = ring + C::NST * C::STAGE;
   static constexpr uint32_t bars = bias + kBiasFloats * 4;
   // barrier slots (8 B each)
   static constexpr uint32_t w_full = bars;
@@ -74,6 +73,8 @@ struct MlpArgs {
   const float* view_bias;             // [P / S, 128] fp32
   float* raw;                         // [P,4]
   int* err;
+  unsigned long long* trace;          // optional clock64 trace of CTA 0 (gbn_mlp_set_trace), else nullptr
+  int trace_tile;
   int64_t stride;
   int64_t P;
   int S;
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) nerf_mlp_kernel(const MlpArgs 
   if (threadIdx.x == 0) {
     for (int i = 0; i < C::NST; ++i) { mbar_init(base + L::w_full + 8 * i, 1); mbar_init(base + L::w_empty + 8 * i, 1); }
     for (int i = 0; i < kNumUnits; ++i) mbar_init(base + L::acc_full + 8 * i, 1);
-    for (int i = 0; i < C::NBLK; ++i) mbar_init(base + L::act_ready + 8 * i, 128);
+    for (int i = 0; i < C::NBLK; ++i) mbar_init(base + L::act_ready + 8 * i, C::KB == 64 ? 256 : 128);
     mbar_init(base + L::enc_full, 128);
     mbar_init(base + L::enc_empty, 1);
     *reinterpret_cast<volatile uint32_t*>(gen + L::abort_flag) = 0;
@@ -154,65 +155,84 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) nerf_mlp_kernel(const MlpArgs 
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + L::tmem_ptr);
 
   if (warp == 0) {
-    // =============================== weight producer (one thread) ========================================
-    if (lane == 0) {
-      uint32_t cnt = 0;
-      auto emit = [&](int u) {
-        for (int j = ub[u]; j < ub[u + 1]; ++j) {
-          const uint32_t s = cnt % C::NST, par = (cnt / C::NST) & 1;
-          wait_bar(base + L::w_empty + 8 * s, par ^ 1, abort_addr, a.err, 0x10000000 | j);
-          const uint32_t bytes = (uint32_t)jobs[j].w_bytes16 * 16;
+    // =============================== weight producer (warp-uniform loop, one elected lane issues) =========
+    uint32_t cnt = 0;
+    auto emit = [&](int u, int t) {
+      unsigned long long* tr = (a.trace && blockIdx.x == 0 && t == a.trace_tile && lane == 0) ? a.trace + 640 : nullptr;
+      for (int j = ub[u]; j < ub[u + 1]; ++j) {
+        const uint32_t s = cnt % C::NST, par = (cnt / C::NST) & 1;
+        if (tr) tr[2 * j] = clock64();
+        wait_bar(base + L::w_empty + 8 * s, par ^ 1, abort_addr, a.err, 0x10000000 | j);
+        if (tr) tr[2 * j + 1] = clock64();
+        const uint32_t bytes = (uint32_t)jobs[j].w_bytes16 * 16;
+        const uint8_t* src = a.packed + jobs[j].w_off;
+        if (elect_one()) {
           mbar_expect_tx(base + L::w_full + 8 * s, bytes);
-          tma_bulk_g2s(base + L::ring + s * kStageBytes, a.packed + jobs[j].w_off, bytes, base + L::w_full + 8 * s);
-          ++cnt;
+          tma_bulk_g2s(base + L::ring + s * C::STAGE, src, bytes, base + L::w_full + 8 * s);
         }
-      };
-      if (my_tiles > 0) emit(0);
-      for (int t = 0; t < my_tiles; ++t) {
-        for (int u = 1; u <= 9; ++u) emit(u);
-        if (t + 1 < my_tiles) emit(0);
-        emit(10);
+        __syncwarp();
+        ++cnt;
       }
+    };
+    if (my_tiles > 0) emit(0, 0);
+    for (int t = 0; t < my_tiles; ++t) {
+      for (int u = 1; u <= 9; ++u) emit(u, t);
+      if (t + 1 < my_tiles) emit(0, t + 1);
+      emit(10, t);
     }
   } else if (warp == 1) {
-    // =============================== MMA issuer (one thread) =============================================
-    if (lane == 0) {
-      uint32_t cnt = 0, act_par = 0;
-      auto issue = [&](int u, int t) {
-        for (int j = ub[u]; j < ub[u + 1]; ++j) {
-          const MlpJob jb = jobs[j];
-          if (jb.flags & JF_WAIT_ENC) wait_bar(base + L::enc_full, t & 1, abort_addr, a.err, 0x20000000 | j);
-          if (jb.flags & JF_WAIT_ACT) {
-            wait_bar(base + L::act_ready + 8 * jb.a_blk, (act_par >> jb.a_blk) & 1, abort_addr, a.err, 0x21000000 | j);
-            act_par ^= 1u << jb.a_blk;
-          }
-          const uint32_t s = cnt % C::NST, par = (cnt / C::NST) & 1;
-          wait_bar(base + L::w_full + 8 * s, par, abort_addr, a.err, 0x22000000 | j);
-          tc_fence_after_sync();
-          const uint32_t a_addr = (jb.a_blk & kEncBlkFlag) ? base + L::enc + (jb.a_blk & 0x7f) * kBlkBytes
-                                                           : base + L::act + jb.a_blk * kBlkBytes;
-          const uint64_t adesc = smem_desc_sw128(a_addr);
-          const uint64_t bdesc = smem_desc_sw128(base + L::ring + s * kStageBytes);
-          const uint32_t idesc = make_idesc(C::FMT, 128, (uint32_t)jb.n8 * 8);
-          const uint32_t d = tmem + jb.d_col;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t accum = ((jb.flags & JF_FIRST) && k == 0) ? 0u : 1u;
-            if constexpr (PREC == GBN_PRECISION_BF16) umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
-            else umma_tf32(d, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+    // =============================== MMA issuer =============================================================
+    // The whole warp walks the job list (warp-uniform control flow, so descriptors live in uniform registers and
+    // UTCHMMA issues without a divergence waterfall); one elected lane issues the MMAs and commits.
+    uint32_t cnt = 0, act_par = 0;
+    auto issue = [&](int u, int t) {
+      unsigned long long* tr = (a.trace && blockIdx.x == 0 && t == a.trace_tile && lane == 0) ? a.trace : nullptr;
+      for (int j = ub[u]; j < ub[u + 1]; ++j) {
+        const MlpJob jb = jobs[j];
+        if (tr) tr[4 * j] = clock64();
+        if (jb.flags & JF_WAIT_ENC) wait_bar(base + L::enc_full, t & 1, abort_addr, a.err, 0x20000000 | j);
+        if (jb.flags & JF_WAIT_ACT) {
+          wait_bar(base + L::act_ready + 8 * jb.a_blk, (act_par >> jb.a_blk) & 1, abort_addr, a.err, 0x21000000 | j);
+          act_par ^= 1u << jb.a_blk;
+        }
+        const uint32_t s = cnt % C::NST, par = (cnt / C::NST) & 1;
+        if (tr) tr[4 * j + 1] = clock64();
+        wait_bar(base + L::w_full + 8 * s, par, abort_addr, a.err, 0x22000000 | j);
+        if (tr) tr[4 * j + 2] = clock64();
+        tc_fence_after_sync();
+        const uint32_t a_addr = (jb.a_blk & kEncBlkFlag) ? base + L::enc + (jb.a_blk & 0x7f) * kBlkBytes
+                                                         : base + L::act + jb.a_blk * kBlkBytes;
+        const uint64_t adesc = smem_desc_sw128(a_addr);
+        const uint64_t bdesc = smem_desc_sw128(base + L::ring + s * C::STAGE);
+        const uint32_t idesc = make_idesc(C::FMT, 128, (uint32_t)jb.n16 * 16);
+        const uint32_t d = tmem + jb.d_col;
+        const uint32_t first = (jb.flags & JF_FIRST) ? 0u : 1u;
+        if (elect_one()) {
+          if constexpr (PREC == GBN_PRECISION_BF16) {
+            umma_bf16(d, adesc, bdesc, idesc, first);
+            umma_bf16(d, adesc + 2, bdesc + 2, idesc, 1u);
+            umma_bf16(d, adesc + 4, bdesc + 4, idesc, 1u);
+            umma_bf16(d, adesc + 6, bdesc + 6, idesc, 1u);
+          } else {
+            umma_tf32(d, adesc, bdesc, idesc, first);
+            umma_tf32(d, adesc + 2, bdesc + 2, idesc, 1u);
+            umma_tf32(d, adesc + 4, bdesc + 4, idesc, 1u);
+            umma_tf32(d, adesc + 6, bdesc + 6, idesc, 1u);
           }
           umma_commit(base + L::w_empty + 8 * s);
           if (jb.flags & JF_COMMIT_ENC) umma_commit(base + L::enc_empty);
           if (jb.flags & JF_COMMIT_ACC) umma_commit(base + L::acc_full + 8 * jb.unit);
-          ++cnt;
         }
-      };
-      if (my_tiles > 0) issue(0, 0);
-      for (int t = 0; t < my_tiles; ++t) {
-        for (int u = 1; u <= 9; ++u) issue(u, t);
-        if (t + 1 < my_tiles) issue(0, t + 1);
-        issue(10, t);
+        __syncwarp();
+        if (tr) tr[4 * j + 3] = clock64();
+        ++cnt;
       }
+    };
+    if (my_tiles > 0) issue(0, 0);
+    for (int t = 0; t < my_tiles; ++t) {
+      for (int u = 1; u <= 9; ++u) issue(u, t);
+      if (t + 1 < my_tiles) issue(0, t + 1);
+      issue(10, t);
     }
   } else if (warp >= 4 && warp < 8) {
     // =============================== encoders: thread == row of the next tile ============================
@@ -221,6 +241,8 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) nerf_mlp_kernel(const MlpArgs 
     for (int t = 0; t < my_tiles; ++t) {
       const int64_t tile = blockIdx.x + (int64_t)t * gridDim.x;
       const int64_t p = tile * kTileRows + row;
+      unsigned long long* tr = (a.trace && blockIdx.x == 0 && t == a.trace_tile && row == 0) ? a.trace + 1216 : nullptr;
+      if (tr) tr[0] = clock64();
       float e[64];
       if (p < a.P) {
         if (a.emb != nullptr) {
@@ -252,7 +274,9 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) nerf_mlp_kernel(const MlpArgs 
 #pragma unroll
         for (int i = 0; i < 64; ++i) e[i] = 0.f;
       }
+      if (tr) tr[1] = clock64();
       if (t > 0) wait_bar(base + L::enc_empty, (t - 1) & 1, abort_addr, a.err, 0x30000000 | t);
+      if (tr) tr[2] = clock64();
       // 64 channels: bf16 -> one K-block (8 chunks); tf32 -> two K-blocks (8 chunks each)
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
@@ -266,6 +290,7 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) nerf_mlp_kernel(const MlpArgs 
       }
       fence_proxy_async_smem();
       mbar_arrive(base + L::enc_full);
+      if (tr) tr[3] = clock64();
     }
   } else if (warp >= 8) {
     // =============================== epilogue: thread == row, two warpgroups split the K-blocks ==========
@@ -280,8 +305,12 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) nerf_mlp_kernel(const MlpArgs 
       const int64_t p = tile * kTileRows + row;
       const uint32_t par = t & 1;
       float sigma_acc = 0.f;
+      unsigned long long* tr = (a.trace && blockIdx.x == 0 && t == a.trace_tile && (threadIdx.x & 127) == 0)
+                                   ? a.trace + 960 + wg * 128 : nullptr;
       for (int u = 0; u <= 9; ++u) {
+        if (tr) tr[u * 10] = clock64();
         wait_bar(base + L::acc_full + 8 * u, par, abort_addr, a.err, 0x40000000 | (u << 8) | wg);
+        if (tr) tr[u * 10 + 1] = clock64();
         tc_fence_after_sync();
         const uint32_t col0 = (u & 1) ? kColY : kColX;
         const int nb = (u == 9) ? (128 / C::KB) : C::NBLK;
@@ -297,40 +326,43 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) nerf_mlp_kernel(const MlpArgs 
             sigma_acc = __uint_as_float(sv);
           }
         }
-        for (int b = wg; b < nb; b += 2) {
-          uint32_t v[GPB][32];
-#pragma unroll
-          for (int g = 0; g < GPB; ++g) tmem_ld32(lane_addr + col0 + b * C::KB + g * 32, v[g]);
+        // bf16: a K-block is 64 columns = two 32-column groups, one per warpgroup, so block 0 (what the next
+        // layer's first MMAs wait for) is ready after half the work; tf32: 32-column blocks alternate
+        for (int b = (GPB == 2 ? 0 : wg); b < nb; b += (GPB == 2 ? 1 : 2)) {
+          const int g = (GPB == 2) ? wg : 0;
+          const int c0 = b * C::KB + g * 32;
+          uint32_t v[32];
+          tmem_ld32(lane_addr + col0 + c0, v);
           tmem_ld_wait();
+          if (tr) tr[u * 10 + 2 + 2 * (GPB == 2 ? b : (b >> 1))] = clock64();
+          float f[32];
+          if (u == 9) {
 #pragma unroll
-          for (int g = 0; g < GPB; ++g) {
-            float f[32];
-            const int c0 = b * C::KB + g * 32;
-            if (u == 9) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(vb + c0 + i));
-                f[i] = __uint_as_float(v[g][i]) + bb.x; f[i + 1] = __uint_as_float(v[g][i + 1]) + bb.y;
-                f[i + 2] = __uint_as_float(v[g][i + 2]) + bb.z; f[i + 3] = __uint_as_float(v[g][i + 3]) + bb.w;
-              }
-            } else {
-              const float4* bp = reinterpret_cast<const float4*>(sbias + (u == 8 ? kBiasFeat : u * 256) + c0);
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                const float4 bb = bp[i >> 2];
-                f[i] = __uint_as_float(v[g][i]) + bb.x; f[i + 1] = __uint_as_float(v[g][i + 1]) + bb.y;
-                f[i + 2] = __uint_as_float(v[g][i + 2]) + bb.z; f[i + 3] = __uint_as_float(v[g][i + 3]) + bb.w;
-              }
+            for (int i = 0; i < 32; i += 4) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(vb + c0 + i));
+              f[i] = __uint_as_float(v[i]) + bb.x; f[i + 1] = __uint_as_float(v[i + 1]) + bb.y;
+              f[i + 2] = __uint_as_float(v[i + 2]) + bb.z; f[i + 3] = __uint_as_float(v[i + 3]) + bb.w;
             }
-            store_group32<PREC>(base + L::act + b * kBlkBytes + row_off, row, g * (GPB == 2 ? 4 : 0), f, relu);
+          } else {
+            const float4* bp = reinterpret_cast<const float4*>(sbias + (u == 8 ? kBiasFeat : u * 256) + c0);
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 bb = bp[i >> 2];
+              f[i] = __uint_as_float(v[i]) + bb.x; f[i + 1] = __uint_as_float(v[i + 1]) + bb.y;
+              f[i + 2] = __uint_as_float(v[i + 2]) + bb.z; f[i + 3] = __uint_as_float(v[i + 3]) + bb.w;
+            }
           }
+          store_group32<PREC>(base + L::act + b * kBlkBytes + row_off, row, g * 4, f, relu);
           fence_proxy_async_smem();
           tc_fence_before_sync();
           mbar_arrive(base + L::act_ready + 8 * b);
+          if (tr) tr[u * 10 + 3 + 2 * (GPB == 2 ? b : (b >> 1))] = clock64();
         }
       }
       // ---- unit 10: rgb accumulator + sigma -> raw[p] ------------------------------------------------------
+      if (tr) tr[100] = clock64();
       wait_bar(base + L::acc_full + 8 * 10, par, abort_addr, a.err, 0x40000000 | (10 << 8) | wg);
+      if (tr) tr[101] = clock64();
       tc_fence_after_sync();
       if (wg == 0) {
         uint32_t c[4];
@@ -345,6 +377,7 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) nerf_mlp_kernel(const MlpArgs 
           st_stream4(reinterpret_cast<float4*>(a.raw) + p, o);
         }
       }
+      if (tr) tr[102] = clock64();
       tc_fence_before_sync();
     }
   }
@@ -362,6 +395,9 @@ static std::once_flag g_plan_once;
 static MlpPlan g_plan[2];
 static bool g_dev_init[64];
 static std::mutex g_dev_mutex;
+
+static unsigned long long* g_trace = nullptr;  // diagnostic only (gbn_mlp_set_trace)
+static int g_trace_tile = 0;
 
 static const MlpPlan& plan(int precision) {
   std::call_once(g_plan_once, [] {
@@ -421,6 +457,7 @@ static int run_mlp(const void* packed, int precision, const float* ro, const flo
   a.packed = reinterpret_cast<const uint8_t*>(packed);
   a.ro = ro; a.rd = rd; a.z = z; a.pts = pts; a.emb = emb;
   a.view_bias = vbias; a.raw = raw; a.err = err;
+  a.trace = g_trace; a.trace_tile = g_trace_tile;
   a.stride = stride; a.P = R * S; a.S = S;
   const int64_t ntiles = (a.P + kTileRows - 1) / kTileRows;
   const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
@@ -438,6 +475,12 @@ using namespace gbn;
 extern "C" size_t gbn_mlp_packed_bytes(int precision) {
   if (precision != GBN_PRECISION_BF16 && precision != GBN_PRECISION_TF32) return 0;
   return mlp_plan(precision).total_bytes;
+}
+
+extern "C" int gbn_mlp_set_trace(void* buf, int tile) {
+  g_trace = static_cast<unsigned long long*>(buf);
+  g_trace_tile = tile;
+  return GBN_OK;
 }
 
 extern "C" size_t gbn_mlp_workspace_bytes(int64_t R) { return 256 + (size_t)(R < 0 ? 0 : R) * 128 * sizeof(float); }

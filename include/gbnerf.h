@@ -110,6 +110,11 @@ int gbn_mlp_forward(const void* packed, int precision, const float* rays_o, cons
                     const float* viewdirs, int64_t ray_stride, const float* z, const float* pts, int64_t R,
                     int S, float* raw, void* workspace, void* stream);
 
+/* Diagnostic: when buf is non-NULL (device memory, >= 16 KiB, zeroed by the caller), CTA 0 of every following MLP
+ * launch records clock64() stamps of its producer / MMA / encoder / epilogue roles for its `tile`-th tile
+ * (layout: tools/mlp_trace.py).  NULL switches tracing off.  Not part of the reference-facing surface. */
+int gbn_mlp_set_trace(void* buf, int tile);
+
 /* Same network on pre-embedded rows (NeRF.forward's own signature): emb [P,90] fp32 -> raw [P,4]. */
 int gbn_mlp_forward_embedded(const void* packed, int precision, const float* emb, int64_t P, float* raw,
                              void* workspace, void* stream);
