@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgbnerf.so")
 
 PRECISION = {"bf16": 0, "tf32": 1}
+PACK_BWD_BF16 = 2
 
 _p, _i64, _i, _f, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t
 
@@ -27,14 +28,19 @@ SIGNATURES = {
     "gbn_mlp_packed_bytes": (_sz, [_i]),
     "gbn_mlp_prepack_weights": (_i, [C.POINTER(_p), _p, _i, _p]),
     "gbn_mlp_workspace_bytes": (_sz, [_i64]),
-    "gbn_mlp_forward": (_i, [_p, _i, _p, _p, _p, _i64, _p, _p, _i64, _i, _p, _p, _p]),
+    "gbn_mlp_forward": (_i, [_p, _i, _p, _p, _p, _i64, _p, _p, _i64, _i, _p, _p, _p, _p]),
+    "gbn_mlp_stash_bytes": (_sz, [_i64]),
+    "gbn_mlp_backward_data": (_i, [_p, _p, _i64, _p, _p, _p, _p]),
+    "gbn_mlp_wgrad_workspace_bytes": (_sz, [_i64]),
+    "gbn_mlp_backward_weights": (_i, [_p, _p, _p, _p, _i64, _i64, _i, C.POINTER(_p), _p, _p]),
     "gbn_mlp_set_trace": (_i, [_p, _i]),
-    "gbn_mlp_forward_embedded": (_i, [_p, _i, _p, _i64, _p, _p, _p]),
+    "gbn_mlp_forward_embedded": (_i, [_p, _i, _p, _i64, _p, _p, _p, _p]),
     "gbn_loss_seed": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _f, _p, _p, _p, _p, _p]),
 }
 
 # kernels each entry point enqueues (bench.py reports the sum over its timed region as gpu_launches)
-KERNELS_PER_CALL = {"gbn_mlp_forward": 2, "gbn_mlp_forward_embedded": 2}
+KERNELS_PER_CALL = {"gbn_mlp_forward": 2, "gbn_mlp_forward_embedded": 2, "gbn_mlp_backward_weights": 3,
+                    "gbn_version": 0, "gbn_mlp_set_trace": 0}
 LAUNCHES = 0
 
 _lib = None

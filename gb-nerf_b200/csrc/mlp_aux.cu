@@ -10,7 +10,7 @@ namespace gbn {
 
 const MlpPlan& mlp_plan(int precision);  // mlp_tc.cu
 
-__constant__ PackJob c_pack[2][kMaxJobs];
+__constant__ PackJob c_pack[kNumPlans][kMaxJobs];
 
 struct ParamPtrs {
   const float* w[GBN_NUM_LINEAR];
@@ -24,16 +24,23 @@ struct PackHeader {
 // one block per weight chunk: [rows x KB] slice of a linear's weight -> K-major, 128-byte-swizzled image
 template <int PREC>
 __global__ void __launch_bounds__(256) prepack_kernel(ParamPtrs pp, uint8_t* __restrict__ out, int njobs,
-                                                      PackHeader hdr) {
+                                                      PackHeader hdr, int plan) {
   constexpr int ESZ = PREC == GBN_PRECISION_BF16 ? 2 : 4;
   constexpr int KB = 128 / ESZ;
   if ((int)blockIdx.x < njobs) {
-    const PackJob q = c_pack[PREC][blockIdx.x];
+    const PackJob q = c_pack[plan][blockIdx.x];
     const float* W = pp.w[q.layer];
     for (int i = threadIdx.x; i < q.rows * KB; i += blockDim.x) {
-      const int n = i / KB, k = i - n * KB;
+      // transposed slabs read W with n as the fast index: let consecutive threads walk n there
+      const int n = q.transpose ? i % q.rows : i / KB;
+      const int k = q.transpose ? i / q.rows : i - n * KB;
       float v = 0.f;
-      if (n < q.rows_valid && k < q.cols_valid) v = __ldg(W + (size_t)(q.row0 + n) * q.ld + q.col0 + k);
+      if (!q.transpose) {
+        if (n < q.rows_valid && k < q.cols_valid) v = __ldg(W + (size_t)(q.row0 + n) * q.ld + q.col0 + k);
+      } else {
+        const int ks = k - (int)q.koff;
+        if (n < q.rows_valid && ks >= 0 && ks < q.cols_valid) v = __ldg(W + (size_t)(q.row0 + ks) * q.ld + q.col0 + n);
+      }
       const uint32_t byte = (uint32_t)k * ESZ;
       uint8_t* dst = out + q.w_off + tc::sw128_offset((uint32_t)n, byte >> 4) + (byte & 15);
       if constexpr (PREC == GBN_PRECISION_BF16) {
@@ -126,7 +133,7 @@ static std::mutex g_pack_mutex;
 using namespace gbn;
 
 extern "C" int gbn_mlp_prepack_weights(const void* const* params, void* packed, int precision, void* stream) {
-  GBN_REQUIRE(precision == GBN_PRECISION_BF16 || precision == GBN_PRECISION_TF32, "prepack: unknown precision %d", precision);
+  GBN_REQUIRE(precision >= 0 && precision < kNumPlans, "prepack: unknown precision/plan %d", precision);
   GBN_REQUIRE(params && packed, "prepack: null pointer");
   GBN_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 255) == 0, "prepack: packed buffer must be 256-byte aligned");
   ParamPtrs pp;
@@ -143,7 +150,7 @@ extern "C" int gbn_mlp_prepack_weights(const void* const* params, void* packed, 
   {
     std::lock_guard<std::mutex> lk(g_pack_mutex);
     if (!g_pack_init[dev]) {
-      for (int pr = 0; pr < 2; ++pr) {
+      for (int pr = 0; pr < kNumPlans; ++pr) {
         const MlpPlan& q = mlp_plan(pr);
         GBN_CUDA(cudaMemcpyToSymbolAsync(c_pack, q.pack.data(), q.pack.size() * sizeof(PackJob),
                                          pr * kMaxJobs * sizeof(PackJob), cudaMemcpyHostToDevice, st));
@@ -154,9 +161,9 @@ extern "C" int gbn_mlp_prepack_weights(const void* const* params, void* packed, 
   PackHeader hdr{0x4e42476bu, (uint32_t)precision, p.off_bias, p.off_wdir, p.off_bdir, p.total_bytes,
                  (uint32_t)p.jobs.size(), 0};
   const int njobs = (int)p.jobs.size();
-  if (precision == GBN_PRECISION_BF16)
-    prepack_kernel<GBN_PRECISION_BF16><<<njobs + 1, 256, 0, st>>>(pp, static_cast<uint8_t*>(packed), njobs, hdr);
+  if (precision != GBN_PRECISION_TF32)
+    prepack_kernel<GBN_PRECISION_BF16><<<njobs + 1, 256, 0, st>>>(pp, static_cast<uint8_t*>(packed), njobs, hdr, precision);
   else
-    prepack_kernel<GBN_PRECISION_TF32><<<njobs + 1, 256, 0, st>>>(pp, static_cast<uint8_t*>(packed), njobs, hdr);
+    prepack_kernel<GBN_PRECISION_TF32><<<njobs + 1, 256, 0, st>>>(pp, static_cast<uint8_t*>(packed), njobs, hdr, precision);
   return check_launch("prepack_kernel");
 }

@@ -1,0 +1,379 @@
+// Parameter gradients of the 8x256 NeRF MLP from the training stashes (H: forward activations, G: pre-activation
+// gradients written by the dgrad pass of mlp_tc.cu).  Autograd equivalent: the weight/bias gradients of the twelve
+// nn.Linear modules of run_nerf_helpers.py:88-104.
+//
+//   wgrad_tc_kernel     dW_l[n,k] = sum_p G_l[p,n] H_{l-1}[p,k] for the ten wide layers on tcgen05: both operands are
+//                       the stash block images themselves ([128 points x 64 channels], 128B swizzle), consumed as
+//                       MN-major UMMA operands (M = out channel, N = in channel, K = points), fp32 accumulators for
+//                       a whole 256x256 weight gradient in TMEM (2 x 256 columns), split-K over point tiles across
+//                       CTAs, flushed with red.global.add.  Bias gradients (column sums of G) are taken from the
+//                       same shared-memory tiles by otherwise idle warps.
+//   head_grad_kernel    rgb_linear / alpha_linear (N = 3 / 1): CUDA-core reductions.
+//   viewdir_grad_kernel the 27 direction columns of views_linears.0 (constant along a ray, folded into a per-ray
+//                       bias in the forward): per-ray sums of g_hv, then an outer product with enc(viewdir).
+#include <mutex>
+
+#include "common.cuh"
+#include "mlp_layout.h"
+#include "tc_ptx.cuh"
+
+namespace gbn {
+
+using namespace tc;
+
+struct WgItem {
+  uint8_t a_blk;      // first G-stash block of the gradient (A operand), 64 output channels per block
+  uint8_t m_blocks;   // 2 (M = 128) or 4 (M = 256, two accumulator halves)
+  uint8_t b_blk;      // first H-stash block of the layer input (B operand)
+  uint8_t n_blocks;   // 1 (N = 64) or 4 (N = 256)
+  uint8_t layer;      // index into the 12 linears (order of gbn_mlp_prepack_weights)
+  uint8_t do_bias;    // this item also reduces the bias gradient of `layer`
+  uint16_t ld;        // in_features of that linear
+  uint16_t col0;      // first weight column this item produces
+  uint16_t n_valid;   // columns that exist (63 for the encoding block)
+  uint16_t cta_begin, cta_end;   // CTAs [begin, end) of the 148 share this item's point tiles
+};
+
+constexpr int kWgItems = 11;
+constexpr int kWgThreads = 384;      // warp 0 producer, 1 MMA, 2 TMEM alloc, 4-7 bias sums, 8-11 flush
+constexpr int kWgStages = 3;
+constexpr int kWgHalf = 8192;        // bytes of the 64-point half of a 16 KB block image
+constexpr int kWgStageBytes = 8 * kWgHalf;
+
+__constant__ WgItem c_wg[kWgItems];
+
+struct WgArgs {
+  const uint8_t* stash_h;
+  const uint8_t* stash_g;
+  float* w[GBN_NUM_LINEAR];
+  float* b[GBN_NUM_LINEAR];
+  int64_t ntiles;
+  int* err;
+};
+
+struct WgSmem {
+  static constexpr uint32_t ring = 0;
+  static constexpr uint32_t full = ring + kWgStages * kWgStageBytes;
+  static constexpr uint32_t empty = full + 8 * kWgStages;
+  static constexpr uint32_t done = empty + 8 * kWgStages;
+  static constexpr uint32_t tmem_ptr = done + 8;
+  static constexpr uint32_t abort_flag = tmem_ptr + 4;
+  static constexpr uint32_t total = abort_flag + 4;
+  static constexpr uint32_t alloc = total + 1024;
+};
+
+// MN-major operand, 128-byte swizzle (cute: ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO))): 64 contiguous channels per
+// 128-byte row, rows = the K (point) index 128 B apart, 8-row groups SBO apart, 64-channel groups LBO apart
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ void wg_wait(uint32_t bar, uint32_t parity, uint32_t abort_addr, int* err, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    uint32_t ab;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(ab) : "r"(abort_addr));
+    if (ab) return;
+    if (clock64() - t0 > kWatchdogCycles) {
+      atomicCAS(err, 0, code);
+      asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(abort_addr), "r"(1u));
+      return;
+    }
+  }
+}
+
+__device__ __forceinline__ void red_add(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgArgs a) {
+  using L = WgSmem;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* const gen = smem_raw + (base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t abort_addr = base + L::abort_flag;
+
+  // which item, which tiles
+  int it = 0;
+  for (int i = 0; i < kWgItems; ++i)
+    if ((int)blockIdx.x >= c_wg[i].cta_begin && (int)blockIdx.x < c_wg[i].cta_end) it = i;
+  const WgItem w = c_wg[it];
+  const int ncta = w.cta_end - w.cta_begin, rank = (int)blockIdx.x - w.cta_begin;
+  const int64_t t_begin = a.ntiles * rank / ncta, t_end = a.ntiles * (rank + 1) / ncta;
+  const int64_t nstages = (t_end - t_begin) * 2;   // 64-point half tiles
+  const int nhalves = w.m_blocks / 2;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kWgStages; ++i) {
+      mbar_init(base + L::full + 8 * i, 1);
+      mbar_init(base + L::empty + 8 * i, 1 + 4);   // MMA commit + the four bias-sum warps
+    }
+    mbar_init(base + L::done, 1);
+    *reinterpret_cast<volatile uint32_t*>(gen + L::abort_flag) = 0;
+    mbar_init_fence();
+  }
+  if (warp == 2) tmem_alloc(base + L::tmem_ptr, kTmemCols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + L::tmem_ptr);
+
+  if (warp == 0) {
+    // ---- producer: per stage (m_blocks + n_blocks) bulk copies of the 8 KB half-block images -----------------
+    for (int64_t i = 0; i < nstages; ++i) {
+      const uint32_t s = (uint32_t)(i % kWgStages), par = (uint32_t)((i / kWgStages) & 1);
+      wg_wait(base + L::empty + 8 * s, par ^ 1, abort_addr, a.err, 0x50000000 | (int)s);
+      const int64_t tile = t_begin + (i >> 1);
+      const uint32_t half_off = (uint32_t)(i & 1) * kWgHalf;
+      const uint8_t* g = a.stash_g + (size_t)tile * kStashTileBytes + (size_t)w.a_blk * kBlkBytes + half_off;
+      const uint8_t* h = a.stash_h + (size_t)tile * kStashTileBytes + (size_t)w.b_blk * kBlkBytes + half_off;
+      if (elect_one()) {
+        mbar_expect_tx(base + L::full + 8 * s, (uint32_t)(w.m_blocks + w.n_blocks) * kWgHalf);
+        for (int b = 0; b < w.m_blocks; ++b)
+          tma_bulk_g2s(base + L::ring + s * kWgStageBytes + b * kWgHalf, g + (size_t)b * kBlkBytes, kWgHalf,
+                       base + L::full + 8 * s);
+        for (int b = 0; b < w.n_blocks; ++b)
+          tma_bulk_g2s(base + L::ring + s * kWgStageBytes + (4 + b) * kWgHalf, h + (size_t)b * kBlkBytes, kWgHalf,
+                       base + L::full + 8 * s);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer: D[half][n_out, k_in] += A^T B over 64 points per stage (4 K-steps of 16) ----------------
+    const uint32_t idesc = make_idesc(1, 128, (uint32_t)w.n_blocks * 64) | (1u << 15) | (1u << 16);
+    for (int64_t i = 0; i < nstages; ++i) {
+      const uint32_t s = (uint32_t)(i % kWgStages), par = (uint32_t)((i / kWgStages) & 1);
+      wg_wait(base + L::full + 8 * s, par, abort_addr, a.err, 0x51000000 | (int)s);
+      tc_fence_after_sync();
+      const uint32_t sa = base + L::ring + s * kWgStageBytes, sb = sa + 4 * kWgHalf;
+      if (elect_one()) {
+        for (int hf = 0; hf < nhalves; ++hf) {
+          const uint64_t adesc = smem_desc_mn_sw128(sa + hf * 2 * kWgHalf, kWgHalf, 1024);
+          const uint64_t bdesc = smem_desc_mn_sw128(sb, kWgHalf, 1024);
+          const uint32_t d = tmem + hf * 256;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // 16 points = 16 rows of 128 B = 2048 B -> +128 in the address field
+            umma_bf16(d, adesc + 128 * k, bdesc + 128 * k, idesc, (i == 0 && k == 0) ? 0u : 1u);
+        }
+        umma_commit(base + L::empty + 8 * s);
+        if (i == nstages - 1) umma_commit(base + L::done);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ---- bias gradient: column sums of the G tile, two adjacent channels (one 32-bit word) per thread ---------
+    const int t = threadIdx.x - 128;            // 0..127 -> channels 2t, 2t+1
+    const int blk = t >> 5, wd = t & 31;        // 64-channel block, word within the 128-byte row
+    const bool active = w.do_bias && blk < w.m_blocks;
+    float s0 = 0.f, s1 = 0.f;
+    for (int64_t i = 0; i < nstages; ++i) {
+      const uint32_t s = (uint32_t)(i % kWgStages), par = (uint32_t)((i / kWgStages) & 1);
+      wg_wait(base + L::full + 8 * s, par, abort_addr, a.err, 0x52000000 | (int)s);
+      if (active) {
+        const uint8_t* blkp = gen + L::ring + s * kWgStageBytes + blk * kWgHalf;
+#pragma unroll 8
+        for (int r = 0; r < 64; ++r) {
+          const uint32_t off = (uint32_t)r * 128u + ((uint32_t)((wd >> 2) ^ (r & 7)) << 4) + (uint32_t)(wd & 3) * 4u;
+          const uint32_t v = *reinterpret_cast<const uint32_t*>(blkp + off);
+          s0 += __uint_as_float(v << 16);
+          s1 += __uint_as_float(v & 0xffff0000u);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(base + L::empty + 8 * s);
+    }
+    if (active && nstages > 0) {
+      red_add(a.b[w.layer] + 2 * t, s0);
+      red_add(a.b[w.layer] + 2 * t + 1, s1);
+    }
+  } else if (warp >= 8) {
+    // ---- flush: accumulator rows -> red.global.add into the nn.Linear-layout gradient ------------------------
+    if (nstages > 0) {
+      wg_wait(base + L::done, 0, abort_addr, a.err, 0x53000000);
+      tc_fence_after_sync();
+      const int q = warp & 3;
+      const uint32_t lane_addr = tmem + ((uint32_t)(q << 5) << 16);
+      for (int hf = 0; hf < nhalves; ++hf) {
+        const int n_out = hf * 128 + q * 32 + lane;
+        float* dst = a.w[w.layer] + (size_t)n_out * w.ld + w.col0;
+        for (int c0 = 0; c0 < w.n_blocks * 64; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(lane_addr + hf * 256 + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < w.n_valid) red_add(dst + c0 + i, __uint_as_float(v[i]));
+        }
+      }
+      tc_fence_before_sync();
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, kTmemCols);
+}
+
+// =========================================================================================================
+// rgb_linear / alpha_linear: dW_rgb[c,j] = sum_p g_c[p] hv[p,j], dw_alpha[k] = sum_p g_sigma[p] h7[p,k] (+ biases)
+// =========================================================================================================
+__device__ __forceinline__ float stash_bf16(const uint8_t* tile, int blk, int row, int col) {
+  const uint32_t off = (uint32_t)blk * kBlkBytes + tc::sw128_offset((uint32_t)row, (uint32_t)(col >> 3)) + (uint32_t)(col & 7) * 2u;
+  return __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(tile + off)) << 16);
+}
+
+__global__ void __launch_bounds__(256) head_grad_kernel(const uint8_t* __restrict__ stash_h, const float* __restrict__ g_raw,
+                                                        int64_t P, int64_t ntiles, float* __restrict__ dw_rgb,
+                                                        float* __restrict__ db_rgb, float* __restrict__ dw_alpha,
+                                                        float* __restrict__ db_alpha) {
+  __shared__ float4 g[kTileRows];
+  const int j = threadIdx.x;
+  float aa = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, sb[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    __syncthreads();
+    if (j < kTileRows) {
+      const int64_t p = tile * kTileRows + j;
+      g[j] = p < P ? __ldg(reinterpret_cast<const float4*>(g_raw) + p) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    const uint8_t* th = stash_h + (size_t)tile * kStashTileBytes;
+    for (int r = 0; r < kTileRows; ++r) {
+      const float4 gr = g[r];
+      aa = fmaf(gr.w, stash_bf16(th, 4 * 7 + (j >> 6), r, j & 63), aa);
+      if (j < 128) {
+        const float hv = stash_bf16(th, kHHv + (j >> 6), r, j & 63);
+        r0 = fmaf(gr.x, hv, r0); r1 = fmaf(gr.y, hv, r1); r2 = fmaf(gr.z, hv, r2);
+      }
+      if (j == 255) { sb[0] += gr.x; sb[1] += gr.y; sb[2] += gr.z; sb[3] += gr.w; }
+    }
+  }
+  red_add(dw_alpha + j, aa);
+  if (j < 128) { red_add(dw_rgb + j, r0); red_add(dw_rgb + 128 + j, r1); red_add(dw_rgb + 256 + j, r2); }
+  if (j == 255) { red_add(db_rgb, sb[0]); red_add(db_rgb + 1, sb[1]); red_add(db_rgb + 2, sb[2]); red_add(db_alpha, sb[3]); }
+}
+
+// =========================================================================================================
+// direction columns of views_linears.0: dW_v[j, 256 + c] = sum_r (sum_s g_hv[r,s,j]) enc4(viewdir_r)[c]
+// =========================================================================================================
+constexpr int kVdRays = 8;
+__global__ void __launch_bounds__(128) viewdir_grad_kernel(const uint8_t* __restrict__ stash_g, const float* __restrict__ vd,
+                                                           int64_t stride, int64_t R, int S, float* __restrict__ dw_views) {
+  __shared__ float enc[kVdRays][28];
+  const int j = threadIdx.x;
+  float acc[27];
+#pragma unroll
+  for (int c = 0; c < 27; ++c) acc[c] = 0.f;
+  const int64_t ngroups = (R + kVdRays - 1) / kVdRays;
+  for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    __syncthreads();
+    const int64_t r0 = grp * kVdRays;
+    if (j < kVdRays * 3) {
+      const int rr = j / 3, ax = j - rr * 3;
+      const float x = (r0 + rr < R) ? __ldg(vd + (r0 + rr) * stride + ax) : 0.f;
+      float sc[8];
+      posenc_axis<4>(x, sc);
+      enc[rr][ax] = x;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { enc[rr][3 + 6 * k + ax] = sc[2 * k]; enc[rr][6 + 6 * k + ax] = sc[2 * k + 1]; }
+    }
+    __syncthreads();
+    for (int rr = 0; rr < kVdRays && r0 + rr < R; ++rr) {
+      float gs = 0.f;
+      const int64_t p0 = (r0 + rr) * S;
+      for (int s = 0; s < S; ++s) {
+        const int64_t p = p0 + s;
+        gs += stash_bf16(stash_g + (size_t)(p >> 7) * kStashTileBytes, kGHv + (j >> 6), (int)(p & 127), j & 63);
+      }
+#pragma unroll
+      for (int c = 0; c < 27; ++c) acc[c] = fmaf(gs, enc[rr][c], acc[c]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 27; ++c) red_add(dw_views + (size_t)j * 283 + 256 + c, acc[c]);
+}
+
+// =========================================================================================================
+// host
+// =========================================================================================================
+static bool g_wg_init[64];
+static std::mutex g_wg_mutex;
+
+static void make_items(WgItem* items) {
+  int n = 0;
+  auto add = [&](int a_blk, int m_blocks, int b_blk, int n_blocks, int layer, int do_bias, int ld, int col0, int n_valid) {
+    WgItem w{};
+    w.a_blk = (uint8_t)a_blk; w.m_blocks = (uint8_t)m_blocks; w.b_blk = (uint8_t)b_blk; w.n_blocks = (uint8_t)n_blocks;
+    w.layer = (uint8_t)layer; w.do_bias = (uint8_t)do_bias; w.ld = (uint16_t)ld; w.col0 = (uint16_t)col0;
+    w.n_valid = (uint16_t)n_valid;
+    items[n++] = w;
+  };
+  add(kGLayer0, 4, kHEnc, 1, 0, 1, 63, 0, 63);                                           // pts_linears.0
+  for (int l = 1; l <= 7; ++l)                                                           // pts_linears.1-7
+    add(kGLayer0 + 4 * l, 4, 4 * (l - 1), 4, l, 1, l == 5 ? 319 : 256, l == 5 ? 63 : 0, 256);
+  add(kGLayer0 + 4 * 5, 4, kHEnc, 1, 5, 0, 319, 0, 63);                                  // skip columns of layer 5
+  add(kGFeat, 4, 4 * 7, 4, LIN_FEATURE, 1, 256, 0, 256);                                 // feature_linear
+  add(kGHv, 2, kHFeat, 4, LIN_VIEWS, 1, 283, 0, 256);                                    // views_linears.0[:, :256]
+  // CTAs in proportion to the bytes each item streams per tile
+  int cost[kWgItems], total = 0;
+  for (int i = 0; i < kWgItems; ++i) { cost[i] = items[i].m_blocks + items[i].n_blocks; total += cost[i]; }
+  int given = 0, share[kWgItems];
+  for (int i = 0; i < kWgItems; ++i) { share[i] = kNumSMs * cost[i] / total; if (share[i] < 1) share[i] = 1; given += share[i]; }
+  for (int i = 0; given < kNumSMs; i = (i + 1) % kWgItems) if (cost[i] == 8) { ++share[i]; ++given; }
+  int c = 0;
+  for (int i = 0; i < kWgItems; ++i) { items[i].cta_begin = (uint16_t)c; c += share[i]; items[i].cta_end = (uint16_t)c; }
+}
+
+}  // namespace gbn
+
+using namespace gbn;
+
+extern "C" size_t gbn_mlp_wgrad_workspace_bytes(int64_t R) { (void)R; return 256; }
+
+extern "C" int gbn_mlp_backward_weights(const void* stash_h, const void* stash_g, const float* g_raw,
+                                        const float* viewdirs, int64_t ray_stride, int64_t R, int S,
+                                        void* const* grads, void* workspace, void* stream) {
+  GBN_REQUIRE(R >= 0 && S >= 1, "mlp_backward_weights: bad sizes");
+  if (R == 0) return GBN_OK;
+  GBN_REQUIRE(stash_h && stash_g && g_raw && viewdirs && grads && workspace, "mlp_backward_weights: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0;
+  GBN_CUDA(cudaGetDevice(&dev));
+  GBN_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
+  {
+    std::lock_guard<std::mutex> lk(g_wg_mutex);
+    if (!g_wg_init[dev]) {
+      WgItem items[kWgItems];
+      make_items(items);
+      GBN_CUDA(cudaMemcpyToSymbolAsync(c_wg, items, sizeof(items), 0, cudaMemcpyHostToDevice, st));
+      GBN_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WgSmem::alloc));
+      g_wg_init[dev] = true;
+    }
+  }
+  WgArgs a{};
+  a.stash_h = static_cast<const uint8_t*>(stash_h);
+  a.stash_g = static_cast<const uint8_t*>(stash_g);
+  for (int i = 0; i < GBN_NUM_LINEAR; ++i) {
+    GBN_REQUIRE(grads[2 * i] && grads[2 * i + 1], "mlp_backward_weights: grads[%d] is null", 2 * i);
+    a.w[i] = static_cast<float*>(grads[2 * i]);
+    a.b[i] = static_cast<float*>(grads[2 * i + 1]);
+  }
+  const int64_t P = R * S;
+  a.ntiles = (P + kTileRows - 1) / kTileRows;
+  a.err = static_cast<int*>(workspace);
+  GBN_CUDA(cudaMemsetAsync(a.err, 0, 256, st));
+  wgrad_tc_kernel<<<kNumSMs, kWgThreads, WgSmem::alloc, st>>>(a);
+  int rc = check_launch("wgrad_tc_kernel");
+  if (rc != GBN_OK) return rc;
+  const int hgrid = (int)(a.ntiles < 2 * kNumSMs ? a.ntiles : 2 * kNumSMs);
+  head_grad_kernel<<<hgrid, 256, 0, st>>>(a.stash_h, g_raw, P, a.ntiles, a.w[LIN_RGB], a.b[LIN_RGB], a.w[LIN_ALPHA],
+                                         a.b[LIN_ALPHA]);
+  rc = check_launch("head_grad_kernel");
+  if (rc != GBN_OK) return rc;
+  const int64_t groups = (R + kVdRays - 1) / kVdRays;
+  const int vgrid = (int)(groups < 2 * kNumSMs ? groups : 2 * kNumSMs);
+  viewdir_grad_kernel<<<vgrid, 128, 0, st>>>(a.stash_g, viewdirs, ray_stride, R, S, a.w[LIN_VIEWS]);
+  return check_launch("viewdir_grad_kernel");
+}

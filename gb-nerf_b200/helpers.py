@@ -83,7 +83,10 @@ class NeRF(nn.Module):
         self.precision = precision or os.environ.get("GBNERF_PRECISION", "bf16")
         self._packed = None
         self._packed_key = None
+        self._packed_bwd = None
+        self._packed_bwd_key = None
         self.last_workspace = None
+        self.last_workspace_bwd = None
 
     # -- kernel plumbing ----------------------------------------------------------------------------------
     def _check_geometry(self):
@@ -111,6 +114,15 @@ class NeRF(nn.Module):
                                                else None)
             self._packed_key = key
         return self._packed
+
+    def packed_weights_bwd(self):
+        """Transposed bf16 weights for the dgrad kernel (same caching rule)."""
+        ps = self.param_list()
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if key != self._packed_bwd_key:
+            self._packed_bwd = ops.prepack_weights(ps, "bf16_bwd", out=self._packed_bwd)
+            self._packed_bwd_key = key
+        return self._packed_bwd
 
     def forward(self, x):
         return ops.mlp_embedded(self, x)

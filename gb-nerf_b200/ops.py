@@ -10,7 +10,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import PRECISION
+from ._lib import PRECISION, PACK_BWD_BF16
 
 
 # bench.py sets this to a list to collect (name, start_event, end_event, points) per MLP launch, recorded on
@@ -204,7 +204,7 @@ PARAM_SHAPES = {"pts_linears.0": (256, 63), "pts_linears.5": (256, 319), "featur
 
 def prepack_weights(params, precision="bf16", out=None):
     """params: 24 tensors (weight, bias) x PARAM_ORDER -> packed uint8 buffer in the kernel's smem layout."""
-    prec = PRECISION[precision]
+    prec = PACK_BWD_BF16 if precision == "bf16_bwd" else PRECISION[precision]
     if len(params) != 24:
         raise ValueError("expected 24 parameter tensors")
     keep = []
@@ -227,7 +227,12 @@ def _workspace(R, device):
     return torch.empty(_lib.load().gbn_mlp_workspace_bytes(int(R)), device=device, dtype=torch.uint8)
 
 
-def mlp_forward_raw(packed, precision, viewdirs, R, S, rays_o=None, rays_d=None, z=None, pts=None):
+def _stash(P, device):
+    """Training stash (H or G): gbn_mlp_stash_bytes(P) bytes; torch allocations are 512-byte aligned."""
+    return torch.empty(_lib.load().gbn_mlp_stash_bytes(int(P)), device=device, dtype=torch.uint8)
+
+
+def mlp_forward_raw(packed, precision, viewdirs, R, S, rays_o=None, rays_d=None, z=None, pts=None, stash=None):
     """Kernel launch only (no autograd): raw [R,S,4]."""
     if pts is not None:
         pts = _dense(pts, "pts").reshape(-1, 3)
@@ -240,7 +245,7 @@ def mlp_forward_raw(packed, precision, viewdirs, R, S, rays_o=None, rays_d=None,
     ws = _workspace(R, viewdirs.device)
     with _timed_launch("mlp", R * S):
         _lib.call("gbn_mlp_forward", _ptr(packed), PRECISION[precision], _ptr(rays_o), _ptr(rays_d), _ptr(viewdirs),
-                  pitch, _ptr(z), _ptr(pts), R, S, _ptr(raw), _ptr(ws), _stream())
+                  pitch, _ptr(z), _ptr(pts), R, S, _ptr(raw), _ptr(ws), _ptr(stash), _stream())
     return raw, ws
 
 
@@ -251,8 +256,32 @@ def mlp_forward_embedded_raw(packed, precision, emb):
     P = emb.shape[0]
     raw = torch.empty(P, 4, device=emb.device, dtype=torch.float32)
     ws = _workspace(P, emb.device)
-    _lib.call("gbn_mlp_forward_embedded", _ptr(packed), PRECISION[precision], _ptr(emb), P, _ptr(raw), _ptr(ws), _stream())
+    _lib.call("gbn_mlp_forward_embedded", _ptr(packed), PRECISION[precision], _ptr(emb), P, _ptr(raw), _ptr(ws), None,
+              _stream())
     return raw, ws
+
+
+def mlp_backward_raw(packed_bwd, g_raw, stash_h, viewdirs, R, S, param_shapes):
+    """dgrad + wgrad launches: returns (list of 24 fp32 gradients in nn.Linear layout, workspace, G stash)."""
+    g_raw = _dense(g_raw.reshape(R * S, 4), "g_raw", 2)
+    (viewdirs,), pitch = _ray_views(viewdirs)
+    dev = g_raw.device
+    stash_g = _stash(R * S, dev)
+    ws = torch.empty(512, device=dev, dtype=torch.uint8)
+    with _timed_launch("mlp_dgrad", R * S):
+        _lib.call("gbn_mlp_backward_data", _ptr(packed_bwd), _ptr(g_raw), R * S, _ptr(stash_h), _ptr(stash_g), _ptr(ws),
+                  _stream())
+    flat = torch.zeros(sum(int(torch.Size(s).numel()) for s in param_shapes), device=dev, dtype=torch.float32)
+    grads, off = [], 0
+    for shp in param_shapes:
+        n = int(torch.Size(shp).numel())
+        grads.append(flat[off:off + n].view(shp))
+        off += n
+    arr = (C.c_void_p * 24)(*[g.data_ptr() for g in grads])
+    with _timed_launch("mlp_wgrad", R * S):
+        _lib.call("gbn_mlp_backward_weights", _ptr(stash_h), _ptr(stash_g), _ptr(g_raw), _ptr(viewdirs), pitch, R, S, arr,
+                  C.c_void_p(ws.data_ptr() + 256), _stream())
+    return grads, ws, stash_g
 
 
 def mlp_error_code(ws):
@@ -268,7 +297,8 @@ def torch_posenc(x, n_freqs):
 
 
 def _torch_mlp(params, emb):
-    """Differentiable restatement used ONLY to obtain parameter gradients in backward (cuBLAS GEMMs)."""
+    """Differentiable restatement (cuBLAS GEMMs on the device) used ONLY for parameter gradients of the two
+    variants the tcgen05 backward does not cover: tf32 modules and the pre-embedded NeRF.forward(x) form."""
     W = lambda i: params[2 * i]
     b = lambda i: params[2 * i + 1]
     x_pts, x_dir = emb[:, :63], emb[:, 63:]
@@ -284,34 +314,56 @@ def _torch_mlp(params, emb):
 
 
 class _Mlp(torch.autograd.Function):
-    """raw = NeRF(embed(o + d z), embed(viewdir)).  Forward: the fused tcgen05 kernel.
+    """raw = NeRF(embed(o + d z), embed(viewdir)).
 
-    Backward (interim, round 1): parameter gradients by recomputation through cuBLAS GEMMs on the device —
-    library code, to be replaced by the tcgen05 dgrad/wgrad kernels.  Inputs carry no gradient, exactly as in
-    the reference where z_samples is detached and rays are data (run.py:2346).
+    Forward: the fused tcgen05 kernel; when parameter gradients are needed (bf16 modules) it also writes the
+    activation stash.  Backward: the tcgen05 dgrad kernel (same skeleton, transposed weights) then the tcgen05
+    wgrad kernel + two small CUDA-core kernels.  Inputs carry no gradient, exactly as in the reference where
+    z_samples is detached and rays are data (run.py:2346).
     """
 
     @staticmethod
     def forward(ctx, module, mode, a0, a1, a2, a3, *params):
         packed = module.packed_weights()
+        need_grad = any(ctx.needs_input_grad[6:])
+        ctx.native = need_grad and module.precision == "bf16" and mode in ("rays", "pts")
+        stash = None
         if mode == "rays":
             rays_o, rays_d, viewdirs, z = a0, a1, a2, a3
             R, S = z.shape
-            raw, ws = mlp_forward_raw(packed, module.precision, viewdirs, R, S, rays_o=rays_o, rays_d=rays_d, z=z)
+            if ctx.native:
+                stash = _stash(R * S, z.device)
+            raw, ws = mlp_forward_raw(packed, module.precision, viewdirs, R, S, rays_o=rays_o, rays_d=rays_d, z=z,
+                                      stash=stash)
         elif mode == "pts":
             pts, viewdirs = a0, a1
             R, S = pts.shape[0], pts.shape[1]
-            raw, ws = mlp_forward_raw(packed, module.precision, viewdirs, R, S, pts=pts.contiguous())
+            if ctx.native:
+                stash = _stash(R * S, pts.device)
+            raw, ws = mlp_forward_raw(packed, module.precision, viewdirs, R, S, pts=pts.contiguous(), stash=stash)
         else:
             raw, ws = mlp_forward_embedded_raw(packed, module.precision, a0)
         module.last_workspace = ws
-        ctx.mode = mode
-        ctx.save_for_backward(*[t for t in (a0, a1, a2, a3) if t is not None], *params)
-        ctx.n_in = sum(t is not None for t in (a0, a1, a2, a3))
+        ctx.mode, ctx.module = mode, module
+        if ctx.native:
+            ctx.stash, ctx.RS = stash, (R, S)
+            ctx.save_for_backward(viewdirs)
+            ctx.shapes = [tuple(p.shape) for p in params]
+        elif need_grad:
+            ctx.save_for_backward(*[t for t in (a0, a1, a2, a3) if t is not None], *params)
+            ctx.n_in = sum(t is not None for t in (a0, a1, a2, a3))
         return raw
 
     @staticmethod
     def backward(ctx, g_raw):
+        if ctx.native:
+            (viewdirs,) = ctx.saved_tensors
+            R, S = ctx.RS
+            grads, ws, _ = mlp_backward_raw(ctx.module.packed_weights_bwd(), g_raw.contiguous(), ctx.stash, viewdirs, R, S,
+                                            ctx.shapes)
+            ctx.module.last_workspace_bwd = ws
+            ctx.stash = None
+            return (None, None, None, None, None, None, *grads)
         saved = ctx.saved_tensors
         ins, params = saved[:ctx.n_in], saved[ctx.n_in:]
         with torch.enable_grad():

@@ -36,6 +36,7 @@ extern "C" {
 
 #define GBN_PRECISION_BF16 0 /* bf16 operands, fp32 accumulate (tcgen05 kind::f16)  */
 #define GBN_PRECISION_TF32 1 /* tf32 operands, fp32 accumulate (tcgen05 kind::tf32) */
+#define GBN_PACK_BWD_BF16 2  /* prepack only: transposed bf16 weights for gbn_mlp_backward_data */
 
 /* Network geometry fixed by the reference (run_nerf_helpers.py:75-104 with D=8, W=256, skips=[4],
  * multires=10, multires_views=4, use_viewdirs=True). */
@@ -108,7 +109,12 @@ int gbn_mlp_prepack_weights(const void* const* params, void* packed, int precisi
 size_t gbn_mlp_workspace_bytes(int64_t R);
 int gbn_mlp_forward(const void* packed, int precision, const float* rays_o, const float* rays_d,
                     const float* viewdirs, int64_t ray_stride, const float* z, const float* pts, int64_t R,
-                    int S, float* raw, void* workspace, void* stream);
+                    int S, float* raw, void* workspace, void* stash, void* stream);
+
+/* Training stash (bf16 only).  When `stash` is non-NULL the forward also writes, per 128-point tile, the bf16
+ * activations the backward needs (8 hidden layers, feature, view-branch hidden, point encoding) as 16 KB block
+ * images of its shared-memory tiles: gbn_mlp_stash_bytes(P) bytes, 128-byte aligned. */
+size_t gbn_mlp_stash_bytes(int64_t P);
 
 /* Diagnostic: when buf is non-NULL (device memory, >= 16 KiB, zeroed by the caller), CTA 0 of every following MLP
  * launch records clock64() stamps of its producer / MMA / encoder / epilogue roles for its `tile`-th tile
@@ -117,7 +123,22 @@ int gbn_mlp_set_trace(void* buf, int tile);
 
 /* Same network on pre-embedded rows (NeRF.forward's own signature): emb [P,90] fp32 -> raw [P,4]. */
 int gbn_mlp_forward_embedded(const void* packed, int precision, const float* emb, int64_t P, float* raw,
-                             void* workspace, void* stream);
+                             void* workspace, void* stash, void* stream);
+
+/* ---- MLP backward (autograd of NeRF.forward wrt its parameters; inputs carry no gradient, run.py:2346) --------
+ * Step 1, data gradients: g_raw [P,4] -> the pre-activation gradient of every layer, written to `stash_g`
+ * (same size and tile layout as the forward stash).  packed_bwd = gbn_mlp_prepack_weights(.., GBN_PACK_BWD_BF16). */
+int gbn_mlp_backward_data(const void* packed_bwd, const float* g_raw, int64_t P, const void* stash_h,
+                          void* stash_g, void* workspace, void* stream);
+
+/* Step 2, parameter gradients: ACCUMULATES (atomic adds) into `grads`, a HOST array of 24 DEVICE pointers to fp32
+ * buffers in nn.Linear layout, same order as gbn_mlp_prepack_weights' params.  g_raw [P,4] as in step 1;
+ * viewdirs [R,3] (pitch ray_stride) are needed for the direction columns of views_linears.0; P = R*S.
+ * workspace: gbn_mlp_wgrad_workspace_bytes(R). */
+size_t gbn_mlp_wgrad_workspace_bytes(int64_t R);
+int gbn_mlp_backward_weights(const void* stash_h, const void* stash_g, const float* g_raw, const float* viewdirs,
+                             int64_t ray_stride, int64_t R, int S, void* const* grads, void* workspace,
+                             void* stream);
 
 /* ---- loss seed: img2mse terms of the training step (run.py:1483,1502,1513-1515) --------------------------
  * loss = mean((rgb-t)^2) + mean((rgb0-t)^2) + depth_lambda*mean((disp-td)^2), means over R_global*3 / R_global.
