@@ -39,7 +39,7 @@ SIGNATURES = {
 }
 
 # kernels each entry point enqueues (bench.py reports the sum over its timed region as gpu_launches)
-KERNELS_PER_CALL = {"gbn_mlp_forward": 2, "gbn_mlp_forward_embedded": 2, "gbn_mlp_backward_weights": 3,
+KERNELS_PER_CALL = {"gbn_mlp_forward": 2, "gbn_mlp_forward_embedded": 2, "gbn_mlp_backward_weights": 2,
                     "gbn_version": 0, "gbn_mlp_set_trace": 0}
 LAUNCHES = 0
 

@@ -8,7 +8,8 @@
 //                       a whole 256x256 weight gradient in TMEM (2 x 256 columns), split-K over point tiles across
 //                       CTAs, flushed with red.global.add.  Bias gradients (column sums of G) are taken from the
 //                       same shared-memory tiles by otherwise idle warps.
-//   head_grad_kernel    rgb_linear / alpha_linear (N = 3 / 1): CUDA-core reductions.
+//                       rgb_linear / alpha_linear ride along as two more items whose A operand is the padded
+//                       g_raw block (M = 128 filled by loading it twice; rows 0..2 / 3 are the gradients).
 //   viewdir_grad_kernel the 27 direction columns of views_linears.0 (constant along a ray, folded into a per-ray
 //                       bias in the forward): per-ray sums of g_hv, then an outer product with enc(viewdir).
 #include <mutex>
@@ -28,13 +29,16 @@ struct WgItem {
   uint8_t n_blocks;   // 1 (N = 64) or 4 (N = 256)
   uint8_t layer;      // index into the 12 linears (order of gbn_mlp_prepack_weights)
   uint8_t do_bias;    // this item also reduces the bias gradient of `layer`
+  uint8_t head;       // 0: wide layer | 1: alpha_linear, 2: rgb_linear (A = the padded g_raw block, loaded twice
+                      //    to fill M = 128; only accumulator rows 3 / 0..2 are meaningful)
+  uint8_t pad;
   uint16_t ld;        // in_features of that linear
   uint16_t col0;      // first weight column this item produces
   uint16_t n_valid;   // columns that exist (63 for the encoding block)
   uint16_t cta_begin, cta_end;   // CTAs [begin, end) of the 148 share this item's point tiles
 };
 
-constexpr int kWgItems = 11;
+constexpr int kWgItems = 13;
 constexpr int kWgThreads = 384;      // warp 0 producer, 1 MMA, 2 TMEM alloc, 4-7 bias sums, 8-11 flush
 constexpr int kWgStages = 3;
 constexpr int kWgHalf = 8192;        // bytes of the 64-point half of a 16 KB block image
@@ -133,8 +137,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgArgs a)
       if (elect_one()) {
         mbar_expect_tx(base + L::full + 8 * s, (uint32_t)(w.m_blocks + w.n_blocks) * kWgHalf);
         for (int b = 0; b < w.m_blocks; ++b)
-          tma_bulk_g2s(base + L::ring + s * kWgStageBytes + b * kWgHalf, g + (size_t)b * kBlkBytes, kWgHalf,
-                       base + L::full + 8 * s);
+          tma_bulk_g2s(base + L::ring + s * kWgStageBytes + b * kWgHalf, g + (w.head ? 0 : (size_t)b * kBlkBytes),
+                       kWgHalf, base + L::full + 8 * s);
         for (int b = 0; b < w.n_blocks; ++b)
           tma_bulk_g2s(base + L::ring + s * kWgStageBytes + (4 + b) * kWgHalf, h + (size_t)b * kBlkBytes, kWgHalf,
                        base + L::full + 8 * s);
@@ -186,8 +190,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgArgs a)
       if (lane == 0) mbar_arrive(base + L::empty + 8 * s);
     }
     if (active && nstages > 0) {
-      red_add(a.b[w.layer] + 2 * t, s0);
-      red_add(a.b[w.layer] + 2 * t + 1, s1);
+      if (w.head == 0) {
+        red_add(a.b[w.layer] + 2 * t, s0);
+        red_add(a.b[w.layer] + 2 * t + 1, s1);
+      } else if (w.head == 1) {          // g_raw channels: (r, g, b, sigma)
+        if (t == 1) red_add(a.b[w.layer], s1);
+      } else {
+        if (t == 0) { red_add(a.b[w.layer], s0); red_add(a.b[w.layer] + 1, s1); }
+        if (t == 1) red_add(a.b[w.layer] + 2, s0);
+      }
     }
   } else if (warp >= 8) {
     // ---- flush: accumulator rows -> red.global.add into the nn.Linear-layout gradient ------------------------
@@ -197,7 +208,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgArgs a)
       const int q = warp & 3;
       const uint32_t lane_addr = tmem + ((uint32_t)(q << 5) << 16);
       for (int hf = 0; hf < nhalves; ++hf) {
-        const int n_out = hf * 128 + q * 32 + lane;
+        int n_out = hf * 128 + q * 32 + lane;
+        bool keep = true;                                            // (tcgen05.ld below is warp-wide: no early out)
+        if (w.head == 1) { keep = (n_out == 3); n_out = 0; }         // alpha_linear.weight is [1, 256]
+        if (w.head == 2) { keep = (n_out < 3); n_out = keep ? n_out : 0; }   // rgb_linear.weight is [3, 128]
         float* dst = a.w[w.layer] + (size_t)n_out * w.ld + w.col0;
         for (int c0 = 0; c0 < w.n_blocks * 64; c0 += 32) {
           uint32_t v[32];
@@ -205,7 +219,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgArgs a)
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (c0 + i < w.n_valid) red_add(dst + c0 + i, __uint_as_float(v[i]));
+            if (keep && c0 + i < w.n_valid) red_add(dst + c0 + i, __uint_as_float(v[i]));
         }
       }
       tc_fence_before_sync();
@@ -217,42 +231,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgArgs a)
   if (warp == 2) tmem_dealloc(tmem, kTmemCols);
 }
 
-// =========================================================================================================
-// rgb_linear / alpha_linear: dW_rgb[c,j] = sum_p g_c[p] hv[p,j], dw_alpha[k] = sum_p g_sigma[p] h7[p,k] (+ biases)
-// =========================================================================================================
 __device__ __forceinline__ float stash_bf16(const uint8_t* tile, int blk, int row, int col) {
   const uint32_t off = (uint32_t)blk * kBlkBytes + tc::sw128_offset((uint32_t)row, (uint32_t)(col >> 3)) + (uint32_t)(col & 7) * 2u;
   return __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(tile + off)) << 16);
-}
-
-__global__ void __launch_bounds__(256) head_grad_kernel(const uint8_t* __restrict__ stash_h, const float* __restrict__ g_raw,
-                                                        int64_t P, int64_t ntiles, float* __restrict__ dw_rgb,
-                                                        float* __restrict__ db_rgb, float* __restrict__ dw_alpha,
-                                                        float* __restrict__ db_alpha) {
-  __shared__ float4 g[kTileRows];
-  const int j = threadIdx.x;
-  float aa = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, sb[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    __syncthreads();
-    if (j < kTileRows) {
-      const int64_t p = tile * kTileRows + j;
-      g[j] = p < P ? __ldg(reinterpret_cast<const float4*>(g_raw) + p) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    __syncthreads();
-    const uint8_t* th = stash_h + (size_t)tile * kStashTileBytes;
-    for (int r = 0; r < kTileRows; ++r) {
-      const float4 gr = g[r];
-      aa = fmaf(gr.w, stash_bf16(th, 4 * 7 + (j >> 6), r, j & 63), aa);
-      if (j < 128) {
-        const float hv = stash_bf16(th, kHHv + (j >> 6), r, j & 63);
-        r0 = fmaf(gr.x, hv, r0); r1 = fmaf(gr.y, hv, r1); r2 = fmaf(gr.z, hv, r2);
-      }
-      if (j == 255) { sb[0] += gr.x; sb[1] += gr.y; sb[2] += gr.z; sb[3] += gr.w; }
-    }
-  }
-  red_add(dw_alpha + j, aa);
-  if (j < 128) { red_add(dw_rgb + j, r0); red_add(dw_rgb + 128 + j, r1); red_add(dw_rgb + 256 + j, r2); }
-  if (j == 255) { red_add(db_rgb, sb[0]); red_add(db_rgb + 1, sb[1]); red_add(db_rgb + 2, sb[2]); red_add(db_alpha, sb[3]); }
 }
 
 // =========================================================================================================
@@ -303,8 +284,10 @@ static std::mutex g_wg_mutex;
 
 static void make_items(WgItem* items) {
   int n = 0;
-  auto add = [&](int a_blk, int m_blocks, int b_blk, int n_blocks, int layer, int do_bias, int ld, int col0, int n_valid) {
+  auto add = [&](int a_blk, int m_blocks, int b_blk, int n_blocks, int layer, int do_bias, int ld, int col0, int n_valid,
+                 int head = 0) {
     WgItem w{};
+    w.head = (uint8_t)head;
     w.a_blk = (uint8_t)a_blk; w.m_blocks = (uint8_t)m_blocks; w.b_blk = (uint8_t)b_blk; w.n_blocks = (uint8_t)n_blocks;
     w.layer = (uint8_t)layer; w.do_bias = (uint8_t)do_bias; w.ld = (uint16_t)ld; w.col0 = (uint16_t)col0;
     w.n_valid = (uint16_t)n_valid;
@@ -316,6 +299,8 @@ static void make_items(WgItem* items) {
   add(kGLayer0 + 4 * 5, 4, kHEnc, 1, 5, 0, 319, 0, 63);                                  // skip columns of layer 5
   add(kGFeat, 4, 4 * 7, 4, LIN_FEATURE, 1, 256, 0, 256);                                 // feature_linear
   add(kGHv, 2, kHFeat, 4, LIN_VIEWS, 1, 283, 0, 256);                                    // views_linears.0[:, :256]
+  add(kGRaw, 2, 4 * 7, 4, LIN_ALPHA, 1, 256, 0, 256, 1);                                 // alpha_linear
+  add(kGRaw, 2, kHHv, 2, LIN_RGB, 1, 128, 0, 128, 2);                                    // rgb_linear
   // CTAs in proportion to the bytes each item streams per tile
   int cost[kWgItems], total = 0;
   for (int i = 0; i < kWgItems; ++i) { cost[i] = items[i].m_blocks + items[i].n_blocks; total += cost[i]; }
@@ -366,11 +351,6 @@ extern "C" int gbn_mlp_backward_weights(const void* stash_h, const void* stash_g
   GBN_CUDA(cudaMemsetAsync(a.err, 0, 256, st));
   wgrad_tc_kernel<<<kNumSMs, kWgThreads, WgSmem::alloc, st>>>(a);
   int rc = check_launch("wgrad_tc_kernel");
-  if (rc != GBN_OK) return rc;
-  const int hgrid = (int)(a.ntiles < 2 * kNumSMs ? a.ntiles : 2 * kNumSMs);
-  head_grad_kernel<<<hgrid, 256, 0, st>>>(a.stash_h, g_raw, P, a.ntiles, a.w[LIN_RGB], a.b[LIN_RGB], a.w[LIN_ALPHA],
-                                         a.b[LIN_ALPHA]);
-  rc = check_launch("head_grad_kernel");
   if (rc != GBN_OK) return rc;
   const int64_t groups = (R + kVdRays - 1) / kVdRays;
   const int vgrid = (int)(groups < 2 * kNumSMs ? groups : 2 * kNumSMs);
