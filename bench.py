@@ -207,6 +207,10 @@ def run_ours(args, rank, world, local_rank):
     e2e = {"value": R * world * e2e_steps / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": R * 6 * 4,
            "d2h_bytes_per_step": R * 6 * 4, "api": "gbnerf_b200.render(H, W, focal, chunk, rays=<pinned host>)"}
 
+    train = None
+    if args.precision == "bf16" and not args.no_train:
+        train = train_step_bench(G, ops, dev, nets, kw, rank, world, timed)
+
     cpu = cpu_baseline(bounded_s=20.0) if rank == 0 and world == 1 and not args.no_cpu else None
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
@@ -217,11 +221,54 @@ def run_ours(args, rank, world, local_rank):
                            "rays_per_gpu": R, "parallelism": f"ray-sharded x{world}",
                            "l2": "256 MiB memset between steps (inside the timed region)"},
                 "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+        if train is not None:
+            line["train_step"] = train
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def train_step_bench(G, ops, dev, nets, kw_test, rank, world, timed):
+    """BASELINE configs[2]: 4096-ray training step (weak scaling: 4096 rays per GPU), train kwargs (perturb=1,
+    raw_noise_std=1), loss of SURVEY §8a row 12 over the GLOBAL batch, backward through the native kernels, one flat
+    gradient all-reduce over NCCL, Adam step.  Reported beside the headline metric, not instead of it."""
+    R = 4096
+    kw = dict(kw_test, perturb=1.0, raw_noise_std=1.0)
+    rays2 = synthetic_frame_rays(rank)
+    idx = torch.randint(0, rays2.shape[1], (R,), generator=torch.Generator().manual_seed(1 + rank))
+    rays = rays2[:, idx].contiguous().to(dev)
+    g = torch.Generator().manual_seed(2 + rank)
+    tgt, tgd = torch.rand(R, 3, generator=g).to(dev), torch.rand(R, generator=g).to(dev)
+    params = [p for n in nets for p in n.parameters()]
+    bucket = G.dist.GradBucket(params)
+    opt = torch.optim.Adam(params, lr=3e-3, betas=(0.9, 0.999))
+    inv_world = 1.0 / world
+
+    def step():
+        rgb, disp, acc, depth, ex = G.render(H, W, FOCAL, chunk=CHUNK, rays=rays, **kw)
+        loss = (G.img2mse(rgb, tgt) + G.img2mse(ex["rgb0"], tgt) + 0.1 * G.img2mse(disp, tgd)) * inv_world
+        bucket.zero()
+        loss.backward()
+        bucket.all_reduce()
+        opt.step()
+        return loss
+
+    steps = 10
+    ms, launches, events, _ = timed(step, steps, 3, kernel_events=True)
+    per = {}
+    for name, a, b, pts in events:
+        d = per.setdefault(name, [0.0, 0])
+        d[0] += a.elapsed_time(b)
+        d[1] += pts
+    flop = sum(d[1] for d in per.values()) * FLOP_PER_POINT           # forward + dgrad + wgrad ~ 3 x forward
+    t_mlp = sum(d[0] for d in per.values())
+    return {"metric": "rays/sec, 4096-ray training step (fwd + bwd + grad all-reduce + Adam)", "value": R * world * steps / (ms * 1e-3),
+            "unit": "rays/s", "ms_per_step": ms / steps, "rays_per_gpu": R, "scaling": "weak",
+            "mlp_kernels_ms_per_step": {k: v[0] / steps for k, v in per.items()},
+            "mlp_tflops_fwd_equivalent": flop / (t_mlp * 1e-3) / 1e12 if t_mlp else None,
+            "grad_allreduce_bytes": bucket.flat.numel() * 4, "gpu_launches": launches}
 
 
 # --------------------------------------------------------------------------------------------------------- #
@@ -293,6 +340,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"])
     ap.add_argument("--rays", type=int, default=0, help="debug: cap rays per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-train", action="store_true", help="skip the 4096-ray training-step leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))
