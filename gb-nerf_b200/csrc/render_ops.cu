@@ -514,6 +514,11 @@ __global__ void __launch_bounds__(256) loss_seed_kernel(const float* __restrict_
   }
 }
 
+
+
+int64_t launch_composite_fwd_staged(const float* raw, const float* z, const float* rays_d, int64_t ray_stride,
+                                    const float* noise, int64_t R, int S, int white, float* rgb, float* disp, float* acc,
+                                    float* depth, float* weights, float* alpha, cudaStream_t stream, int* rc);  // render_staged.cu
 }  // namespace gbn
 
 // =========================================================================================================
@@ -561,6 +566,17 @@ extern "C" int gbn_composite_forward(const float* raw, const float* z, const flo
   GBN_REQUIRE(raw && z && rays_d && rgb && disp && acc && depth && weights, "composite_forward: null pointer");
   GBN_REQUIRE(R >= 0 && S >= 1 && S <= 1024, "composite_forward: S=%d outside [1,1024]", S);
   GBN_REQUIRE((reinterpret_cast<uintptr_t>(raw) & 15) == 0, "composite_forward: raw must be 16-byte aligned");
+  // bulk-copy pipelined kernel for the leading groups of 8 rays, generic warp-per-ray kernel for the rest
+  int rc = GBN_OK;
+  const int64_t done = launch_composite_fwd_staged(raw, z, rays_d, ray_stride, noise, R, S, white_bkgd, rgb, disp, acc,
+                                                   depth, weights, alpha, (cudaStream_t)stream, &rc);
+  if (rc != GBN_OK) return rc;
+  if (done == R) return GBN_OK;
+  raw += done * S * 4; z += done * S; rays_d += done * ray_stride;
+  if (noise) noise += done * S;
+  rgb += done * 3; disp += done; acc += done; depth += done; weights += done * S;
+  if (alpha) alpha += done * S;
+  R -= done;
   const int grid = persistent_grid(R, 8);
 #define CALL(N) composite_fwd_kernel<N><<<grid, kThreads, 0, (cudaStream_t)stream>>>( \
       raw, z, rays_d, ray_stride, noise, R, S, white_bkgd, rgb, disp, acc, depth, weights, alpha)

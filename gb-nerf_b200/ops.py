@@ -147,6 +147,17 @@ class _Composite(torch.autograd.Function):
         return g_raw, None, None, None, None, None, None
 
 
+def composite_backward_raw(raw, z, rays_d, noise, white_bkgd, detach_weights, g_rgb, g_disp, g_acc, g_depth, g_weights=None):
+    """Kernel launch only: gradient wrt raw [R,S,4] given the output gradients (no autograd)."""
+    (rays_d,), pitch = _ray_views(rays_d)
+    R, S = z.shape
+    g_raw = torch.empty_like(raw)
+    _lib.call("gbn_composite_backward", _ptr(raw), _ptr(z), _ptr(rays_d), pitch, _ptr(noise), R, S, int(bool(white_bkgd)),
+              int(bool(detach_weights)), _ptr(g_rgb), _ptr(g_disp), _ptr(g_acc), _ptr(g_depth), _ptr(g_weights), _ptr(g_raw),
+              _stream())
+    return g_raw
+
+
 def composite(raw, z_vals, rays_d, noise=None, white_bkgd=False, detach_weights=False, need_alpha=False):
     """raw2outputs on the device: returns (rgb, disp, acc, weights, depth, alpha-or-None)."""
     rgb, disp, acc, weights, depth, alpha = _Composite.apply(raw, z_vals, rays_d, noise, white_bkgd, detach_weights,
