@@ -1,5 +1,7 @@
 // Companions of the tcgen05 MLP kernel: the weight pre-packer (nn.Linear fp32 -> UMMA shared-memory images)
 // and the per-ray view-direction bias of views_linears.0 (run_nerf_helpers.py:117-121).
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "common.cuh"
@@ -115,14 +117,26 @@ __global__ void __launch_bounds__(128) view_bias_kernel(const float* __restrict_
   }
 }
 
-int launch_view_bias(const uint8_t* packed, const MlpPlan& p, const float* viewdirs, int64_t stride,
-                     const float* emb, int64_t n, float* out, cudaStream_t stream) {
+int launch_view_bias_raw(const float* wdir, const float* bdir, const float* viewdirs, int64_t stride, const float* emb,
+                         int64_t n, float* out, cudaStream_t stream) {
   const int64_t groups = (n + kVbRays - 1) / kVbRays;
   const int grid = (int)(groups < kNumSMs * 8 ? groups : kNumSMs * 8);
-  view_bias_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const float*>(packed + p.off_wdir),
-                                             reinterpret_cast<const float*>(packed + p.off_bdir), viewdirs, stride, emb,
-                                             n, out);
+  view_bias_kernel<<<grid, 128, 0, stream>>>(wdir, bdir, viewdirs, stride, emb, n, out);
   return check_launch("view_bias_kernel");
+}
+
+int launch_view_bias(const uint8_t* packed, const MlpPlan& p, const float* viewdirs, int64_t stride,
+                     const float* emb, int64_t n, float* out, cudaStream_t stream) {
+  return launch_view_bias_raw(reinterpret_cast<const float*>(packed + p.off_wdir),
+                              reinterpret_cast<const float*>(packed + p.off_bdir), viewdirs, stride, emb, n, out, stream);
+}
+
+// TMEM-operand bf16 kernels (mlp_ts.cu); GBNERF_MLP_SS=1 selects the shared-memory-operand kernels instead
+size_t ts_packed_bytes(int bwd);
+int ts_prepack(const void* const* params, void* packed, int bwd, cudaStream_t st);
+bool mlp_use_ts() {
+  static const bool v = [] { const char* e = getenv("GBNERF_MLP_SS"); return !(e && e[0] == '1'); }();
+  return v;
 }
 
 static bool g_pack_init[64];
@@ -136,6 +150,9 @@ extern "C" int gbn_mlp_prepack_weights(const void* const* params, void* packed, 
   GBN_REQUIRE(precision >= 0 && precision < kNumPlans, "prepack: unknown precision/plan %d", precision);
   GBN_REQUIRE(params && packed, "prepack: null pointer");
   GBN_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 255) == 0, "prepack: packed buffer must be 256-byte aligned");
+  for (int i = 0; i < 2 * GBN_NUM_LINEAR; ++i) GBN_REQUIRE(params[i], "prepack: params[%d] is null", i);
+  if (precision != GBN_PRECISION_TF32 && mlp_use_ts())
+    return ts_prepack(params, packed, precision == GBN_PACK_BWD_BF16, (cudaStream_t)stream);
   ParamPtrs pp;
   for (int i = 0; i < GBN_NUM_LINEAR; ++i) {
     GBN_REQUIRE(params[2 * i] && params[2 * i + 1], "prepack: params[%d] is null", 2 * i);

@@ -500,6 +500,7 @@ static const MlpPlan& plan(int which) {
 }
 
 const MlpPlan& mlp_plan(int which) { return plan(which); }
+void mlp_get_trace(unsigned long long** buf, int* tile) { *buf = g_trace; *tile = g_trace_tile; }
 
 // per-device one-time setup: job tables -> constant memory, opt-in shared memory size
 static int ensure_device(cudaStream_t stream) {
@@ -526,6 +527,13 @@ static int ensure_device(cudaStream_t stream) {
 
 int launch_view_bias(const uint8_t* packed, const MlpPlan& p, const float* viewdirs, int64_t stride,
                      const float* emb, int64_t n, float* out, cudaStream_t stream);  // mlp_aux.cu
+bool mlp_use_ts();                                                                    // mlp_aux.cu
+size_t ts_packed_bytes(int bwd);                                                      // mlp_ts.cu
+int ts_forward(const void* packed, const float* ro, const float* rd, const float* vd, int64_t stride, const float* z,
+               const float* pts, const float* emb, int64_t R, int S, float* raw, void* workspace, void* stash,
+               cudaStream_t stream);
+int ts_backward_data(const void* packed_bwd, const float* g_raw, int64_t P, const void* stash_h, void* stash_g, void* workspace,
+                     cudaStream_t stream);
 
 static int run_mlp(const void* packed, int precision, const float* ro, const float* rd, const float* vd,
                    int64_t stride, const float* z, const float* pts, const float* emb, int64_t R, int S, float* raw,
@@ -539,6 +547,8 @@ static int run_mlp(const void* packed, int precision, const float* ro, const flo
               "mlp: raw / workspace must be 16-byte aligned");
   GBN_REQUIRE(stash == nullptr || precision == GBN_PRECISION_BF16, "mlp: the training stash exists for bf16 only");
   GBN_REQUIRE((reinterpret_cast<uintptr_t>(stash) & 127) == 0, "mlp: stash must be 128-byte aligned");
+  if (precision == GBN_PRECISION_BF16 && mlp_use_ts())
+    return ts_forward(packed, ro, rd, vd, stride, z, pts, emb, R, S, raw, workspace, stash, stream);
   int rc = ensure_device(stream);
   if (rc != GBN_OK) return rc;
   const MlpPlan& p = plan(precision);
@@ -569,6 +579,7 @@ using namespace gbn;
 
 extern "C" size_t gbn_mlp_packed_bytes(int precision) {
   if (precision < 0 || precision >= kNumPlans) return 0;
+  if (precision != GBN_PRECISION_TF32 && mlp_use_ts()) return ts_packed_bytes(precision == GBN_PACK_BWD_BF16);
   return mlp_plan(precision).total_bytes;
 }
 
@@ -611,6 +622,7 @@ extern "C" int gbn_mlp_backward_data(const void* packed_bwd, const float* g_raw,
                   ((reinterpret_cast<uintptr_t>(stash_h) | reinterpret_cast<uintptr_t>(stash_g)) & 127) == 0,
               "mlp_backward_data: misaligned buffer");
   cudaStream_t st = (cudaStream_t)stream;
+  if (mlp_use_ts()) return ts_backward_data(packed_bwd, g_raw, P, stash_h, stash_g, workspace, st);
   int rc = ensure_device(st);
   if (rc != GBN_OK) return rc;
   int* err = reinterpret_cast<int*>(workspace);

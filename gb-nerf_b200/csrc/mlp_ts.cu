@@ -1,0 +1,588 @@
+// bf16 NeRF MLP with the activations resident in TENSOR MEMORY (tcgen05.mma with the A operand in TMEM).
+// Same network, same roles and same drop-in entry points as mlp_tc.cu (run_nerf_helpers.py:75-129 fused with
+// run.py:2317 / run_nerf_helpers.py:23-53); see mlp_ts_layout.h for why this layout exists and for the job tables.
+//
+//   warp 0      weight producer: 32 KB slabs ([128 out x 128 in] bf16, K-major 128B-swizzle) L2 -> smem ring, bulk TMA
+//   warp 1      MMA issuer: per job 8 x tcgen05.mma (M=128, N=128, K=16), A from TMEM (or the shared-memory
+//               encoding block), B = weight slab, D = accumulator half in TMEM
+//   warp 2      TMEM allocator
+//   warps 4-7   per-tile input block (forward: points + positional encoding, backward: padded g_raw) -> smem
+//   warps 8-15  epilogue: accumulator half -> registers (tcgen05.ld) -> +bias/ReLU (or ReLU gate) -> bf16 ->
+//               tcgen05.st into the other A buffer (the next layer's operand) [+ training stash to HBM]
+#include <stdlib.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "mlp_ts_layout.h"
+#include "tc_ptx.cuh"
+
+namespace gbn {
+
+using namespace tc;
+
+__constant__ TsJob c_tsjobs[2][kTsMaxJobs];
+__constant__ TsStep c_tssteps[2][kTsMaxSteps];
+__constant__ TsPackJob c_tspack[2][kTsMaxJobs];
+
+constexpr int kTsThreads = 512;
+constexpr int kTsStages = 6;
+constexpr int kTsStageBytes = 32768;
+
+struct TsSmem {
+  static constexpr uint32_t enc = 0;
+  static constexpr uint32_t ring = enc + kBlkBytes;
+  static constexpr uint32_t bias = ring + kTsStages * kTsStageBytes;
+  static constexpr uint32_t bars = bias + kBiasFloats * 4;
+  static constexpr uint32_t w_full = bars;
+  static constexpr uint32_t w_empty = w_full + 8 * kTsStages;
+  static constexpr uint32_t acc_full = w_empty + 8 * kTsStages;     // [2]
+  static constexpr uint32_t a_ready = acc_full + 16;                // [buf][half]
+  static constexpr uint32_t enc_full = a_ready + 32;
+  static constexpr uint32_t enc_empty = enc_full + 8;
+  static constexpr uint32_t tile_done = enc_empty + 8;
+  static constexpr uint32_t order = tile_done + 8;
+  static constexpr uint32_t tmem_ptr = order + 8;
+  static constexpr uint32_t abort_flag = tmem_ptr + 4;
+  static constexpr uint32_t total = abort_flag + 4;
+  static constexpr uint32_t alloc = total + 1024;
+};
+
+struct TsArgs {
+  const uint8_t* packed;
+  const float* ro; const float* rd; const float* z; const float* pts; const float* emb;
+  const float* view_bias;
+  float* raw;                          // forward: out [P,4]; backward: gradient in
+  uint8_t* stash_h; uint8_t* stash_g;
+  int* err;
+  unsigned long long* trace;           // optional clock64 trace of CTA 0 (gbn_mlp_set_trace)
+  int trace_tile;
+  int64_t stride, P;
+  int S, njobs, nsteps;
+  int ready_per_tile[4];
+  int order_per_tile;
+};
+
+__device__ __forceinline__ void ts_wait(uint32_t bar, uint32_t parity, uint32_t abort_addr, int* err, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    uint32_t ab;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(ab) : "r"(abort_addr));
+    if (ab) return;
+    if (clock64() - t0 > kWatchdogCycles) {
+      atomicCAS(err, 0, code);
+      asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(abort_addr), "r"(1u));
+      return;
+    }
+  }
+}
+
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&w)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[8]), "r"(w[9]), "r"(w[10]),
+      "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void ts_st_global16(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs a) {
+  using L = TsSmem;
+  constexpr int PROG = BWD ? 1 : 0;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* const gen = smem_raw + (base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ntiles = (a.P + kTileRows - 1) / kTileRows;
+  const int my_tiles = (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  const uint32_t abort_addr = base + L::abort_flag;
+  const TsJob* jobs = c_tsjobs[PROG];
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kTsStages; ++i) { mbar_init(base + L::w_full + 8 * i, 1); mbar_init(base + L::w_empty + 8 * i, 1); }
+    mbar_init(base + L::acc_full, 1); mbar_init(base + L::acc_full + 8, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(base + L::a_ready + 8 * i, 256);
+    mbar_init(base + L::enc_full, 128);
+    mbar_init(base + L::enc_empty, 2);   // one commit from each of the two MMA warps
+    mbar_init(base + L::tile_done, 256);
+    mbar_init(base + L::order, 1);
+    *reinterpret_cast<volatile uint32_t*>(gen + L::abort_flag) = 0;
+    mbar_init_fence();
+  }
+  if (warp == 2) tmem_alloc(base + L::tmem_ptr, kTmemCols);
+  if constexpr (!BWD) {
+    const float* gb = reinterpret_cast<const float*>(a.packed + reinterpret_cast<const uint32_t*>(a.packed)[2]);
+    float* sb = reinterpret_cast<float*>(gen + L::bias);
+    for (int i = threadIdx.x; i < kBiasFloats; i += blockDim.x) sb[i] = __ldg(gb + i);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + L::tmem_ptr);
+
+  if (warp == 0) {
+    // =============================== weight producer ========================================================
+    uint32_t cnt = 0;
+    for (int t = 0; t < my_tiles; ++t)
+      for (int j = 0; j < a.njobs; ++j) {
+        const uint32_t s = cnt % kTsStages, par = (cnt / kTsStages) & 1;
+        ts_wait(base + L::w_empty + 8 * s, par ^ 1, abort_addr, a.err, 0x10000000 | j);
+        const uint32_t bytes = (uint32_t)jobs[j].w_bytes16 * 16;
+        const uint8_t* src = a.packed + jobs[j].w_off;
+        if (elect_one()) {
+          mbar_expect_tx(base + L::w_full + 8 * s, bytes);
+          tma_bulk_g2s(base + L::ring + s * kTsStageBytes, src, bytes, base + L::w_full + 8 * s);
+        }
+        __syncwarp();
+        ++cnt;
+      }
+  } else if (warp == 1 || warp == 3) {
+    // =============================== MMA issuers ===============================================================
+    // Two warps: warp 1 issues every job that accumulates into acc0, warp 3 those into acc1.  The halves are
+    // independent accumulators, so no ordering is needed between the two instruction streams; what it buys is that
+    // one warp's barrier waits / job bookkeeping (~500 cycles per job, the tensor queue is shallow) overlap the
+    // other's MMAs.  Each loop is warp-uniform; one elected lane issues.
+    const bool second = (warp == 3);
+    uint32_t cnt = 0;
+    constexpr int kAnyWait = TJ_WAIT_ENC | TJ_WAIT_TILE | TJ_WAIT_A0 | TJ_WAIT_A1;
+    const uint64_t adesc = smem_desc_sw128(base + L::enc);
+    TsJob nxt = jobs[0];
+    for (int t = 0; t < my_tiles; ++t)
+      for (int j = 0; j < a.njobs; ++j) {
+        const TsJob jb = nxt;
+        nxt = jobs[j + 1 < a.njobs ? j + 1 : 0];   // constant-memory fetch of the next job overlaps this one
+        if ((jb.d_col >= kTsAcc1) != second) { ++cnt; continue; }
+        unsigned long long* tr = (a.trace && blockIdx.x == 0 && t == a.trace_tile && lane == 0) ? a.trace : nullptr;
+        if (tr) tr[4 * j] = clock64();
+        if (jb.flags & kAnyWait) {
+          if (jb.flags & TJ_WAIT_ENC) ts_wait(base + L::enc_full, t & 1, abort_addr, a.err, 0x20000000 | j);
+          if ((jb.flags & TJ_WAIT_TILE) && t > 0) ts_wait(base + L::tile_done, (t - 1) & 1, abort_addr, a.err, 0x23000000 | j);
+          if (jb.flags & TJ_WAIT_A0) {
+            const int b = (jb.wait_buf & 1) * 2;
+            const uint32_t seq = (uint32_t)t * a.ready_per_tile[b] + ((jb.wait_buf >> 1) & 7);
+            ts_wait(base + L::a_ready + 8 * b, seq & 1, abort_addr, a.err, 0x21000000 | j);
+          }
+          if (jb.flags & TJ_WAIT_A1) {
+            const int b = (jb.wait_buf & 1) * 2 + 1;
+            const uint32_t seq = (uint32_t)t * a.ready_per_tile[b] + ((jb.wait_buf >> 4) & 7);
+            ts_wait(base + L::a_ready + 8 * b, seq & 1, abort_addr, a.err, 0x21800000 | j);
+          }
+        }
+        if (jb.flags & TJ_WAIT_ORDER) {
+          const uint32_t seq = (uint32_t)t * a.order_per_tile + ((jb.ksteps >> 4) & 7);
+          ts_wait(base + L::order, seq & 1, abort_addr, a.err, 0x24000000 | j);
+        }
+        const uint32_t s = cnt % kTsStages, par = (cnt / kTsStages) & 1;
+        if (tr) tr[4 * j + 1] = clock64();
+        ts_wait(base + L::w_full + 8 * s, par, abort_addr, a.err, 0x22000000 | j);
+        if (tr) tr[4 * j + 2] = clock64();
+        tc_fence_after_sync();
+        const uint32_t N = (uint32_t)jb.n16 * 16;
+        const uint64_t bd0 = smem_desc_sw128(base + L::ring + s * kTsStageBytes);
+        const uint64_t bd1 = bd0 + (uint64_t)(N * 8);                       // second K-block image: N rows x 128 B on
+        const uint32_t idesc = make_idesc(1, 128, N);
+        const uint32_t d = tmem + jb.d_col;
+        const uint32_t a_t = tmem + jb.a_col;
+        const uint32_t first = (jb.flags & TJ_FIRST) ? 0u : 1u;
+        const bool a_smem = (jb.flags & TJ_A_SMEM) != 0;
+        if (elect_one()) {
+          if (!a_smem && jb.nkb == 2) {          // the common job: 8 back-to-back MMAs, A from TMEM
+            umma_bf16_ts(d, a_t, bd0, idesc, first);
+            umma_bf16_ts(d, a_t + 8, bd0 + 2, idesc, 1u);
+            umma_bf16_ts(d, a_t + 16, bd0 + 4, idesc, 1u);
+            umma_bf16_ts(d, a_t + 24, bd0 + 6, idesc, 1u);
+            umma_bf16_ts(d, a_t + 32, bd1, idesc, 1u);
+            umma_bf16_ts(d, a_t + 40, bd1 + 2, idesc, 1u);
+            umma_bf16_ts(d, a_t + 48, bd1 + 4, idesc, 1u);
+            umma_bf16_ts(d, a_t + 56, bd1 + 6, idesc, 1u);
+          } else if (a_smem) {                   // encoding block (4 steps) / padded g_raw block (1 step)
+            umma_bf16(d, adesc, bd0, idesc, first);
+            if ((jb.ksteps & 7) == 4) {
+              umma_bf16(d, adesc + 2, bd0 + 2, idesc, 1u);
+              umma_bf16(d, adesc + 4, bd0 + 4, idesc, 1u);
+              umma_bf16(d, adesc + 6, bd0 + 6, idesc, 1u);
+            }
+          } else {                               // single K-block from TMEM (not used by the current plans)
+            umma_bf16_ts(d, a_t, bd0, idesc, first);
+            umma_bf16_ts(d, a_t + 8, bd0 + 2, idesc, 1u);
+            umma_bf16_ts(d, a_t + 16, bd0 + 4, idesc, 1u);
+            umma_bf16_ts(d, a_t + 24, bd0 + 6, idesc, 1u);
+          }
+          umma_commit(base + L::w_empty + 8 * s);
+          if (jb.flags & TJ_COMMIT_ENC) umma_commit(base + L::enc_empty);
+          if (jb.flags & TJ_COMMIT_ACC0) umma_commit(base + L::acc_full);
+          if (jb.flags & TJ_COMMIT_ACC1) umma_commit(base + L::acc_full + 8);
+          if (jb.flags & TJ_SIGNAL_ORDER) mbar_arrive(base + L::order);
+        }
+        __syncwarp();
+        if (tr) tr[4 * j + 3] = clock64();
+        ++cnt;
+      }
+  } else if (warp >= 4 && warp < 8) {
+    // =============================== per-tile input block: thread == row =======================================
+    const int row = threadIdx.x - 128;
+    const uint32_t row_off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int64_t tile = blockIdx.x + (int64_t)t * gridDim.x;
+      const int64_t p = tile * kTileRows + row;
+      uint32_t w[32];   // 64 bf16 channels of this row
+      if constexpr (BWD) {
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p < a.P) g = ld_stream4(reinterpret_cast<const float4*>(a.raw) + p);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) w[i] = 0u;
+        w[0] = pack_bf16(g.x, g.y);
+        w[1] = pack_bf16(g.z, g.w);
+      } else {
+        float e[64];
+        if (p < a.P) {
+          if (a.emb != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 63; ++i) e[i] = __ldg(a.emb + p * GBN_EMB_CH + i);
+          } else {
+            float x[3];
+            if (a.pts != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 3; ++i) x[i] = __ldg(a.pts + p * 3 + i);
+            } else {
+              const int64_t r = p / a.S;
+              const float zz = __ldg(a.z + p);
+#pragma unroll
+              for (int i = 0; i < 3; ++i)
+                x[i] = __fadd_rn(__ldg(a.ro + r * a.stride + i), __fmul_rn(__ldg(a.rd + r * a.stride + i), zz));
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              float sc[20];
+              posenc_axis<10>(x[i], sc);
+              e[i] = x[i];
+#pragma unroll
+              for (int k = 0; k < 10; ++k) { e[3 + 6 * k + i] = sc[2 * k]; e[6 + 6 * k + i] = sc[2 * k + 1]; }
+            }
+          }
+          e[63] = 0.f;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) e[i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) w[i] = pack_bf16(e[2 * i], e[2 * i + 1]);
+      }
+      if (t > 0) ts_wait(base + L::enc_empty, (t - 1) & 1, abort_addr, a.err, 0x30000000 | t);
+      uint8_t* gblk = nullptr;
+      if constexpr (BWD) gblk = a.stash_g + (size_t)tile * kStashTileBytes + (size_t)kGRaw * kBlkBytes + row_off;
+      else if (a.stash_h != nullptr) gblk = a.stash_h + (size_t)tile * kStashTileBytes + (size_t)kHEnc * kBlkBytes + row_off;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t off = ((uint32_t)(c ^ (row & 7)) << 4);
+        st_smem16(base + L::enc + row_off + off, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+        if (gblk != nullptr) ts_st_global16(gblk + off, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(base + L::enc_full);
+    }
+  } else if (warp >= 8) {
+    // =============================== epilogue: thread == row, warpgroup == 64-channel slice of the half ========
+    const int wg = (warp - 8) >> 2;
+    const int row = ((warp & 3) << 5) | lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) << 5) << 16);
+    const uint32_t row_off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
+    const float* sbias = reinterpret_cast<const float*>(gen + L::bias);
+    uint32_t accpar = 0;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int64_t tile = blockIdx.x + (int64_t)t * gridDim.x;
+      const int64_t p = tile * kTileRows + row;
+      float sigma_acc = 0.f;
+      uint8_t* const tile_h = a.stash_h != nullptr ? a.stash_h + (size_t)tile * kStashTileBytes + row_off : nullptr;
+      uint8_t* const tile_g = BWD ? a.stash_g + (size_t)tile * kStashTileBytes + row_off : nullptr;
+      unsigned long long* tr = (a.trace && blockIdx.x == 0 && t == a.trace_tile && (threadIdx.x & 127) == 0)
+                                   ? a.trace + 960 + wg * 128 : nullptr;
+      for (int si = 0; si < a.nsteps; ++si) {
+        const TsStep st = c_tssteps[PROG][si];
+        if (tr) tr[si * 4] = clock64();
+        ts_wait(base + L::acc_full + 8 * st.acc, (accpar >> st.acc) & 1, abort_addr, a.err, 0x40000000 | (si << 8) | wg);
+        accpar ^= 1u << st.acc;
+        if (tr) tr[si * 4 + 1] = clock64();
+        tc_fence_after_sync();
+        if (st.mode == EPI_OUT) {
+          if (wg == 0) {
+            uint32_t c[4];
+            tmem_ld4(lane_addr + kTsAcc0 + kTsColRgb, c);
+            tmem_ld_wait();
+            if (p < a.P) {
+              float4 o;
+              o.x = __uint_as_float(c[0]) + sbias[kBiasRgb + 0];
+              o.y = __uint_as_float(c[1]) + sbias[kBiasRgb + 1];
+              o.z = __uint_as_float(c[2]) + sbias[kBiasRgb + 2];
+              o.w = sigma_acc + sbias[kBiasAlpha];
+              st_stream4(reinterpret_cast<float4*>(a.raw) + p, o);
+            }
+          }
+          continue;
+        }
+        const float* vb = nullptr;
+        if (st.mode == EPI_VBIAS_RELU) {
+          const int64_t pr = p < a.P ? p : a.P - 1;
+          vb = a.view_bias + (pr / a.S) * 128;
+          if (wg == 0) {
+            uint32_t sv;
+            tmem_ld1(lane_addr + kTsAcc0 + kTsColAlpha, sv);
+            tmem_ld_wait();
+            sigma_acc = __uint_as_float(sv);
+          }
+        }
+        const bool relu = (st.mode == EPI_BIAS_RELU || st.mode == EPI_VBIAS_RELU);
+        const uint32_t acc_col = (st.acc ? kTsAcc1 : kTsAcc0) + 64u * wg;
+        const int ch0 = 128 * st.out_half + 64 * wg;            // first of this thread's 64 channels in the layer
+        const uint32_t out_col = (st.out_buf ? kTsA1 : kTsA0) + 64u * st.out_half + 32u * wg;
+        uint8_t* gout = nullptr;
+        if (st.out_blk != 0xff) {
+          if constexpr (BWD) gout = tile_g + (size_t)(st.out_blk + wg) * kBlkBytes;
+          else if (tile_h != nullptr) gout = tile_h + (size_t)(st.out_blk + wg) * kBlkBytes;
+        }
+        // both 32-channel groups in flight at once: two tcgen05.ld, one wait, then the arithmetic, two tcgen05.st
+        uint4 hm[2][4];
+        if constexpr (BWD) {
+          if (st.mode == EPI_MASK) {
+            const uint8_t* hb = tile_h + (size_t)(st.mask_blk + wg) * kBlkBytes;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              hm[c >> 2][c & 3] = __ldg(reinterpret_cast<const uint4*>(hb + ((uint32_t)(c ^ (row & 7)) << 4)));
+          }
+        }
+        uint32_t v[2][32];
+        tmem_ld32(lane_addr + acc_col, v[0]);
+        tmem_ld32(lane_addr + acc_col + 32, v[1]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          float f[32];
+          if constexpr (BWD) {
+            if (st.mode == EPI_MASK) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const uint32_t hw[4] = {hm[g][c].x, hm[g][c].y, hm[g][c].z, hm[g][c].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  f[c * 8 + 2 * i] = ((hw[i] & 0x7fffu) != 0u) ? __uint_as_float(v[g][c * 8 + 2 * i]) : 0.f;
+                  f[c * 8 + 2 * i + 1] = ((hw[i] & 0x7fff0000u) != 0u) ? __uint_as_float(v[g][c * 8 + 2 * i + 1]) : 0.f;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[g][i]);
+            }
+          } else if (st.mode == EPI_VBIAS_RELU) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(vb + ch0 + 32 * g + i));
+              f[i] = __uint_as_float(v[g][i]) + bb.x; f[i + 1] = __uint_as_float(v[g][i + 1]) + bb.y;
+              f[i + 2] = __uint_as_float(v[g][i + 2]) + bb.z; f[i + 3] = __uint_as_float(v[g][i + 3]) + bb.w;
+            }
+          } else {
+            const float4* bp = reinterpret_cast<const float4*>(sbias + st.bias_off + ch0 + 32 * g);
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 bb = bp[i >> 2];
+              f[i] = __uint_as_float(v[g][i]) + bb.x; f[i + 1] = __uint_as_float(v[g][i + 1]) + bb.y;
+              f[i + 2] = __uint_as_float(v[g][i + 2]) + bb.z; f[i + 3] = __uint_as_float(v[g][i + 3]) + bb.w;
+            }
+          }
+          uint32_t w[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) w[i] = relu ? pack_bf16_relu(f[2 * i], f[2 * i + 1]) : pack_bf16(f[2 * i], f[2 * i + 1]);
+          if (!st.no_act) tmem_st16(lane_addr + out_col + 16 * g, w);
+          if (gout != nullptr) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              ts_st_global16(gout + ((uint32_t)((g * 4 + c) ^ (row & 7)) << 4), w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+          }
+        }
+        if (!st.no_act) {
+          tmem_st_wait();
+          tc_fence_before_sync();
+          mbar_arrive(base + L::a_ready + 8 * (st.out_buf * 2 + st.out_half));
+        }
+        if (tr) tr[si * 4 + 2] = clock64();
+      }
+      tc_fence_before_sync();
+      mbar_arrive(base + L::tile_done);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, kTmemCols);
+}
+
+// ---- weight pre-pack for the TS plans: slab = nkb K-block images of [rows x 128 B], K-major, 128B swizzle ------------
+struct TsParamPtrs {
+  const float* w[GBN_NUM_LINEAR];
+  const float* b[GBN_NUM_LINEAR];
+};
+struct TsPackHeader {
+  uint32_t magic, plan, off_bias, off_wdir, off_bdir, total_bytes, njobs, pad;
+};
+
+__global__ void __launch_bounds__(256) ts_prepack_kernel(TsParamPtrs pp, uint8_t* __restrict__ out, int njobs, TsPackHeader hdr,
+                                                         int prog) {
+  if ((int)blockIdx.x < njobs) {
+    const TsPackJob q = c_tspack[prog][blockIdx.x];
+    const float* W = pp.w[q.layer];
+    const int kcols = 64 * q.nkb;
+    for (int i = threadIdx.x; i < q.rows * kcols; i += blockDim.x) {
+      const int n = q.transpose ? i % q.rows : i / kcols;
+      const int k = q.transpose ? i / q.rows : i - n * kcols;
+      const int ks = k - (int)q.koff;
+      float v = 0.f;
+      if (n < q.rows_valid && ks >= 0 && ks < q.cols_valid)
+        v = q.transpose ? __ldg(W + (size_t)(q.row0 + ks) * q.ld + q.col0 + n) : __ldg(W + (size_t)(q.row0 + n) * q.ld + q.col0 + ks);
+      const int kb = k >> 6, kk = k & 63;
+      uint8_t* dst = out + q.w_off + (size_t)kb * q.rows * 128 + sw128_offset((uint32_t)n, (uint32_t)(kk >> 3)) + (kk & 7) * 2;
+      *reinterpret_cast<uint16_t*>(dst) = (uint16_t)(pack_bf16(v, 0.f) & 0xffff);
+    }
+    return;
+  }
+  if (threadIdx.x == 0) *reinterpret_cast<TsPackHeader*>(out) = hdr;
+  float* bias = reinterpret_cast<float*>(out + hdr.off_bias);
+  for (int i = threadIdx.x; i < kBiasFloats; i += blockDim.x) {
+    float v = 0.f;
+    if (i < kBiasFeat) v = pp.b[i >> 8][i & 255];
+    else if (i < kBiasAlpha) v = pp.b[LIN_FEATURE][i - kBiasFeat];
+    else if (i == kBiasAlpha) v = pp.b[LIN_ALPHA][0];
+    else if (i >= kBiasRgb && i < kBiasRgb + 3) v = pp.b[LIN_RGB][i - kBiasRgb];
+    bias[i] = v;
+  }
+  float* wdir = reinterpret_cast<float*>(out + hdr.off_wdir);
+  for (int i = threadIdx.x; i < 128 * 27; i += blockDim.x) {
+    const int j = i / 27, c = i - j * 27;
+    wdir[i] = pp.w[LIN_VIEWS][(size_t)j * 283 + 256 + c];
+  }
+  float* bdir = reinterpret_cast<float*>(out + hdr.off_bdir);
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) bdir[i] = pp.b[LIN_VIEWS][i];
+}
+
+// =========================================================================================================
+// host side (called from the C ABI entry points in mlp_tc.cu / mlp_aux.cu)
+// =========================================================================================================
+static std::once_flag g_ts_once;
+static TsPlan g_ts_plan[2];
+static bool g_ts_init[64];
+static std::mutex g_ts_mutex;
+
+const TsPlan& ts_plan(int bwd) {
+  std::call_once(g_ts_once, [] {
+    const char* e = getenv("GBNERF_TS_STAGGER");
+    const bool stagger = e && e[0] == '1';
+    g_ts_plan[0] = make_ts_plan(kTsFwd, stagger);
+    g_ts_plan[1] = make_ts_plan(kTsBwd, stagger);
+  });
+  return g_ts_plan[bwd ? 1 : 0];
+}
+
+static int ts_ensure_device(cudaStream_t stream) {
+  int dev = 0;
+  GBN_CUDA(cudaGetDevice(&dev));
+  GBN_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
+  std::lock_guard<std::mutex> lk(g_ts_mutex);
+  if (g_ts_init[dev]) return GBN_OK;
+  for (int pr = 0; pr < 2; ++pr) {
+    const TsPlan& p = ts_plan(pr);
+    GBN_REQUIRE((int)p.jobs.size() <= kTsMaxJobs && (int)p.steps.size() <= kTsMaxSteps, "TS table overflow");
+    GBN_CUDA(cudaMemcpyToSymbolAsync(c_tsjobs, p.jobs.data(), p.jobs.size() * sizeof(TsJob), pr * kTsMaxJobs * sizeof(TsJob),
+                                     cudaMemcpyHostToDevice, stream));
+    GBN_CUDA(cudaMemcpyToSymbolAsync(c_tssteps, p.steps.data(), p.steps.size() * sizeof(TsStep),
+                                     pr * kTsMaxSteps * sizeof(TsStep), cudaMemcpyHostToDevice, stream));
+    GBN_CUDA(cudaMemcpyToSymbolAsync(c_tspack, p.pack.data(), p.pack.size() * sizeof(TsPackJob),
+                                     pr * kTsMaxJobs * sizeof(TsPackJob), cudaMemcpyHostToDevice, stream));
+  }
+  GBN_CUDA(cudaFuncSetAttribute(nerf_mlp_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TsSmem::alloc));
+  GBN_CUDA(cudaFuncSetAttribute(nerf_mlp_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TsSmem::alloc));
+  g_ts_init[dev] = true;
+  return GBN_OK;
+}
+
+size_t ts_packed_bytes(int bwd) { return ts_plan(bwd).total_bytes; }
+
+int ts_prepack(const void* const* params, void* packed, int bwd, cudaStream_t st) {
+  int rc = ts_ensure_device(st);
+  if (rc != GBN_OK) return rc;
+  TsParamPtrs pp;
+  for (int i = 0; i < GBN_NUM_LINEAR; ++i) {
+    pp.w[i] = static_cast<const float*>(params[2 * i]);
+    pp.b[i] = static_cast<const float*>(params[2 * i + 1]);
+  }
+  const TsPlan& p = ts_plan(bwd);
+  TsPackHeader hdr{0x4e425473u, (uint32_t)p.id, p.off_bias, p.off_wdir, p.off_bdir, p.total_bytes, (uint32_t)p.jobs.size(), 0};
+  const int njobs = (int)p.jobs.size();
+  ts_prepack_kernel<<<njobs + 1, 256, 0, st>>>(pp, static_cast<uint8_t*>(packed), njobs, hdr, bwd ? 1 : 0);
+  return check_launch("ts_prepack_kernel");
+}
+
+void mlp_get_trace(unsigned long long** buf, int* tile);   // mlp_tc.cu
+int launch_view_bias_raw(const float* wdir, const float* bdir, const float* viewdirs, int64_t stride, const float* emb,
+                         int64_t n, float* out, cudaStream_t stream);  // mlp_aux.cu
+
+int ts_forward(const void* packed, const float* ro, const float* rd, const float* vd, int64_t stride, const float* z,
+               const float* pts, const float* emb, int64_t R, int S, float* raw, void* workspace, void* stash,
+               cudaStream_t stream) {
+  int rc = ts_ensure_device(stream);
+  if (rc != GBN_OK) return rc;
+  const TsPlan& p = ts_plan(0);
+  int* err = reinterpret_cast<int*>(workspace);
+  float* vbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + 256);
+  GBN_CUDA(cudaMemsetAsync(err, 0, 256, stream));
+  const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
+  rc = launch_view_bias_raw(reinterpret_cast<const float*>(pk + p.off_wdir), reinterpret_cast<const float*>(pk + p.off_bdir), vd,
+                            stride, emb, R, vbias, stream);
+  if (rc != GBN_OK) return rc;
+  TsArgs a{};
+  a.packed = pk; a.ro = ro; a.rd = rd; a.z = z; a.pts = pts; a.emb = emb; a.view_bias = vbias; a.raw = raw;
+  a.stash_h = static_cast<uint8_t*>(stash); a.err = err; a.stride = stride; a.P = R * S; a.S = S;
+  a.njobs = (int)p.jobs.size(); a.nsteps = (int)p.steps.size();
+  for (int i = 0; i < 4; ++i) a.ready_per_tile[i] = p.ready_per_tile[i];
+  a.order_per_tile = p.order_per_tile;
+  mlp_get_trace(&a.trace, &a.trace_tile);
+  const int64_t ntiles = (a.P + kTileRows - 1) / kTileRows;
+  const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
+  nerf_mlp_ts_kernel<false><<<grid, kTsThreads, TsSmem::alloc, stream>>>(a);
+  return check_launch("nerf_mlp_ts_kernel");
+}
+
+int ts_backward_data(const void* packed_bwd, const float* g_raw, int64_t P, const void* stash_h, void* stash_g, void* workspace,
+                     cudaStream_t stream) {
+  int rc = ts_ensure_device(stream);
+  if (rc != GBN_OK) return rc;
+  const TsPlan& p = ts_plan(1);
+  int* err = reinterpret_cast<int*>(workspace);
+  GBN_CUDA(cudaMemsetAsync(err, 0, 256, stream));
+  TsArgs a{};
+  a.packed = reinterpret_cast<const uint8_t*>(packed_bwd);
+  a.raw = const_cast<float*>(g_raw);
+  a.stash_h = static_cast<uint8_t*>(const_cast<void*>(stash_h));
+  a.stash_g = static_cast<uint8_t*>(stash_g);
+  a.err = err; a.P = P; a.S = 1;
+  a.njobs = (int)p.jobs.size(); a.nsteps = (int)p.steps.size();
+  for (int i = 0; i < 4; ++i) a.ready_per_tile[i] = p.ready_per_tile[i];
+  a.order_per_tile = p.order_per_tile;
+  const int64_t ntiles = (P + kTileRows - 1) / kTileRows;
+  const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
+  nerf_mlp_ts_kernel<true><<<grid, kTsThreads, TsSmem::alloc, stream>>>(a);
+  return check_launch("nerf_mlp_ts_kernel<bwd>");
+}
+
+}  // namespace gbn

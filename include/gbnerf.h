@@ -121,6 +121,11 @@ size_t gbn_mlp_stash_bytes(int64_t P);
  * (layout: tools/mlp_trace.py).  NULL switches tracing off.  Not part of the reference-facing surface. */
 int gbn_mlp_set_trace(void* buf, int tile);
 
+/* Diagnostic: one 128x128x64 bf16 tcgen05.mma with the A operand in TMEM (A [128,64] bf16 row-major, Bimg a 16 KB
+ * K-major 128B-swizzled tile image, D [128,128] fp32 out).  Used by tests/test_gpu_mlp_render.py to pin the TMEM
+ * operand layout the MLP kernel relies on. */
+int gbn_debug_ts_mma(const void* A, const void* Bimg, float* D, int a_col, int col_per_kstep, void* stream);
+
 /* Same network on pre-embedded rows (NeRF.forward's own signature): emb [P,90] fp32 -> raw [P,4]. */
 int gbn_mlp_forward_embedded(const void* packed, int precision, const float* emb, int64_t P, float* raw,
                              void* workspace, void* stash, void* stream);
