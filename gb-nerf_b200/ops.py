@@ -334,9 +334,12 @@ class _Mlp(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, module, mode, a0, a1, a2, a3, *params):
+    def forward(ctx, module, mode, grad_mode, a0, a1, a2, a3, *params):
         packed = module.packed_weights()
-        need_grad = any(ctx.needs_input_grad[6:])
+        # needs_input_grad mirrors requires_grad of the inputs even under torch.no_grad(), and grad mode is always off
+        # inside forward(): the caller's grad mode comes in as an argument, or every inference call would write the
+        # training stash
+        need_grad = grad_mode and any(ctx.needs_input_grad[7:])
         ctx.native = need_grad and module.precision == "bf16" and mode in ("rays", "pts")
         stash = None
         if mode == "rays":
@@ -374,7 +377,7 @@ class _Mlp(torch.autograd.Function):
                                             ctx.shapes)
             ctx.module.last_workspace_bwd = ws
             ctx.stash = None
-            return (None, None, None, None, None, None, *grads)
+            return (None, None, None, None, None, None, None, *grads)
         saved = ctx.saved_tensors
         ins, params = saved[:ctx.n_in], saved[ctx.n_in:]
         with torch.enable_grad():
@@ -392,19 +395,19 @@ class _Mlp(torch.autograd.Function):
                 (emb,) = ins
             out = _torch_mlp(ps, emb)
             grads = torch.autograd.grad(out, ps, g_raw.reshape(out.shape))
-        return (None, None, None, None, None, None, *grads)
+        return (None, None, None, None, None, None, None, *grads)
 
 
 def mlp_rays(module, rays_o, rays_d, viewdirs, z):
-    return _Mlp.apply(module, "rays", rays_o, rays_d, viewdirs, z, *module.param_list())
+    return _Mlp.apply(module, "rays", torch.is_grad_enabled(), rays_o, rays_d, viewdirs, z, *module.param_list())
 
 
 def mlp_points(module, pts, viewdirs):
-    return _Mlp.apply(module, "pts", pts, viewdirs, None, None, *module.param_list())
+    return _Mlp.apply(module, "pts", torch.is_grad_enabled(), pts, viewdirs, None, None, *module.param_list())
 
 
 def mlp_embedded(module, emb):
-    return _Mlp.apply(module, "emb", emb, None, None, None, *module.param_list())
+    return _Mlp.apply(module, "emb", torch.is_grad_enabled(), emb, None, None, None, *module.param_list())
 
 
 # --------------------------------------------------------------------------------------------------------- #
