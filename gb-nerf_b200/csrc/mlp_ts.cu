@@ -26,27 +26,35 @@ __constant__ TsStep c_tssteps[2][kTsMaxSteps];
 __constant__ TsPackJob c_tspack[2][kTsMaxJobs];
 
 constexpr int kTsThreads = 512;
-constexpr int kTsStages = 6;
 constexpr int kTsStageBytes = 32768;
 
-struct TsSmem {
+// Shared memory: input block | weight ring | stash-out staging (2 block images, one per epilogue warpgroup) |
+// [backward: gate staging, 2 x 2 block images] | [forward: bias table] | barriers
+template <bool BWD>
+struct TsSmemT {
+  static constexpr int NST = BWD ? 3 : 5;
   static constexpr uint32_t enc = 0;
   static constexpr uint32_t ring = enc + kBlkBytes;
-  static constexpr uint32_t bias = ring + kTsStages * kTsStageBytes;
-  static constexpr uint32_t bars = bias + kBiasFloats * 4;
+  static constexpr uint32_t ostage = ring + NST * kTsStageBytes;
+  static constexpr uint32_t mstage = ostage + 2 * kBlkBytes;
+  static constexpr uint32_t bias = mstage + (BWD ? 4 * kBlkBytes : 0);
+  static constexpr uint32_t bars = bias + (BWD ? 0 : kBiasFloats * 4);
   static constexpr uint32_t w_full = bars;
-  static constexpr uint32_t w_empty = w_full + 8 * kTsStages;
-  static constexpr uint32_t acc_full = w_empty + 8 * kTsStages;     // [2]
+  static constexpr uint32_t w_empty = w_full + 8 * NST;
+  static constexpr uint32_t acc_full = w_empty + 8 * NST;           // [2]
   static constexpr uint32_t a_ready = acc_full + 16;                // [buf][half]
   static constexpr uint32_t enc_full = a_ready + 32;
   static constexpr uint32_t enc_empty = enc_full + 8;
   static constexpr uint32_t tile_done = enc_empty + 8;
   static constexpr uint32_t order = tile_done + 8;
-  static constexpr uint32_t tmem_ptr = order + 8;
+  static constexpr uint32_t m_full = order + 8;                     // [2]
+  static constexpr uint32_t m_empty = m_full + 16;                  // [2]
+  static constexpr uint32_t tmem_ptr = m_empty + 16;
   static constexpr uint32_t abort_flag = tmem_ptr + 4;
   static constexpr uint32_t total = abort_flag + 4;
   static constexpr uint32_t alloc = total + 1024;
 };
+static_assert(TsSmemT<false>::alloc <= 232448 && TsSmemT<true>::alloc <= 232448, "shared memory budget");
 
 struct TsArgs {
   const uint8_t* packed;
@@ -99,9 +107,24 @@ __device__ __forceinline__ void ts_st_global16(void* p, uint32_t a, uint32_t b, 
   asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// bulk async store shared -> global (one 16 KB stash block image per call), tracked by bulk async-groups
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void wg_bar(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory"); }
+__device__ __forceinline__ uint4 ld_smem16(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+
 template <bool BWD>
 __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs a) {
-  using L = TsSmem;
+  using L = TsSmemT<BWD>;
+  constexpr int kTsStages = L::NST;
   constexpr int PROG = BWD ? 1 : 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -120,6 +143,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
     mbar_init(base + L::enc_empty, 2);   // one commit from each of the two MMA warps
     mbar_init(base + L::tile_done, 256);
     mbar_init(base + L::order, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(base + L::m_full + 8 * i, 1); mbar_init(base + L::m_empty + 8 * i, 256); }
     *reinterpret_cast<volatile uint32_t*>(gen + L::abort_flag) = 0;
     mbar_init_fence();
   }
@@ -232,6 +256,31 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
         if (tr) tr[4 * j + 3] = clock64();
         ++cnt;
       }
+  } else if (warp == 2) {
+    // =============================== backward: gate producer ====================================================
+    // streams the two H-stash block images whose sign gates the next epilogue step into a double-buffered staging
+    // area (one 32 KB bulk copy per step), so the epilogue reads them from shared memory instead of issuing
+    // row-strided 16-byte global loads
+    if constexpr (BWD) {
+      uint32_t mc = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const int64_t tile = blockIdx.x + (int64_t)t * gridDim.x;
+        for (int si = 0; si < a.nsteps; ++si) {
+          const TsStep st = c_tssteps[PROG][si];
+          if (st.mode != EPI_MASK) continue;
+          const uint32_t b = mc & 1, par = (mc >> 1) & 1;
+          ts_wait(base + L::m_empty + 8 * b, par ^ 1, abort_addr, a.err, 0x60000000 | si);
+          if (elect_one()) {
+            mbar_expect_tx(base + L::m_full + 8 * b, 2 * kBlkBytes);
+            tma_bulk_g2s(base + L::mstage + b * 2 * kBlkBytes,
+                         a.stash_h + (size_t)tile * kStashTileBytes + (size_t)st.mask_blk * kBlkBytes, 2 * kBlkBytes,
+                         base + L::m_full + 8 * b);
+          }
+          __syncwarp();
+          ++mc;
+        }
+      }
+    }
   } else if (warp >= 4 && warp < 8) {
     // =============================== per-tile input block: thread == row =======================================
     const int row = threadIdx.x - 128;
@@ -302,7 +351,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) << 5) << 16);
     const uint32_t row_off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
     const float* sbias = reinterpret_cast<const float*>(gen + L::bias);
-    uint32_t accpar = 0;
+    const bool storer = (threadIdx.x & 127) == 0;      // issues this warpgroup's bulk stash stores
+    const uint32_t my_ostage = base + L::ostage + wg * kBlkBytes;
+    uint32_t accpar = 0, mc = 0;
     for (int t = 0; t < my_tiles; ++t) {
       const int64_t tile = blockIdx.x + (int64_t)t * gridDim.x;
       const int64_t p = tile * kTileRows + row;
@@ -349,19 +400,26 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
         const uint32_t acc_col = (st.acc ? kTsAcc1 : kTsAcc0) + 64u * wg;
         const int ch0 = 128 * st.out_half + 64 * wg;            // first of this thread's 64 channels in the layer
         const uint32_t out_col = (st.out_buf ? kTsA1 : kTsA0) + 64u * st.out_half + 32u * wg;
-        uint8_t* gout = nullptr;
+        uint8_t* gout = nullptr;   // this warpgroup's 16 KB block image of the result in the stash
         if (st.out_blk != 0xff) {
-          if constexpr (BWD) gout = tile_g + (size_t)(st.out_blk + wg) * kBlkBytes;
-          else if (tile_h != nullptr) gout = tile_h + (size_t)(st.out_blk + wg) * kBlkBytes;
+          if constexpr (BWD) gout = a.stash_g + (size_t)tile * kStashTileBytes + (size_t)(st.out_blk + wg) * kBlkBytes;
+          else if (a.stash_h != nullptr) gout = a.stash_h + (size_t)tile * kStashTileBytes + (size_t)(st.out_blk + wg) * kBlkBytes;
+        }
+        if (gout != nullptr) {       // the previous bulk store must have finished reading the staging block
+          if (storer) bulk_wait_read0();
+          wg_bar(wg);
         }
         // both 32-channel groups in flight at once: two tcgen05.ld, one wait, then the arithmetic, two tcgen05.st
         uint4 hm[2][4];
         if constexpr (BWD) {
           if (st.mode == EPI_MASK) {
-            const uint8_t* hb = tile_h + (size_t)(st.mask_blk + wg) * kBlkBytes;
+            const uint32_t b = mc & 1;
+            ts_wait(base + L::m_full + 8 * b, (mc >> 1) & 1, abort_addr, a.err, 0x41000000 | (si << 8) | wg);
+            const uint32_t hb = base + L::mstage + (b * 2 + wg) * kBlkBytes + row_off;
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-              hm[c >> 2][c & 3] = __ldg(reinterpret_cast<const uint4*>(hb + ((uint32_t)(c ^ (row & 7)) << 4)));
+            for (int c = 0; c < 8; ++c) hm[c >> 2][c & 3] = ld_smem16(hb + ((uint32_t)(c ^ (row & 7)) << 4));
+            mbar_arrive(base + L::m_empty + 8 * b);
+            ++mc;
           }
         }
         uint32_t v[2][32];
@@ -409,8 +467,14 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
           if (gout != nullptr) {
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-              ts_st_global16(gout + ((uint32_t)((g * 4 + c) ^ (row & 7)) << 4), w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+              st_smem16(my_ostage + row_off + ((uint32_t)((g * 4 + c) ^ (row & 7)) << 4), w[4 * c], w[4 * c + 1], w[4 * c + 2],
+                        w[4 * c + 3]);
           }
+        }
+        if (gout != nullptr) {       // block image complete in shared memory -> one 16 KB bulk store per warpgroup
+          fence_proxy_async_smem();
+          wg_bar(wg);
+          if (storer) bulk_s2g(gout, my_ostage, kBlkBytes);
         }
         if (!st.no_act) {
           tmem_st_wait();
@@ -422,6 +486,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
       tc_fence_before_sync();
       mbar_arrive(base + L::tile_done);
     }
+    if (storer) bulk_wait0();
   }
 
   tc_fence_before_sync();
@@ -510,8 +575,8 @@ static int ts_ensure_device(cudaStream_t stream) {
     GBN_CUDA(cudaMemcpyToSymbolAsync(c_tspack, p.pack.data(), p.pack.size() * sizeof(TsPackJob),
                                      pr * kTsMaxJobs * sizeof(TsPackJob), cudaMemcpyHostToDevice, stream));
   }
-  GBN_CUDA(cudaFuncSetAttribute(nerf_mlp_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TsSmem::alloc));
-  GBN_CUDA(cudaFuncSetAttribute(nerf_mlp_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TsSmem::alloc));
+  GBN_CUDA(cudaFuncSetAttribute(nerf_mlp_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TsSmemT<false>::alloc));
+  GBN_CUDA(cudaFuncSetAttribute(nerf_mlp_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TsSmemT<true>::alloc));
   g_ts_init[dev] = true;
   return GBN_OK;
 }
@@ -559,7 +624,7 @@ int ts_forward(const void* packed, const float* ro, const float* rd, const float
   mlp_get_trace(&a.trace, &a.trace_tile);
   const int64_t ntiles = (a.P + kTileRows - 1) / kTileRows;
   const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
-  nerf_mlp_ts_kernel<false><<<grid, kTsThreads, TsSmem::alloc, stream>>>(a);
+  nerf_mlp_ts_kernel<false><<<grid, kTsThreads, TsSmemT<false>::alloc, stream>>>(a);
   return check_launch("nerf_mlp_ts_kernel");
 }
 
@@ -581,7 +646,7 @@ int ts_backward_data(const void* packed_bwd, const float* g_raw, int64_t P, cons
   a.order_per_tile = p.order_per_tile;
   const int64_t ntiles = (P + kTileRows - 1) / kTileRows;
   const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
-  nerf_mlp_ts_kernel<true><<<grid, kTsThreads, TsSmem::alloc, stream>>>(a);
+  nerf_mlp_ts_kernel<true><<<grid, kTsThreads, TsSmemT<true>::alloc, stream>>>(a);
   return check_launch("nerf_mlp_ts_kernel<bwd>");
 }
 
