@@ -25,11 +25,12 @@ constexpr int kPlanBwd = 2;
 
 // Training stash (bf16 only): per 128-point tile, 16 KB blocks that are byte images of the kernel's shared-memory
 // K-blocks ([128 rows x 128 B], 128-byte swizzle), so every consumer moves them with plain bulk copies.
-//   H (written by the forward): h_l block b -> 4*l + b (l = 0..7) | feature -> 32..35 | hv -> 36,37 | enc -> 38
+//   H (written by the forward): h_l block b -> 4*l + b (l = 0..7) | feature -> 32..35 | hv -> 36,37 | enc -> 38 |
+//                               per-point view-direction encoding (27 of 64 channels) -> 39
 //   G (written by dgrad): g_hv -> 0,1 | g_feature -> 2..5 | g_l block b -> 6 + 4*l + b | g_raw (padded) -> 38
-constexpr int kStashBlocks = 39;
+constexpr int kStashBlocks = 40;
 constexpr size_t kStashTileBytes = (size_t)kStashBlocks * kBlkBytes;
-constexpr int kHFeat = 32, kHHv = 36, kHEnc = 38;
+constexpr int kHFeat = 32, kHHv = 36, kHEnc = 38, kHDir = 39;
 constexpr int kGHv = 0, kGFeat = 2, kGLayer0 = 6, kGRaw = 38;
 
 enum : uint8_t { EPI_BIAS_RELU = 0, EPI_BIAS = 1, EPI_VBIAS_RELU = 2, EPI_OUT = 3, EPI_MASK = 4, EPI_PLAIN = 5 };

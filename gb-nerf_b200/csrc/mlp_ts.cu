@@ -60,6 +60,7 @@ struct TsArgs {
   const uint8_t* packed;
   const float* ro; const float* rd; const float* z; const float* pts; const float* emb;
   const float* view_bias;
+  const float* vd;                     // forward with stash: view directions [R,3] (pitch `stride`)
   float* raw;                          // forward: out [P,4]; backward: gradient in
   uint8_t* stash_h; uint8_t* stash_g;
   int* err;
@@ -343,6 +344,36 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
       }
       fence_proxy_async_smem();
       mbar_arrive(base + L::enc_full);
+      if constexpr (!BWD) {
+        // training: the per-point view-direction encoding (B operand of the wgrad item for views_linears.0[:, 256:])
+        if (a.stash_h != nullptr && a.vd != nullptr) {
+          float e[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) e[i] = 0.f;
+          if (p < a.P) {
+            const int64_t r = p / a.S;
+#pragma unroll
+            for (int ax = 0; ax < 3; ++ax) {
+              const float x = __ldg(a.vd + r * a.stride + ax);
+              float sc[8];
+              posenc_axis<4>(x, sc);
+              e[ax] = x;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) { e[3 + 6 * k + ax] = sc[2 * k]; e[6 + 6 * k + ax] = sc[2 * k + 1]; }
+            }
+          }
+          uint8_t* db = a.stash_h + (size_t)tile * kStashTileBytes + (size_t)kHDir * kBlkBytes + row_off;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint32_t q[4] = {0u, 0u, 0u, 0u};
+            if (c < 4) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) q[i] = pack_bf16(e[8 * c + 2 * i], e[8 * c + 2 * i + 1]);
+            }
+            ts_st_global16(db + ((uint32_t)(c ^ (row & 7)) << 4), q[0], q[1], q[2], q[3]);
+          }
+        }
+      }
     }
   } else if (warp >= 8) {
     // =============================== epilogue: thread == row, warpgroup == 64-channel slice of the half ========
@@ -616,7 +647,7 @@ int ts_forward(const void* packed, const float* ro, const float* rd, const float
                             stride, emb, R, vbias, stream);
   if (rc != GBN_OK) return rc;
   TsArgs a{};
-  a.packed = pk; a.ro = ro; a.rd = rd; a.z = z; a.pts = pts; a.emb = emb; a.view_bias = vbias; a.raw = raw;
+  a.packed = pk; a.ro = ro; a.rd = rd; a.z = z; a.pts = pts; a.emb = emb; a.view_bias = vbias; a.vd = vd; a.raw = raw;
   a.stash_h = static_cast<uint8_t*>(stash); a.err = err; a.stride = stride; a.P = R * S; a.S = S;
   a.njobs = (int)p.jobs.size(); a.nsteps = (int)p.steps.size();
   for (int i = 0; i < 4; ++i) a.ready_per_tile[i] = p.ready_per_tile[i];

@@ -38,7 +38,7 @@ struct WgItem {
   uint16_t cta_begin, cta_end;   // CTAs [begin, end) of the 148 share this item's point tiles
 };
 
-constexpr int kWgItems = 13;
+constexpr int kWgItems = 14;
 constexpr int kWgThreads = 384;      // warp 0 producer, 1 MMA, 2 TMEM alloc, 4-7 bias sums, 8-11 flush
 constexpr int kWgStages = 3;
 constexpr int kWgHalf = 8192;        // bytes of the 64-point half of a 16 KB block image
@@ -282,7 +282,9 @@ __global__ void __launch_bounds__(128) viewdir_grad_kernel(const uint8_t* __rest
 static bool g_wg_init[64];
 static std::mutex g_wg_mutex;
 
-static void make_items(WgItem* items) {
+bool mlp_use_ts();  // mlp_aux.cu
+
+static void make_items(WgItem* items, bool with_dir) {
   int n = 0;
   auto add = [&](int a_blk, int m_blocks, int b_blk, int n_blocks, int layer, int do_bias, int ld, int col0, int n_valid,
                  int head = 0) {
@@ -301,14 +303,17 @@ static void make_items(WgItem* items) {
   add(kGHv, 2, kHFeat, 4, LIN_VIEWS, 1, 283, 0, 256);                                    // views_linears.0[:, :256]
   add(kGRaw, 2, 4 * 7, 4, LIN_ALPHA, 1, 256, 0, 256, 1);                                 // alpha_linear
   add(kGRaw, 2, kHHv, 2, LIN_RGB, 1, 128, 0, 128, 2);                                    // rgb_linear
+  add(kGHv, 2, kHDir, 1, LIN_VIEWS, 0, 283, 256, 27);                                    // views_linears.0[:, 256:283]
   // CTAs in proportion to the bytes each item streams per tile
+  const int nitems = with_dir ? kWgItems : kWgItems - 1;   // the direction item needs the forward's dir stash block
   int cost[kWgItems], total = 0;
-  for (int i = 0; i < kWgItems; ++i) { cost[i] = items[i].m_blocks + items[i].n_blocks; total += cost[i]; }
+  for (int i = 0; i < nitems; ++i) { cost[i] = items[i].m_blocks + items[i].n_blocks; total += cost[i]; }
   int given = 0, share[kWgItems];
-  for (int i = 0; i < kWgItems; ++i) { share[i] = kNumSMs * cost[i] / total; if (share[i] < 1) share[i] = 1; given += share[i]; }
-  for (int i = 0; given < kNumSMs; i = (i + 1) % kWgItems) if (cost[i] == 8) { ++share[i]; ++given; }
+  for (int i = 0; i < nitems; ++i) { share[i] = kNumSMs * cost[i] / total; if (share[i] < 1) share[i] = 1; given += share[i]; }
+  for (int i = 0; given < kNumSMs; i = (i + 1) % nitems) if (cost[i] == 8) { ++share[i]; ++given; }
   int c = 0;
-  for (int i = 0; i < kWgItems; ++i) { items[i].cta_begin = (uint16_t)c; c += share[i]; items[i].cta_end = (uint16_t)c; }
+  for (int i = 0; i < nitems; ++i) { items[i].cta_begin = (uint16_t)c; c += share[i]; items[i].cta_end = (uint16_t)c; }
+  for (int i = nitems; i < kWgItems; ++i) { items[i].cta_begin = items[i].cta_end = 0xffff; }
 }
 
 }  // namespace gbn
@@ -331,7 +336,7 @@ extern "C" int gbn_mlp_backward_weights(const void* stash_h, const void* stash_g
     std::lock_guard<std::mutex> lk(g_wg_mutex);
     if (!g_wg_init[dev]) {
       WgItem items[kWgItems];
-      make_items(items);
+      make_items(items, mlp_use_ts());
       GBN_CUDA(cudaMemcpyToSymbolAsync(c_wg, items, sizeof(items), 0, cudaMemcpyHostToDevice, st));
       GBN_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WgSmem::alloc));
       g_wg_init[dev] = true;
@@ -352,6 +357,7 @@ extern "C" int gbn_mlp_backward_weights(const void* stash_h, const void* stash_g
   wgrad_tc_kernel<<<kNumSMs, kWgThreads, WgSmem::alloc, st>>>(a);
   int rc = check_launch("wgrad_tc_kernel");
   if (rc != GBN_OK) return rc;
+  if (mlp_use_ts()) return GBN_OK;   // direction columns came from the tensor-core item
   const int64_t groups = (R + kVdRays - 1) / kVdRays;
   const int vgrid = (int)(groups < 2 * kNumSMs ? groups : 2 * kNumSMs);
   viewdir_grad_kernel<<<vgrid, 128, 0, st>>>(a.stash_g, viewdirs, ray_stride, R, S, a.w[LIN_VIEWS]);

@@ -94,6 +94,6 @@ def test_argument_validation(lib):
     assert l.gbn_sample_pdf_merge(None, None, None, 4, 2, 4, None, None, None, None) == 1
     assert l.gbn_mlp_forward(None, 5, None, None, None, 3, None, None, 4, 4, None, None, None, None) == 1
     assert l.gbn_mlp_backward_data(None, None, 4, None, None, None, None) == 1
-    assert l.gbn_mlp_stash_bytes(129) == 2 * 39 * 16384 and l.gbn_mlp_stash_bytes(0) == 0
+    assert l.gbn_mlp_stash_bytes(129) == 2 * 40 * 16384 and l.gbn_mlp_stash_bytes(0) == 0
     assert l.gbn_mlp_packed_bytes(2) > 1_000_000    # transposed bf16 weights for the dgrad pass
     assert l.gbn_composite_forward(None, None, None, 3, None, 0, 64, 1, None, None, None, None, None, None, None) == 0

@@ -7,7 +7,7 @@ from oracle import nerf_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-N_BLOCKS = 39
+N_BLOCKS = 40
 H_FEAT, H_HV, H_ENC = 32, 36, 38
 G_HV, G_FEAT, G_L0, G_RAW = 0, 2, 6, 38
 
