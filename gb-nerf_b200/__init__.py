@@ -6,12 +6,14 @@ Layout
   ops.py       tensor-level operators + autograd wiring over the ABI
   helpers.py   drop-in for DS_NeRF/run_nerf_helpers.py (NeRF, get_embedder, sample_pdf, raw2outputs, get_rays …)
   run.py       drop-in for run.py's create_nerf / render / batchify_rays / render_rays / run_network / batchify
+  loss.py      drop-in for DS_NeRF/loss.py (SigmaLoss)
   dist.py      ray sharding across one-process-per-GPU ranks, gradient all-reduce, image gather
 
 The package directory is ``gb-nerf_b200`` (the project's name); import it as ``gbnerf_b200`` through the
 alias module at the repository root.  There is no CPU path: every operator raises without a CUDA device.
 """
-from . import _lib, ops, helpers, run, dist  # noqa: F401
+from . import _lib, ops, helpers, run, dist, loss  # noqa: F401
+from .loss import SigmaLoss  # noqa: F401
 from .helpers import (NeRF, Embedder, get_embedder, get_rays, get_rays_np, ndc_rays, sample_pdf,  # noqa: F401
                       raw2outputs, img2mse, mse2psnr, to8b)
 from .run import (batchify, run_network, batchify_rays, render, create_nerf, render_rays, install, NetworkQuery)  # noqa: F401

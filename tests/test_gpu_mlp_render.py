@@ -231,3 +231,33 @@ def test_create_nerf_api(G, tmp_path):
     rgb2, *_ = G.render(O.H_FULL, O.W_FULL, O.FOCAL, chunk=32768, rays=torch.stack([rays[:, 0:3], rays[:, 3:6]]),
                         **dict(kw_test, near=O.NEAR, far=O.FAR))
     assert torch.isfinite(rgb2).all()
+
+
+def test_sigma_loss_vs_reference_formula(G, params):
+    """SigmaLoss (DS_NeRF/loss.py:15-44): extra march near -> depth, same random tensors injected on both sides."""
+    import torch.nn.functional as F
+    nets, nq = build_path(G, params, "tf32")
+    R, S = 150, 64
+    rays = O.synthetic_rays(R, seed=21)
+    g = torch.Generator().manual_seed(3)
+    depths = 2.0 + 3.0 * torch.rand(R, generator=g)
+    t_rand = torch.rand(R, S, generator=g)
+    noise = torch.randn(R, S, generator=g)
+    sl = G.SigmaLoss(S, 1.0, 1.0)
+    r = rays.cuda()
+    with torch.no_grad():
+        got = sl.calculate_loss(r[:, 0:3], r[:, 3:6], r[:, 8:11], r[:, 6:7], r[:, 7:8], depths.cuda(), nq, nets[1],
+                                _randoms={"t_rand": t_rand.cuda(), "noise": noise.cuda()})
+    # reference formula on the oracle
+    z = O.stratified_z(rays[:, 6:7], depths[:, None], S, False, t_rand)
+    pts = rays[:, None, 0:3] + rays[:, None, 3:6] * z[:, :, None]
+    raw = O.run_network(params[1], pts, rays[:, 8:11])
+    sigma = F.relu(raw[..., 3] + noise)
+    want = -torch.exp(sigma[:, -1]) / (torch.sum(torch.exp(sigma), 1) + 1)
+    assert got.shape == (R,)
+    torch.testing.assert_close(got.cpu(), want, rtol=2e-3, atol=2e-4)
+    # and through render_rays when the batch carries depths (run.py:2372-2375)
+    batch = torch.cat([rays[:, :8], depths[:, None], rays[:, 8:11]], -1).cuda()
+    ret = G.render_rays(batch, nets[0], nq, 64, lindisp=True, perturb=0., N_importance=64, network_fine=nets[1],
+                        white_bkgd=True, raw_noise_std=0., sigma_loss=G.SigmaLoss(S, 0., 0.))
+    assert ret["sigma_loss"].shape == (R,) and torch.isfinite(ret["sigma_loss"]).all()
