@@ -2,6 +2,10 @@
 // and the per-ray view-direction bias of views_linears.0 (run_nerf_helpers.py:117-121).
 #include <stdlib.h>
 
+#ifndef GBN_DEFAULT_MLP_VARIANT
+#define GBN_DEFAULT_MLP_VARIANT 1
+#endif
+
 #include <mutex>
 
 #include "common.cuh"
@@ -134,10 +138,23 @@ int launch_view_bias(const uint8_t* packed, const MlpPlan& p, const float* viewd
 // TMEM-operand bf16 kernels (mlp_ts.cu); GBNERF_MLP_SS=1 selects the shared-memory-operand kernels instead
 size_t ts_packed_bytes(int bwd);
 int ts_prepack(const void* const* params, void* packed, int bwd, cudaStream_t st);
-bool mlp_use_ts() {
-  static const bool v = [] { const char* e = getenv("GBNERF_MLP_SS"); return !(e && e[0] == '1'); }();
+size_t tq_packed_bytes(int bwd);
+int tq_prepack(const void* const* params, void* packed, int bwd, cudaStream_t st);
+// bf16 kernel family: 0 = shared-memory operands (mlp_tc.cu), 1 = TMEM operands in halves (mlp_ts.cu),
+// 2 = TMEM operands in quarters (mlp_tq.cu).  GBNERF_MLP=ss|ts|tq overrides the default (GBNERF_MLP_SS=1 == ss).
+int mlp_variant() {
+  static const int v = [] {
+    const char* e = getenv("GBNERF_MLP");
+    if (e && e[0] == 's') return 0;
+    if (e && e[0] == 't' && e[1] == 's') return 1;
+    if (e && e[0] == 't' && e[1] == 'q') return 2;
+    const char* s = getenv("GBNERF_MLP_SS");
+    if (s && s[0] == '1') return 0;
+    return GBN_DEFAULT_MLP_VARIANT;
+  }();
   return v;
 }
+bool mlp_use_ts() { return mlp_variant() != 0; }
 
 static bool g_pack_init[64];
 static std::mutex g_pack_mutex;
@@ -151,7 +168,9 @@ extern "C" int gbn_mlp_prepack_weights(const void* const* params, void* packed, 
   GBN_REQUIRE(params && packed, "prepack: null pointer");
   GBN_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 255) == 0, "prepack: packed buffer must be 256-byte aligned");
   for (int i = 0; i < 2 * GBN_NUM_LINEAR; ++i) GBN_REQUIRE(params[i], "prepack: params[%d] is null", i);
-  if (precision != GBN_PRECISION_TF32 && mlp_use_ts())
+  if (precision != GBN_PRECISION_TF32 && mlp_variant() == 2)
+    return tq_prepack(params, packed, precision == GBN_PACK_BWD_BF16, (cudaStream_t)stream);
+  if (precision != GBN_PRECISION_TF32 && mlp_variant() == 1)
     return ts_prepack(params, packed, precision == GBN_PACK_BWD_BF16, (cudaStream_t)stream);
   ParamPtrs pp;
   for (int i = 0; i < GBN_NUM_LINEAR; ++i) {

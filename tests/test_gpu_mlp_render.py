@@ -261,3 +261,80 @@ def test_sigma_loss_vs_reference_formula(G, params):
     ret = G.render_rays(batch, nets[0], nq, 64, lindisp=True, perturb=0., N_importance=64, network_fine=nets[1],
                         white_bkgd=True, raw_noise_std=0., sigma_loss=G.SigmaLoss(S, 0., 0.))
     assert ret["sigma_loss"].shape == (R,) and torch.isfinite(ret["sigma_loss"]).all()
+
+
+# ---- API behaviour of the drop-in functions (run.py:1624-1748, 2235-2381) ----------------------------------------- #
+def test_render_from_c2w_and_options(G, params):
+    """render(c2w=...) generates rays like get_rays (helpers:251-262); N_importance=0, lindisp/white_bkgd off,
+    need_alpha, detach_weights, patch and c2w_staticcam all follow the reference's branches."""
+    nets, nq = build_path(G, params, "tf32")
+    c2w = O.synthetic_c2w().cuda()
+    H, W, focal = 12, 16, 14.0
+    kw = dict(network_query_fn=nq, perturb=0., N_importance=64, network_fine=nets[1], N_samples=64, network_fn=nets[0],
+              white_bkgd=True, raw_noise_std=0., lindisp=True)
+    with torch.no_grad():
+        rgb, disp, acc, depth, ex = G.render(H, W, focal, chunk=64, c2w=c2w[:3, :4], near=O.NEAR, far=O.FAR, use_viewdirs=True,
+                                             ndc=False, **kw)
+        assert rgb.shape == (H, W, 3) and disp.shape == (H, W) and ex["weights"].shape == (H, W, 128)
+        # same thing through explicit rays
+        o, d = O.get_rays(H, W, focal, O.synthetic_c2w())
+        rgb2, *_ = G.render(H, W, focal, chunk=1000, rays=torch.stack([o.reshape(-1, 3), d.reshape(-1, 3)]).cuda(), near=O.NEAR,
+                            far=O.FAR, use_viewdirs=True, ndc=False, **kw)
+        torch.testing.assert_close(rgb.reshape(-1, 3), rgb2, rtol=1e-4, atol=1e-5)
+        # oracle on the same rays (coarse-only, linear depth sampling, black background)
+        rays = O.pack_rays(o, d, O.NEAR, O.FAR)
+        kw0 = dict(kw, N_importance=0, white_bkgd=False, lindisp=False)
+        r0, d0, a0, z0, e0 = G.render(H, W, focal, chunk=50, c2w=c2w[:3, :4], near=O.NEAR, far=O.FAR, use_viewdirs=True, ndc=False,
+                                      retraw=True, **kw0)
+        want = O.render(rays, chunk=64, p_coarse=params[0], p_fine=None, n_samples=64, n_importance=0, lindisp=False,
+                        white_bkgd=False, retraw=True)
+        assert set(e0) == {"weights", "z_vals", "raw"}
+        assert (r0.reshape(-1, 3).cpu() - want["rgb_map"]).abs().max().item() < TOL["tf32"]
+        assert (e0["z_vals"].reshape(-1, 64).cpu() - want["z_vals"]).abs().max().item() < 1e-5
+        # a patch of the frame == the same pixels of the full frame
+        p_rgb, *_ = G.render(H, W, focal, chunk=64, c2w=c2w[:3, :4], near=O.NEAR, far=O.FAR, use_viewdirs=True, ndc=False,
+                             patch=(2, 3, 5, 6), **kw)
+        torch.testing.assert_close(p_rgb, rgb[2:7, 3:9], rtol=1e-4, atol=1e-5)
+        # need_alpha adds alpha / alpha0; with N_importance == 0 the reference raises (undefined alpha0, run.py:2365)
+        *_, ea = G.render(H, W, focal, chunk=64, c2w=c2w[:3, :4], near=O.NEAR, far=O.FAR, use_viewdirs=True, ndc=False,
+                          need_alpha=True, **kw)
+        assert ea["alpha"].shape == (H, W, 128) and ea["alpha0"].shape == (H, W, 64)
+    with pytest.raises(NameError):
+        G.render(H, W, focal, chunk=64, c2w=c2w[:3, :4], near=O.NEAR, far=O.FAR, use_viewdirs=True, ndc=False, need_alpha=True,
+                 **dict(kw, N_importance=0))
+
+
+def test_ndc_and_foreign_network_fallback(G, params):
+    """ndc=True runs ndc_rays (helpers:285-302) before packing; run_network keeps the reference's generic route
+    (embed, concatenate, netchunk slices) for a network that is not the package's NeRF."""
+    nets, nq = build_path(G, params, "tf32")
+    H, W, focal = 8, 10, 9.0
+    c2w = O.synthetic_c2w()
+    o, d = O.get_rays(H, W, focal, c2w)
+    on, dn = O.ndc_rays(H, W, focal, 1., o, d)
+    got_o, got_d = G.ndc_rays(H, W, focal, 1., o.cuda(), d.cuda())
+    torch.testing.assert_close(got_o.cpu(), on, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(got_d.cpu(), dn, rtol=1e-5, atol=1e-6)
+    with torch.no_grad():
+        rgb, *_ = G.render(H, W, focal, chunk=64, c2w=c2w.cuda()[:3, :4], near=0., far=1., use_viewdirs=True, ndc=True,
+                           network_query_fn=nq, perturb=0., N_importance=0, network_fine=None, N_samples=32, network_fn=nets[0],
+                           white_bkgd=False, raw_noise_std=0.)
+    assert rgb.shape == (H, W, 3) and torch.isfinite(rgb).all()
+
+    class Foreign(torch.nn.Module):           # anything callable on [P, 90] -> [P, 4]
+        def __init__(self, p):
+            super().__init__()
+            self.p = {k: v.cuda() for k, v in p.items()}
+
+        def forward(self, x):
+            return O.mlp_forward(self.p, x)
+
+    rays = O.synthetic_rays(20, seed=3)
+    z = O.stratified_z(rays[:, 6:7], rays[:, 7:8], 16, True)
+    pts = (rays[:, None, 0:3] + rays[:, None, 3:6] * z[:, :, None]).cuda()
+    with torch.no_grad():
+        raw_f = G.run_network(pts, rays[:, 8:11].cuda(), Foreign(params[0]), nq.embed_fn, nq.embeddirs_fn, netchunk=100)
+        raw_n = G.run_network(pts, rays[:, 8:11].cuda(), nets[0], nq.embed_fn, nq.embeddirs_fn)
+    assert raw_f.shape == (20, 16, 4)
+    assert (raw_f - raw_n).abs().max().item() < TOL["tf32"]
+    assert G.batchify(lambda t: t * 2, None)(torch.ones(3)).sum().item() == 6
