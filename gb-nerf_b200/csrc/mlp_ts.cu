@@ -32,13 +32,14 @@ constexpr int kTsStageBytes = 32768;
 // [backward: gate staging, 2 x 2 block images] | [forward: bias table] | barriers
 template <bool BWD>
 struct TsSmemT {
-  static constexpr int NST = BWD ? 3 : 5;
+  static constexpr int NST = BWD ? 3 : 4;
   static constexpr uint32_t enc = 0;
-  static constexpr uint32_t ring = enc + kBlkBytes;
+  static constexpr uint32_t dir = enc + kBlkBytes;                       // forward only: view-direction encoding block
+  static constexpr uint32_t ring = dir + (BWD ? 0 : kBlkBytes);
   static constexpr uint32_t ostage = ring + NST * kTsStageBytes;
   static constexpr uint32_t mstage = ostage + 2 * kBlkBytes;
   static constexpr uint32_t bias = mstage + (BWD ? 4 * kBlkBytes : 0);
-  static constexpr uint32_t bars = bias + (BWD ? 0 : kBiasFloats * 4);
+  static constexpr uint32_t bars = bias + (BWD ? 0 : kTsBiasFloats * 4);
   static constexpr uint32_t w_full = bars;
   static constexpr uint32_t w_empty = w_full + 8 * NST;
   static constexpr uint32_t acc_full = w_empty + 8 * NST;           // [2]
@@ -49,7 +50,9 @@ struct TsSmemT {
   static constexpr uint32_t order = tile_done + 8;
   static constexpr uint32_t m_full = order + 8;                     // [2]
   static constexpr uint32_t m_empty = m_full + 16;                  // [2]
-  static constexpr uint32_t tmem_ptr = m_empty + 16;
+  static constexpr uint32_t dir_full = m_empty + 16;
+  static constexpr uint32_t dir_empty = dir_full + 8;
+  static constexpr uint32_t tmem_ptr = dir_empty + 8;
   static constexpr uint32_t abort_flag = tmem_ptr + 4;
   static constexpr uint32_t total = abort_flag + 4;
   static constexpr uint32_t alloc = total + 1024;
@@ -145,6 +148,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
     mbar_init(base + L::tile_done, 256);
     mbar_init(base + L::order, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(base + L::m_full + 8 * i, 1); mbar_init(base + L::m_empty + 8 * i, 256); }
+    mbar_init(base + L::dir_full, 128);
+    mbar_init(base + L::dir_empty, 1);
     *reinterpret_cast<volatile uint32_t*>(gen + L::abort_flag) = 0;
     mbar_init_fence();
   }
@@ -152,7 +157,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
   if constexpr (!BWD) {
     const float* gb = reinterpret_cast<const float*>(a.packed + reinterpret_cast<const uint32_t*>(a.packed)[2]);
     float* sb = reinterpret_cast<float*>(gen + L::bias);
-    for (int i = threadIdx.x; i < kBiasFloats; i += blockDim.x) sb[i] = __ldg(gb + i);
+    for (int i = threadIdx.x; i < kTsBiasFloats; i += blockDim.x) sb[i] = __ldg(gb + i);
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -183,8 +188,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
     // other's MMAs.  Each loop is warp-uniform; one elected lane issues.
     const bool second = (warp == 3);
     uint32_t cnt = 0;
-    constexpr int kAnyWait = TJ_WAIT_ENC | TJ_WAIT_TILE | TJ_WAIT_A0 | TJ_WAIT_A1;
-    const uint64_t adesc = smem_desc_sw128(base + L::enc);
+    constexpr int kAnyWait = TJ_WAIT_ENC | TJ_WAIT_TILE | TJ_WAIT_A0 | TJ_WAIT_A1 | TJ_WAIT_DIR;
+    const uint64_t adesc_enc = smem_desc_sw128(base + L::enc);
+    const uint64_t adesc_dir = smem_desc_sw128(base + L::dir);
     TsJob nxt = jobs[0];
     for (int t = 0; t < my_tiles; ++t)
       for (int j = 0; j < a.njobs; ++j) {
@@ -195,6 +201,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
         if (tr) tr[4 * j] = clock64();
         if (jb.flags & kAnyWait) {
           if (jb.flags & TJ_WAIT_ENC) ts_wait(base + L::enc_full, t & 1, abort_addr, a.err, 0x20000000 | j);
+          if (jb.flags & TJ_WAIT_DIR) ts_wait(base + L::dir_full, t & 1, abort_addr, a.err, 0x20800000 | j);
           if ((jb.flags & TJ_WAIT_TILE) && t > 0) ts_wait(base + L::tile_done, (t - 1) & 1, abort_addr, a.err, 0x23000000 | j);
           if (jb.flags & TJ_WAIT_A0) {
             const int b = (jb.wait_buf & 1) * 2;
@@ -224,6 +231,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
         const uint32_t a_t = tmem + jb.a_col;
         const uint32_t first = (jb.flags & TJ_FIRST) ? 0u : 1u;
         const bool a_smem = (jb.flags & TJ_A_SMEM) != 0;
+        const uint64_t adesc = (jb.flags & TJ_A_DIR) ? adesc_dir : adesc_enc;
         if (elect_one()) {
           if (!a_smem && jb.nkb == 2) {          // the common job: 8 back-to-back MMAs, A from TMEM
             umma_bf16_ts(d, a_t, bd0, idesc, first);
@@ -236,8 +244,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
             umma_bf16_ts(d, a_t + 56, bd1 + 6, idesc, 1u);
           } else if (a_smem) {                   // encoding block (4 steps) / padded g_raw block (1 step)
             umma_bf16(d, adesc, bd0, idesc, first);
+            if ((jb.ksteps & 7) >= 2) umma_bf16(d, adesc + 2, bd0 + 2, idesc, 1u);
             if ((jb.ksteps & 7) == 4) {
-              umma_bf16(d, adesc + 2, bd0 + 2, idesc, 1u);
               umma_bf16(d, adesc + 4, bd0 + 4, idesc, 1u);
               umma_bf16(d, adesc + 6, bd0 + 6, idesc, 1u);
             }
@@ -249,6 +257,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
           }
           umma_commit(base + L::w_empty + 8 * s);
           if (jb.flags & TJ_COMMIT_ENC) umma_commit(base + L::enc_empty);
+          if (jb.flags & TJ_COMMIT_DIR) umma_commit(base + L::dir_empty);
           if (jb.flags & TJ_COMMIT_ACC0) umma_commit(base + L::acc_full);
           if (jb.flags & TJ_COMMIT_ACC1) umma_commit(base + L::acc_full + 8);
           if (jb.flags & TJ_SIGNAL_ORDER) mbar_arrive(base + L::order);
@@ -345,12 +354,16 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
       fence_proxy_async_smem();
       mbar_arrive(base + L::enc_full);
       if constexpr (!BWD) {
-        // training: the per-point view-direction encoding (B operand of the wgrad item for views_linears.0[:, 256:])
-        if (a.stash_h != nullptr && a.vd != nullptr) {
-          float e[32];
+        // view-direction encoding (27 of 64 channels): A operand of the direction columns of views_linears.0 and,
+        // in training, the B operand of their wgrad item
+        float e[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) e[i] = 0.f;
-          if (p < a.P) {
+        for (int i = 0; i < 32; ++i) e[i] = 0.f;
+        if (p < a.P) {
+          if (a.emb != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 27; ++i) e[i] = __ldg(a.emb + p * GBN_EMB_CH + GBN_PTS_CH + i);
+          } else {
             const int64_t r = p / a.S;
 #pragma unroll
             for (int ax = 0; ax < 3; ++ax) {
@@ -362,17 +375,22 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
               for (int k = 0; k < 4; ++k) { e[3 + 6 * k + ax] = sc[2 * k]; e[6 + 6 * k + ax] = sc[2 * k + 1]; }
             }
           }
-          uint8_t* db = a.stash_h + (size_t)tile * kStashTileBytes + (size_t)kHDir * kBlkBytes + row_off;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            uint32_t q[4] = {0u, 0u, 0u, 0u};
-            if (c < 4) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) q[i] = pack_bf16(e[8 * c + 2 * i], e[8 * c + 2 * i + 1]);
-            }
-            ts_st_global16(db + ((uint32_t)(c ^ (row & 7)) << 4), q[0], q[1], q[2], q[3]);
-          }
         }
+        if (t > 0) ts_wait(base + L::dir_empty, (t - 1) & 1, abort_addr, a.err, 0x31000000 | t);
+        uint8_t* db = a.stash_h != nullptr ? a.stash_h + (size_t)tile * kStashTileBytes + (size_t)kHDir * kBlkBytes + row_off : nullptr;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint32_t q[4] = {0u, 0u, 0u, 0u};
+          if (c < 4) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) q[i] = pack_bf16(e[8 * c + 2 * i], e[8 * c + 2 * i + 1]);
+          }
+          const uint32_t off = ((uint32_t)(c ^ (row & 7)) << 4);
+          st_smem16(base + L::dir + row_off + off, q[0], q[1], q[2], q[3]);
+          if (db != nullptr) ts_st_global16(db + off, q[0], q[1], q[2], q[3]);
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(base + L::dir_full);
       }
     }
   } else if (warp >= 8) {
@@ -402,9 +420,11 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
         tc_fence_after_sync();
         if (st.mode == EPI_OUT) {
           if (wg == 0) {
-            uint32_t c[4];
+            uint32_t c[4], sv;
             tmem_ld4(lane_addr + kTsAcc0 + kTsColRgb, c);
+            tmem_ld1(lane_addr + kTsAcc0 + kTsColAlpha, sv);
             tmem_ld_wait();
+            sigma_acc = __uint_as_float(sv);
             if (p < a.P) {
               float4 o;
               o.x = __uint_as_float(c[0]) + sbias[kBiasRgb + 0];
@@ -416,18 +436,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
           }
           continue;
         }
-        const float* vb = nullptr;
-        if (st.mode == EPI_VBIAS_RELU) {
-          const int64_t pr = p < a.P ? p : a.P - 1;
-          vb = a.view_bias + (pr / a.S) * 128;
-          if (wg == 0) {
-            uint32_t sv;
-            tmem_ld1(lane_addr + kTsAcc0 + kTsColAlpha, sv);
-            tmem_ld_wait();
-            sigma_acc = __uint_as_float(sv);
-          }
-        }
-        const bool relu = (st.mode == EPI_BIAS_RELU || st.mode == EPI_VBIAS_RELU);
+        const bool relu = (st.mode == EPI_BIAS_RELU);
         const uint32_t acc_col = (st.acc ? kTsAcc1 : kTsAcc0) + 64u * wg;
         const int ch0 = 128 * st.out_half + 64 * wg;            // first of this thread's 64 channels in the layer
         const uint32_t out_col = (st.out_buf ? kTsA1 : kTsA0) + 64u * st.out_half + 32u * wg;
@@ -474,13 +483,6 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[g][i]);
-            }
-          } else if (st.mode == EPI_VBIAS_RELU) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(vb + ch0 + 32 * g + i));
-              f[i] = __uint_as_float(v[g][i]) + bb.x; f[i + 1] = __uint_as_float(v[g][i + 1]) + bb.y;
-              f[i + 2] = __uint_as_float(v[g][i + 2]) + bb.z; f[i + 3] = __uint_as_float(v[g][i + 3]) + bb.w;
             }
           } else {
             const float4* bp = reinterpret_cast<const float4*>(sbias + st.bias_off + ch0 + 32 * g);
@@ -555,12 +557,13 @@ __global__ void __launch_bounds__(256) ts_prepack_kernel(TsParamPtrs pp, uint8_t
   }
   if (threadIdx.x == 0) *reinterpret_cast<TsPackHeader*>(out) = hdr;
   float* bias = reinterpret_cast<float*>(out + hdr.off_bias);
-  for (int i = threadIdx.x; i < kBiasFloats; i += blockDim.x) {
+  for (int i = threadIdx.x; i < kTsBiasFloats; i += blockDim.x) {
     float v = 0.f;
     if (i < kBiasFeat) v = pp.b[i >> 8][i & 255];
     else if (i < kBiasAlpha) v = pp.b[LIN_FEATURE][i - kBiasFeat];
     else if (i == kBiasAlpha) v = pp.b[LIN_ALPHA][0];
     else if (i >= kBiasRgb && i < kBiasRgb + 3) v = pp.b[LIN_RGB][i - kBiasRgb];
+    else if (i >= kTsBiasViews) v = pp.b[LIN_VIEWS][i - kTsBiasViews];
     bias[i] = v;
   }
   float* wdir = reinterpret_cast<float*>(out + hdr.off_wdir);
@@ -640,14 +643,10 @@ int ts_forward(const void* packed, const float* ro, const float* rd, const float
   if (rc != GBN_OK) return rc;
   const TsPlan& p = ts_plan(0);
   int* err = reinterpret_cast<int*>(workspace);
-  float* vbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + 256);
   GBN_CUDA(cudaMemsetAsync(err, 0, 256, stream));
   const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
-  rc = launch_view_bias_raw(reinterpret_cast<const float*>(pk + p.off_wdir), reinterpret_cast<const float*>(pk + p.off_bdir), vd,
-                            stride, emb, R, vbias, stream);
-  if (rc != GBN_OK) return rc;
   TsArgs a{};
-  a.packed = pk; a.ro = ro; a.rd = rd; a.z = z; a.pts = pts; a.emb = emb; a.view_bias = vbias; a.vd = vd; a.raw = raw;
+  a.packed = pk; a.ro = ro; a.rd = rd; a.z = z; a.pts = pts; a.emb = emb; a.vd = vd; a.raw = raw;
   a.stash_h = static_cast<uint8_t*>(stash); a.err = err; a.stride = stride; a.P = R * S; a.S = S;
   a.njobs = (int)p.jobs.size(); a.nsteps = (int)p.steps.size();
   for (int i = 0; i < 4; ++i) a.ready_per_tile[i] = p.ready_per_tile[i];

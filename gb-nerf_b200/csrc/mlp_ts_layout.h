@@ -30,8 +30,12 @@ enum : uint16_t {
   TJ_COMMIT_ACC0 = 64, TJ_COMMIT_ACC1 = 128, TJ_A_SMEM = 256,
   // stagger of the two issuing warps inside a wide layer: the acc1 warp starts only after the acc0 warp has ISSUED
   // its half, so half 0 finishes first and is drained/converted while half 1's MMAs run
-  TJ_SIGNAL_ORDER = 512, TJ_WAIT_ORDER = 1024
+  TJ_SIGNAL_ORDER = 512, TJ_WAIT_ORDER = 1024,
+  // the view-direction encoding block in shared memory as A operand (direction columns of views_linears.0)
+  TJ_A_DIR = 2048, TJ_WAIT_DIR = 4096, TJ_COMMIT_DIR = 8192
 };
+constexpr int kTsBiasViews = kBiasFloats;            // b_views appended to the bias block (128 floats)
+constexpr int kTsBiasFloats = kBiasFloats + 128;
 
 struct TsJob {
   uint32_t w_off;       // weight slab offset in the packed buffer
@@ -170,11 +174,13 @@ inline TsPlan make_ts_plan(int id, bool stagger = false) {
     for (int kp = 0; kp < 2; ++kp)
       job(LIN_ALPHA, 256, 0, 1, 16, 128 * kp, 128, 0, 2, 4, kp == 0 ? (TJ_WAIT_A0 | TJ_FIRST) : 0, kTsAcc0 + kTsColAlpha,
           abuf[1] + 64 * kp, 0);
-    // views_linears.0 on the feature (K = 256 of its 283 inputs; the direction part is the per-ray bias)
+    // views_linears.0: the feature (K = 256) from TMEM + the 27 direction columns on the direction block in smem
     for (int kp = 0; kp < 2; ++kp)
       job(LIN_VIEWS, 283, 0, 128, 128, 128 * kp, 128, 0, 2, 4,
-          kp == 0 ? (TJ_WAIT_A0 | TJ_WAIT_A1 | TJ_FIRST) : TJ_COMMIT_ACC1, kTsAcc1, abuf[0] + 64 * kp, 0);
-    step(1, EPI_VBIAS_RELU, 1, 0, 0, 0xff, kHHv, 0);
+          kp == 0 ? (TJ_WAIT_A0 | TJ_WAIT_A1 | TJ_FIRST) : 0, kTsAcc1, abuf[0] + 64 * kp, 0);
+    job(LIN_VIEWS, 283, 0, 128, 128, 256, 27, 0, 1, 2, TJ_A_SMEM | TJ_A_DIR | TJ_WAIT_DIR | TJ_COMMIT_DIR | TJ_COMMIT_ACC1, kTsAcc1,
+        0, 0);
+    step(1, EPI_BIAS_RELU, 1, 0, 0, 0xff, kHHv, kTsBiasViews);
     // rgb_linear on hv (buffer 1, K = 128)
     job(LIN_RGB, 128, 0, 3, 16, 0, 128, 0, 2, 4, TJ_WAIT_A0 | TJ_FIRST | TJ_COMMIT_ACC0, kTsAcc0 + kTsColRgb, abuf[1], 1);
     step(0, EPI_OUT, 0, 0, 1, 0xff, 0xff, 0);
@@ -230,7 +236,7 @@ inline TsPlan make_ts_plan(int id, bool stagger = false) {
   p.order_per_tile = order;
   for (int i = 0; i < 4; ++i) p.ready_per_tile[i] = done[i];
   p.off_bias = off;
-  off += kBiasFloats * 4;
+  off += kTsBiasFloats * 4;
   p.off_wdir = off; off += 128 * 27 * 4;
   p.off_bdir = off; off += 128 * 4;
   p.total_bytes = (off + 255) & ~255u;

@@ -1,5 +1,7 @@
 """GPU parity of the MLP training path: forward stash, tcgen05 dgrad, tcgen05 wgrad (+ the two small CUDA-core
 gradient kernels) against fp32 autograd of the CPU oracle, stage by stage so a failure names the layer."""
+import os
+
 import pytest
 import torch
 
@@ -60,7 +62,9 @@ def oracle_forward_backward(p, emb, g_raw, emulate_bf16=False):
     sigma = lin("alpha_linear", h)
     feat = q(lin("feature_linear", h))
     feat.retain_grad()
-    if emulate_bf16:   # the kernel keeps the 27 direction columns (a per-ray bias) in exact fp32
+    # (the default bf16 kernels feed the 27 direction columns through the tensor cores as bf16 too; only the
+    # shared-memory-operand fallback keeps them as an exact fp32 per-ray bias)
+    if emulate_bf16 and os.environ.get("GBNERF_MLP", "") == "ss":
         wv = prm["views_linears.0.weight"]
         av = feat @ q(wv[:, :256]).t() + emb_exact[:, 63:] @ wv[:, 256:].t() + prm["views_linears.0.bias"]
     else:
