@@ -167,7 +167,7 @@ def run_ours(args, rank, world, local_rank):
             sampler.start()
         if kernel_events:
             ops.KERNEL_EVENTS = []
-        _lib.LAUNCHES = 0
+        launches0 = _lib.kernel_launches()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(steps):
@@ -176,7 +176,7 @@ def run_ours(args, rank, world, local_rank):
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
-        launches = _lib.LAUNCHES
+        launches = _lib.kernel_launches() - launches0
         events = ops.KERNEL_EVENTS
         ops.KERNEL_EVENTS = None
         clocks = sampler.stop() if sampler else None
@@ -195,7 +195,9 @@ def run_ours(args, rank, world, local_rank):
     mlp_pts = sum(pts for (name, a, b, pts) in events if name == "mlp")
     achieved = mlp_pts * FLOP_PER_POINT / (sum(mlp_ms) * 1e-3) / 1e12 if mlp_ms else None
     peak = pk["bf16_tflops_sustained"]
-    roofline = {"kernel": f"nerf_mlp_kernel<{args.precision}> (fused point generation + posenc + 8x256 MLP)",
+    variant = os.environ.get("GBNERF_MLP", "ts") if args.precision == "bf16" else "ss"   # csrc/mlp_aux.cu mlp_variant()
+    mlp_kernel_name = {"ts": "nerf_mlp_ts_kernel", "tq": "nerf_mlp_tq_kernel"}.get(variant, "nerf_mlp_kernel")
+    roofline = {"kernel": f"{mlp_kernel_name}<{args.precision}> (fused point generation + posenc + 8x256 MLP)",
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak if achieved else None, "peak_source": pk["source"] + " bf16 sustained",
                 "traffic": None, "launches_timed": len(mlp_ms), "avg_launch_ms": sum(mlp_ms) / max(1, len(mlp_ms)),

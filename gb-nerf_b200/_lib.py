@@ -18,6 +18,7 @@ _p, _i64, _i, _f, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t
 SIGNATURES = {
     "gbn_version": (_i, []),
     "gbn_last_error_string": (C.c_char_p, []),
+    "gbn_kernel_launches": (C.c_ulonglong, []),
     "gbn_zvals_stratified": (_i, [_p, _p, _i64, _i64, _i, _i, _p, _p, _p]),
     "gbn_encode_points": (_i, [_p, _p, _p, _i64, _p, _i64, _i, _p, _p]),
     "gbn_composite_forward": (_i, [_p, _p, _p, _i64, _p, _i64, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
@@ -39,10 +40,12 @@ SIGNATURES = {
     "gbn_loss_seed": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _f, _p, _p, _p, _p, _p]),
 }
 
-# kernels each entry point enqueues (bench.py reports the sum over its timed region as gpu_launches)
-KERNELS_PER_CALL = {"gbn_mlp_forward": 2, "gbn_mlp_forward_embedded": 2, "gbn_mlp_backward_weights": 2,
-                    "gbn_version": 0, "gbn_mlp_set_trace": 0}
-LAUNCHES = 0
+
+def kernel_launches():
+    """Kernels the library has launched in this process so far (counted at every launch site in csrc/; bench.py
+    reports the difference over its timed region as ``gpu_launches``)."""
+    return int(load().gbn_kernel_launches())
+
 
 _lib = None
 
@@ -69,10 +72,8 @@ def load():
 
 def call(name, *args):
     """Invoke an int-returning entry point and raise on a non-zero code."""
-    global LAUNCHES
     lib = load()
     rc = getattr(lib, name)(*args)
-    LAUNCHES += KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         msg = lib.gbn_last_error_string().decode(errors="replace")
         if rc == 1:

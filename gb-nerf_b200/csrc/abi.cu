@@ -1,4 +1,5 @@
 // Error reporting and version of the C ABI (include/gbnerf.h).
+#include <atomic>
 #include <stdarg.h>
 
 #include "common.cuh"
@@ -24,3 +25,10 @@ int cuda_fail(cudaError_t e, const char* what) {
 extern "C" int gbn_version(void) { return 100; }  // 0.1.0
 
 extern "C" const char* gbn_last_error_string(void) { return gbn::g_err; }
+
+namespace gbn {
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace gbn
+
+extern "C" unsigned long long gbn_kernel_launches(void) { return gbn::g_launches.load(std::memory_order_relaxed); }

@@ -30,12 +30,15 @@ int cuda_fail(cudaError_t e, const char* what);
     if (e__ != cudaSuccess) return ::gbn::cuda_fail(e__, #call); \
   } while (0)
 
+void count_launch();   // abi.cu: one more kernel of this library went onto a stream (gbn_kernel_launches)
+
 inline int check_launch(const char* what) {
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {
     cudaGetLastError();
     return cuda_fail(e, what);
   }
+  count_launch();
   return GBN_OK;
 }
 

@@ -49,6 +49,8 @@ extern "C" {
 
 int gbn_version(void);
 const char* gbn_last_error_string(void);
+/* Number of CUDA kernels this library has launched in this process so far (every launch site counts itself). */
+unsigned long long gbn_kernel_launches(void);
 
 /* ---- stratified depths: run.py:2291-2315 ---------------------------------------------------------------
  * near/far: [R] with pitch ray_stride (floats).  t_rand: [R,S] uniform [0,1) or NULL (perturb == 0).
