@@ -245,7 +245,7 @@ def train_step_bench(G, ops, dev, nets, kw_test, rank, world, timed):
     tgt, tgd = torch.rand(R, 3, generator=g).to(dev), torch.rand(R, generator=g).to(dev)
     params = [p for n in nets for p in n.parameters()]
     bucket = G.dist.GradBucket(params)
-    opt = torch.optim.Adam(params, lr=3e-3, betas=(0.9, 0.999))
+    opt = G.FusedAdam(params, lr=3e-3, betas=(0.9, 0.999))   # what create_nerf returns: a torch.optim.Adam, one launch/net
     inv_world = 1.0 / world
 
     def step():

@@ -12,7 +12,8 @@ Layout
 The package directory is ``gb-nerf_b200`` (the project's name); import it as ``gbnerf_b200`` through the
 alias module at the repository root.  There is no CPU path: every operator raises without a CUDA device.
 """
-from . import _lib, ops, helpers, run, dist, loss  # noqa: F401
+from . import _lib, ops, helpers, run, dist, loss, optim  # noqa: F401
+from .optim import FusedAdam  # noqa: F401
 from .loss import SigmaLoss  # noqa: F401
 from .helpers import (NeRF, Embedder, get_embedder, get_rays, get_rays_np, ndc_rays, sample_pdf,  # noqa: F401
                       raw2outputs, img2mse, mse2psnr, to8b)

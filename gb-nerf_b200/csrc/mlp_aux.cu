@@ -138,6 +138,8 @@ int launch_view_bias(const uint8_t* packed, const MlpPlan& p, const float* viewd
 // TMEM-operand bf16 kernels (mlp_ts.cu); GBNERF_MLP_SS=1 selects the shared-memory-operand kernels instead
 size_t ts_packed_bytes(int bwd);
 int ts_prepack(const void* const* params, void* packed, int bwd, cudaStream_t st);
+int ts_adam_repack(void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq, double lr,
+                   double beta1, double beta2, double eps, int64_t step, void* packed_fwd, void* packed_bwd, cudaStream_t st);
 size_t tq_packed_bytes(int bwd);
 int tq_prepack(const void* const* params, void* packed, int bwd, cudaStream_t st);
 // bf16 kernel family: 0 = shared-memory operands (mlp_tc.cu), 1 = TMEM operands in halves (mlp_ts.cu),
@@ -202,4 +204,20 @@ extern "C" int gbn_mlp_prepack_weights(const void* const* params, void* packed, 
   else
     prepack_kernel<GBN_PRECISION_TF32><<<njobs + 1, 256, 0, st>>>(pp, static_cast<uint8_t*>(packed), njobs, hdr, precision);
   return check_launch("prepack_kernel");
+}
+
+extern "C" int gbn_mlp_variant(void) { return mlp_variant(); }
+
+extern "C" int gbn_adam_step_repack(void* const* params, const void* const* grads, void* const* exp_avg,
+                                    void* const* exp_avg_sq, double lr, double beta1, double beta2, double eps, int64_t step,
+                                    void* packed_fwd, void* packed_bwd, void* stream) {
+  GBN_REQUIRE(params && grads && exp_avg && exp_avg_sq, "adam_step_repack: null pointer table");
+  for (int i = 0; i < 2 * GBN_NUM_LINEAR; ++i)
+    GBN_REQUIRE(params[i] && grads[i] && exp_avg[i] && exp_avg_sq[i], "adam_step_repack: tensor %d has a null pointer", i);
+  GBN_REQUIRE(step >= 1, "adam_step_repack: step counts from 1 (got %lld)", (long long)step);
+  GBN_REQUIRE(lr >= 0 && beta1 >= 0 && beta1 < 1 && beta2 >= 0 && beta2 < 1 && eps >= 0, "adam_step_repack: bad hyper-parameters");
+  GBN_REQUIRE((packed_fwd == nullptr && packed_bwd == nullptr) || mlp_variant() == 1,
+              "adam_step_repack: in-place re-pack exists for the default bf16 weight images only (pass NULL and re-pack)");
+  return ts_adam_repack(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, packed_fwd, packed_bwd,
+                        (cudaStream_t)stream);
 }

@@ -9,6 +9,7 @@
 //   warps 4-7   per-tile input block (forward: points + positional encoding, backward: padded g_raw) -> smem
 //   warps 8-15  epilogue: accumulator half -> registers (tcgen05.ld) -> +bias/ReLU (or ReLU gate) -> bf16 ->
 //               tcgen05.st into the other A buffer (the next layer's operand) [+ training stash to HBM]
+#include <cmath>
 #include <stdlib.h>
 
 #include <mutex>
@@ -630,6 +631,125 @@ int ts_prepack(const void* const* params, void* packed, int bwd, cudaStream_t st
   const int njobs = (int)p.jobs.size();
   ts_prepack_kernel<<<njobs + 1, 256, 0, st>>>(pp, static_cast<uint8_t*>(packed), njobs, hdr, bwd ? 1 : 0);
   return check_launch("ts_prepack_kernel");
+}
+
+// ---- optimizer step fused with the re-pack ---------------------------------------------------
+// torch.optim.Adam(betas, eps; no weight decay, no amsgrad) on the 24 nn.Linear tensors of one network, in place,
+// one thread per parameter; the same thread then drops the new value (bf16) at its position(s) in the forward and the
+// transposed (dgrad) weight images by walking the pack-job table backwards, so no separate re-pack pass runs after
+// an optimizer step.  Padding bytes of the images are never touched (they were zeroed by ts_prepack_kernel).
+struct TsAdamArgs {
+  float* p[2 * GBN_NUM_LINEAR];
+  const float* g[2 * GBN_NUM_LINEAR];
+  float* m[2 * GBN_NUM_LINEAR];
+  float* v[2 * GBN_NUM_LINEAR];
+  uint32_t start[2 * GBN_NUM_LINEAR + 1];
+  uint16_t ld[GBN_NUM_LINEAR];
+  uint8_t* pack[2];
+  uint32_t njobs[2];
+  uint32_t off_bias[2], off_wdir[2], off_bdir[2];
+  float step_size, w1, b2, w2, eps, bc2_sqrt;
+};
+
+__device__ __forceinline__ void ts_scatter_weight(const TsAdamArgs& a, int layer, int n, int k, float val) {
+  const uint16_t bits = (uint16_t)(pack_bf16(val, 0.f) & 0xffff);
+#pragma unroll
+  for (int prog = 0; prog < 2; ++prog) {
+    uint8_t* out = a.pack[prog];
+    if (!out) continue;
+    for (int j = 0; j < (int)a.njobs[prog]; ++j) {
+      const TsPackJob q = c_tspack[prog][j];
+      if (q.layer != layer) continue;
+      const int nl = q.transpose ? k - (int)q.col0 : n - (int)q.row0;
+      const int ks = q.transpose ? n - (int)q.row0 : k - (int)q.col0;
+      if (nl < 0 || nl >= (int)q.rows_valid || ks < 0 || ks >= (int)q.cols_valid) continue;
+      const int kpos = ks + (int)q.koff, kb = kpos >> 6, kk = kpos & 63;
+      uint8_t* dst = out + q.w_off + (size_t)kb * q.rows * 128 + sw128_offset((uint32_t)nl, (uint32_t)(kk >> 3)) + (kk & 7) * 2;
+      *reinterpret_cast<uint16_t*>(dst) = bits;
+    }
+    if (layer == LIN_VIEWS && k >= 256) reinterpret_cast<float*>(out + a.off_wdir[prog])[n * 27 + (k - 256)] = val;
+  }
+}
+
+__device__ __forceinline__ void ts_scatter_bias(const TsAdamArgs& a, int layer, int i, float val) {
+  int at;
+  if (layer < 8) at = 256 * layer + i;
+  else if (layer == LIN_FEATURE) at = kBiasFeat + i;
+  else if (layer == LIN_ALPHA) at = kBiasAlpha;
+  else if (layer == LIN_RGB) at = kBiasRgb + i;
+  else at = kTsBiasViews + i;
+#pragma unroll
+  for (int prog = 0; prog < 2; ++prog) {
+    uint8_t* out = a.pack[prog];
+    if (!out) continue;
+    reinterpret_cast<float*>(out + a.off_bias[prog])[at] = val;
+    if (layer == LIN_VIEWS) reinterpret_cast<float*>(out + a.off_bdir[prog])[i] = val;
+  }
+}
+
+__global__ void __launch_bounds__(256) adam_repack_kernel(const __grid_constant__ TsAdamArgs a) {
+  const uint32_t total = a.start[2 * GBN_NUM_LINEAR];
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    int lo = 0, hi = 2 * GBN_NUM_LINEAR;   // tensor ti with start[ti] <= e < start[ti+1]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (a.start[mid] <= e) lo = mid; else hi = mid;
+    }
+    const int ti = lo;
+    const uint32_t i = e - a.start[ti];
+    const float g = __ldg(a.g[ti] + i);
+    float m = a.m[ti][i], v = a.v[ti][i], p = a.p[ti][i];
+    m = m + a.w1 * (g - m);                       // exp_avg.lerp_(grad, 1 - beta1)
+    v = v * a.b2;                                 // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value = 1 - beta2)
+    v = v + a.w2 * g * g;
+    const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
+    p = p + (-a.step_size) * (m / denom);         // param.addcdiv_(exp_avg, denom, value = -lr / bias_correction1)
+    a.m[ti][i] = m; a.v[ti][i] = v; a.p[ti][i] = p;
+    const int layer = ti >> 1;
+    if (ti & 1) ts_scatter_bias(a, layer, (int)i, p);
+    else {
+      const int ld = a.ld[layer];
+      const int n = (int)(i / (uint32_t)ld);
+      ts_scatter_weight(a, layer, n, (int)i - n * ld, p);
+    }
+  }
+}
+
+int ts_adam_repack(void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq, double lr,
+                   double beta1, double beta2, double eps, int64_t step, void* packed_fwd, void* packed_bwd, cudaStream_t st) {
+  int rc = ts_ensure_device(st);
+  if (rc != GBN_OK) return rc;
+  static const int kIn[GBN_NUM_LINEAR] = {63, 256, 256, 256, 256, 319, 256, 256, 256, 256, 283, 128};
+  static const int kOut[GBN_NUM_LINEAR] = {256, 256, 256, 256, 256, 256, 256, 256, 256, 1, 128, 3};
+  TsAdamArgs a{};
+  uint32_t off = 0;
+  for (int l = 0; l < GBN_NUM_LINEAR; ++l) {
+    a.ld[l] = (uint16_t)kIn[l];
+    for (int b = 0; b < 2; ++b) {
+      const int ti = 2 * l + b;
+      a.p[ti] = static_cast<float*>(params[ti]);
+      a.g[ti] = static_cast<const float*>(grads[ti]);
+      a.m[ti] = static_cast<float*>(exp_avg[ti]);
+      a.v[ti] = static_cast<float*>(exp_avg_sq[ti]);
+      a.start[ti] = off;
+      off += (uint32_t)(b ? kOut[l] : kOut[l] * kIn[l]);
+    }
+  }
+  a.start[2 * GBN_NUM_LINEAR] = off;   // == GBN_PARAM_COUNT
+  const TsPlan& pf = ts_plan(0);
+  const TsPlan& pb = ts_plan(1);
+  a.pack[0] = static_cast<uint8_t*>(packed_fwd);
+  a.pack[1] = static_cast<uint8_t*>(packed_bwd);
+  a.njobs[0] = (uint32_t)pf.pack.size();
+  a.njobs[1] = (uint32_t)pb.pack.size();
+  a.off_bias[0] = pf.off_bias; a.off_wdir[0] = pf.off_wdir; a.off_bdir[0] = pf.off_bdir;
+  a.off_bias[1] = pb.off_bias; a.off_wdir[1] = pb.off_wdir; a.off_bdir[1] = pb.off_bdir;
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  a.step_size = (float)(lr / bc1);
+  a.w1 = (float)(1.0 - beta1); a.b2 = (float)beta2; a.w2 = (float)(1.0 - beta2);
+  a.eps = (float)eps; a.bc2_sqrt = (float)sqrt(bc2);
+  adam_repack_kernel<<<(off + 255) / 256, 256, 0, st>>>(a);
+  return check_launch("adam_repack_kernel");
 }
 
 void mlp_get_trace(unsigned long long** buf, int* tile);   // mlp_tc.cu

@@ -6,6 +6,7 @@ the render path — ``get_embedder``/``NeRF``/``sample_pdf``/``raw2outputs``/``g
 touching the caller.
 """
 import os
+import weakref
 
 import numpy as np
 import torch
@@ -54,6 +55,9 @@ def get_embedder(multires, i=0):
     return embed, eo.out_dim
 
 
+_NERF_REGISTRY = weakref.WeakSet()   # live NeRF modules (optim.FusedAdam finds the owner of a parameter here)
+
+
 # ---- the model (helpers:75-158) -------------------------------------------------------------------------- #
 class NeRF(nn.Module):
     """Parameter container with the reference's module tree (so ``state_dict`` keys/shapes and the default
@@ -81,6 +85,7 @@ class NeRF(nn.Module):
         else:
             self.output_linear = nn.Linear(W, output_ch)
         self.precision = precision or os.environ.get("GBNERF_PRECISION", "bf16")
+        _NERF_REGISTRY.add(self)
         self._packed = None
         self._packed_key = None
         self._packed_bwd = None

@@ -9,6 +9,7 @@ import numpy as np
 import torch
 
 from . import helpers, ops
+from .optim import FusedAdam
 from .helpers import NeRF, SingleDeviceParallel, get_embedder, get_rays, ndc_rays, unwrap
 
 DEBUG = False
@@ -144,7 +145,8 @@ def create_nerf(args):
         grad_vars += list(model_fine.parameters())
         model_fine = SingleDeviceParallel(model_fine)
     network_query_fn = NetworkQuery(embed_fn, embeddirs_fn, args.netchunk)
-    optimizer = torch.optim.Adam(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999))
+    # a torch.optim.Adam whose step() is one fused kernel per network (optim.py); same state_dict layout
+    optimizer = FusedAdam(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999))
 
     start = 0
     basedir, expname = args.basedir, args.expname

@@ -123,6 +123,21 @@ size_t gbn_mlp_stash_bytes(int64_t P);
  * (layout: tools/mlp_trace.py).  NULL switches tracing off.  Not part of the reference-facing surface. */
 int gbn_mlp_set_trace(void* buf, int tile);
 
+/* Which bf16 kernel family this process uses (env GBNERF_MLP): 0 = operands in shared memory ("ss"), 1 = activations
+ * in tensor memory ("ts", default), 2 = quarter-pipelined experiment ("tq").  The packed weight images differ. */
+int gbn_mlp_variant(void);
+
+/* ---- optimizer step fused with the weight re-pack: run.py:1529 `optimizer.step()` on the Adam of run.py:2065 --------
+ * One network per call.  params / grads / exp_avg / exp_avg_sq: HOST arrays of 24 DEVICE pointers (fp32, nn.Linear
+ * layout, the order of gbn_mlp_prepack_weights).  Updates exp_avg, exp_avg_sq and params in place with
+ * torch.optim.Adam's arithmetic (no weight decay, no amsgrad); `step` is the 1-based count of this step (bias
+ * corrections 1 - beta^step are taken on the host in double, as torch does).  packed_fwd (GBN_PRECISION_BF16 image)
+ * and packed_bwd (GBN_PACK_BWD_BF16 image), each NULL or previously filled by gbn_mlp_prepack_weights, receive the
+ * new values at their positions in the same launch, so no re-pack pass follows an optimizer step. */
+int gbn_adam_step_repack(void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
+                         double lr, double beta1, double beta2, double eps, int64_t step, void* packed_fwd,
+                         void* packed_bwd, void* stream);
+
 /* Diagnostic: one 128x128x64 bf16 tcgen05.mma with the A operand in TMEM (A [128,64] bf16 row-major, Bimg a 16 KB
  * K-major 128B-swizzled tile image, D [128,128] fp32 out).  Used by tests/test_gpu_mlp_render.py to pin the TMEM
  * operand layout the MLP kernel relies on. */

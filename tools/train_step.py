@@ -26,7 +26,7 @@ rays = rays2[:, idx].contiguous().to(dev)
 g = torch.Generator().manual_seed(2)
 tgt, tgd = torch.rand(R, 3, generator=g).to(dev), torch.rand(R, generator=g).to(dev)
 params = [p for n in nets for p in n.parameters()]
-opt = torch.optim.Adam(params, lr=3e-3)
+opt = (torch.optim.Adam if os.environ.get('STOCK_ADAM') else G.FusedAdam)(params, lr=3e-3)
 
 
 def step(with_opt=True):
