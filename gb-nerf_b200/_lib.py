@@ -19,6 +19,8 @@ SIGNATURES = {
     "gbn_version": (_i, []),
     "gbn_last_error_string": (C.c_char_p, []),
     "gbn_kernel_launches": (C.c_ulonglong, []),
+    "gbn_pack_rays": (_i, [_p, _i, _p, _i, _p, _i64, _p, _i64, _p, _i, _i, C.c_double, _i, _i, _i, _i, _i, _i, _f, _f, _i64,
+                           _p, _p]),
     "gbn_zvals_stratified": (_i, [_p, _p, _i64, _i64, _i, _i, _p, _p, _p]),
     "gbn_encode_points": (_i, [_p, _p, _p, _i64, _p, _i64, _i, _p, _p]),
     "gbn_composite_forward": (_i, [_p, _p, _p, _i64, _p, _i64, _i, _i, _p, _p, _p, _p, _p, _p, _p]),

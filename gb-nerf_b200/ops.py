@@ -82,6 +82,43 @@ def _ray_views(*cols):
 
 
 # --------------------------------------------------------------------------------------------------------- #
+def pack_rays(H, W, focal, near, far, c2w=None, rays_o=None, rays_d=None, c2w_staticcam=None, depths=None, patch=None,
+              use_viewdirs=False, ndc=False):
+    """The ray batch render() hands to batchify_rays (run.py:1700-1736) in one launch: ``[R, 8 (+1) (+3)]`` =
+    o, d, near, far, (depth), (unit viewdir).  Either a pose ``c2w`` [3,>=4] (optionally a ``patch`` =
+    (i, j, len1, len2) of the frame and a ``c2w_staticcam``) or ``rays_o``/``rays_d`` [...,3]."""
+    if c2w is not None:
+        c2w = _chk(c2w, "c2w", 2)
+        if c2w.shape[0] < 3 or c2w.shape[1] < 4 or c2w.stride(1) != 1:
+            raise ValueError(f"c2w must be a dense [3,>=4] pose, got {tuple(c2w.shape)}")
+        if c2w_staticcam is not None:
+            c2w_staticcam = _chk(c2w_staticcam, "c2w_staticcam", 2)
+            if c2w_staticcam.shape[0] < 3 or c2w_staticcam.shape[1] < 4 or c2w_staticcam.stride(1) != 1:
+                raise ValueError("c2w_staticcam must be a dense [3,>=4] pose")
+        pi, pj, ph, pw = (0, 0, H, W) if patch is None else [int(v) for v in patch]
+        ph, pw = max(0, min(ph, H - pi)), max(0, min(pw, W - pj))    # python slicing clamps (run.py:1703-1704)
+        R, o, d, dev = ph * pw, None, None, c2w.device
+    else:
+        o = _chk(rays_o, "rays_o").reshape(-1, 3)
+        d = _chk(rays_d, "rays_d").reshape(-1, 3)
+        o = o if o.stride(1) == 1 and o.stride(0) >= 3 else o.contiguous()
+        d = d if d.stride(1) == 1 and d.stride(0) >= 3 else d.contiguous()
+        if o.shape != d.shape:
+            raise ValueError("rays_o and rays_d disagree in shape")
+        pi = pj = ph = pw = 0
+        R, dev = o.shape[0], o.device
+    if depths is not None:
+        depths = _chk(depths, "depths").reshape(-1).contiguous()
+        if depths.numel() != R:
+            raise ValueError("depths must hold one value per ray")
+    out = torch.empty(R, 8 + (depths is not None) + (3 if use_viewdirs else 0), device=dev, dtype=torch.float32)
+    _lib.call("gbn_pack_rays", _ptr(c2w), c2w.stride(0) if c2w is not None else 0, _ptr(c2w_staticcam),
+              c2w_staticcam.stride(0) if c2w_staticcam is not None else 0, _ptr(o), o.stride(0) if o is not None else 0,
+              _ptr(d), d.stride(0) if d is not None else 0, _ptr(depths), int(H), int(W), float(focal), pi, pj, ph, pw,
+              int(bool(use_viewdirs)), int(bool(ndc)), float(near), float(far), R, _ptr(out), _stream())
+    return out
+
+
 def zvals_stratified(near, far, n_samples, lindisp=False, t_rand=None):
     """near, far: [R] or [R,1] (column views of the ray batch are fine) -> z [R,S].  run.py:2291-2315."""
     near = near.reshape(near.shape[0], -1)[:, :1] if near.dim() != 2 else near[:, :1]

@@ -83,36 +83,66 @@ def batchify_rays(rays_flat, chunk=1024 * 32, need_alpha=False, detach_weights=F
     return {k: (v[0] if len(v) == 1 else torch.cat(v, 0)) for k, v in all_ret.items()}
 
 
+def _pack_rays_fused(H, W, focal, rays, c2w, ndc, near, far, use_viewdirs, c2w_staticcam, depths, patch):
+    """One-launch ray setup (ops.pack_rays) when every input is a plain fp32 CUDA tensor without gradient and
+    near/far are numbers; returns (ray batch, shape of rays_d) or None."""
+    import numbers
+    if not (isinstance(near, numbers.Real) and isinstance(far, numbers.Real)):
+        return None
+    ok = lambda t: isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and not t.requires_grad
+    if depths is not None and not ok(depths):
+        return None
+    if c2w is not None:
+        if not ok(c2w) or c2w.dim() != 2 or (c2w_staticcam is not None and (not ok(c2w_staticcam) or not use_viewdirs)):
+            return None
+        batch = ops.pack_rays(H, W, focal, near, far, c2w=c2w, c2w_staticcam=c2w_staticcam, depths=depths, patch=patch,
+                              use_viewdirs=use_viewdirs, ndc=ndc)
+        if patch is None:
+            return batch, (H, W, 3)
+        i, j, len1, len2 = [int(v) for v in patch]
+        return batch, (max(0, min(len1, H - i)), max(0, min(len2, W - j)), 3)
+    rays_o, rays_d = rays
+    if not (ok(rays_o) and ok(rays_d)) or rays_o.shape != rays_d.shape or rays_d.shape[-1] != 3:
+        return None
+    batch = ops.pack_rays(H, W, focal, near, far, rays_o=rays_o, rays_d=rays_d, depths=depths, use_viewdirs=use_viewdirs,
+                          ndc=ndc)
+    return batch, tuple(rays_d.shape)
+
+
 # ---- run.py:1672-1748 ------------------------------------------------------------------------------------ #
 def render(H, W, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far=1., use_viewdirs=False,
            c2w_staticcam=None, depths=None, need_alpha=False, detach_weights=False, patch=None, **kwargs):
     """Same contract as run.py:1672: returns [rgb_map, disp_map, acc_map, depth_map, extras]."""
-    if c2w is not None:
-        rays_o, rays_d = get_rays(H, W, focal, c2w)
-        if patch is not None:
-            i, j, len1, len2 = patch
-            rays_o = rays_o[i:i + len1, j:j + len2, :]
-            rays_d = rays_d[i:i + len1, j:j + len2, :]
-    else:
-        rays_o, rays_d = rays
-    if use_viewdirs:
-        viewdirs = rays_d
-        if c2w_staticcam is not None:
-            rays_o, rays_d = get_rays(H, W, focal, c2w_staticcam)
-        viewdirs = viewdirs / torch.norm(viewdirs, dim=-1, keepdim=True)
-        viewdirs = torch.reshape(viewdirs, [-1, 3]).float()
-    sh = rays_d.shape
-    if ndc:
-        rays_o, rays_d = ndc_rays(H, W, focal, 1., rays_o, rays_d)
-    rays_o = torch.reshape(rays_o, [-1, 3]).float()
-    rays_d = torch.reshape(rays_d, [-1, 3]).float()
-    near, far = near * torch.ones_like(rays_d[..., :1]), far * torch.ones_like(rays_d[..., :1])
-    cols = [rays_o, rays_d, near, far]
-    if depths is not None:
-        cols.append(depths.reshape(-1, 1))
-    if use_viewdirs:
-        cols.append(viewdirs)
-    rays = torch.cat(cols, -1)
+    packed = _pack_rays_fused(H, W, focal, rays, c2w, ndc, near, far, use_viewdirs, c2w_staticcam, depths, patch)
+    if packed is not None:
+        rays, sh = packed
+    else:   # tensors the kernel does not take (other dtypes, gradients into the rays, tensor-valued near/far)
+        if c2w is not None:
+            rays_o, rays_d = get_rays(H, W, focal, c2w)
+            if patch is not None:
+                i, j, len1, len2 = patch
+                rays_o = rays_o[i:i + len1, j:j + len2, :]
+                rays_d = rays_d[i:i + len1, j:j + len2, :]
+        else:
+            rays_o, rays_d = rays
+        if use_viewdirs:
+            viewdirs = rays_d
+            if c2w_staticcam is not None:
+                rays_o, rays_d = get_rays(H, W, focal, c2w_staticcam)
+            viewdirs = viewdirs / torch.norm(viewdirs, dim=-1, keepdim=True)
+            viewdirs = torch.reshape(viewdirs, [-1, 3]).float()
+        sh = rays_d.shape
+        if ndc:
+            rays_o, rays_d = ndc_rays(H, W, focal, 1., rays_o, rays_d)
+        rays_o = torch.reshape(rays_o, [-1, 3]).float()
+        rays_d = torch.reshape(rays_d, [-1, 3]).float()
+        near, far = near * torch.ones_like(rays_d[..., :1]), far * torch.ones_like(rays_d[..., :1])
+        cols = [rays_o, rays_d, near, far]
+        if depths is not None:
+            cols.append(depths.reshape(-1, 1))
+        if use_viewdirs:
+            cols.append(viewdirs)
+        rays = torch.cat(cols, -1)
     all_ret = batchify_rays(rays, chunk, need_alpha=need_alpha, detach_weights=detach_weights, **kwargs)
     for k in all_ret:
         all_ret[k] = torch.reshape(all_ret[k], list(sh[:-1]) + list(all_ret[k].shape[1:]))

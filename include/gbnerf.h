@@ -52,6 +52,18 @@ const char* gbn_last_error_string(void);
 /* Number of CUDA kernels this library has launched in this process so far (every launch site counts itself). */
 unsigned long long gbn_kernel_launches(void);
 
+/* ---- ray setup of render(): run.py:1700-1736 with get_rays / ndc_rays (run_nerf_helpers.py:251-262, 285-302) ------
+ * Writes the packed ray batch [R, 8 (+1 if depths) (+3 if use_viewdirs)] = o, d, near, far, (depth), (unit viewdir).
+ * Either a camera pose: c2w DEVICE [3,>=4] row-major with pitch c2w_ld, rays of the patch rows [patch_i, +patch_h) x
+ * columns [patch_j, +patch_w) of the H x W frame (R = patch_h*patch_w; full frame: 0,0,H,W), optional c2w_static
+ * (run.py:1713: origins/directions from it, view directions from c2w); or a ray batch rays_o / rays_d [R,3] (pitches
+ * o_ld / d_ld floats) with c2w = NULL.  ndc != 0 applies ndc_rays(H, W, focal, 1., o, d) after the view directions
+ * are taken, as render() does. */
+int gbn_pack_rays(const float* c2w, int c2w_ld, const float* c2w_static, int c2w_static_ld, const float* rays_o,
+                  int64_t o_ld, const float* rays_d, int64_t d_ld, const float* depths, int H, int W, double focal,
+                  int patch_i, int patch_j, int patch_h, int patch_w, int use_viewdirs, int ndc, float near, float far,
+                  int64_t R, float* rays_out, void* stream);
+
 /* ---- stratified depths: run.py:2291-2315 ---------------------------------------------------------------
  * near/far: [R] with pitch ray_stride (floats).  t_rand: [R,S] uniform [0,1) or NULL (perturb == 0).
  * z out: [R,S].  lindisp != 0 samples linearly in inverse depth. */

@@ -96,4 +96,7 @@ def test_argument_validation(lib):
     assert l.gbn_mlp_backward_data(None, None, 4, None, None, None, None) == 1
     assert l.gbn_mlp_stash_bytes(129) == 2 * 40 * 16384 and l.gbn_mlp_stash_bytes(0) == 0
     assert l.gbn_mlp_packed_bytes(2) > 1_000_000    # transposed bf16 weights for the dgrad pass
+    assert l.gbn_pack_rays(None, 0, None, 0, None, 0, None, 0, None, 4, 4, 1.0, 0, 0, 4, 4, 1, 0, 0.0, 1.0, 16, None, None) == 1
+    assert l.gbn_adam_step_repack(None, None, None, None, 1e-3, 0.9, 0.999, 1e-8, 1, None, None, None) == 1
+    assert l.gbn_mlp_variant() in (0, 1, 2) and l.gbn_kernel_launches() >= 0
     assert l.gbn_composite_forward(None, None, None, 3, None, 0, 64, 1, None, None, None, None, None, None, None) == 0
