@@ -14,9 +14,12 @@ alias module at the repository root.  There is no CPU path: every operator raise
 """
 from . import _lib, ops, helpers, run, dist, loss, optim  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
+from . import tcnn  # noqa: F401
+from .tcnn import NeRF_TCNN  # noqa: F401
 from .loss import SigmaLoss  # noqa: F401
 from .helpers import (NeRF, Embedder, get_embedder, get_rays, get_rays_np, ndc_rays, sample_pdf,  # noqa: F401
                       raw2outputs, img2mse, mse2psnr, to8b)
-from .run import (batchify, run_network, batchify_rays, render, create_nerf, render_rays, install, NetworkQuery)  # noqa: F401
+from .run import (batchify, run_network, batchify_rays, render, create_nerf, create_nerf_tcnn, render_rays, install,  # noqa: F401
+                  NetworkQuery)  # noqa: F401
 
 __version__ = "0.1.0"

@@ -1,0 +1,731 @@
+// NeRF_TCNN (BASELINE config 5): the hash-grid model the reference builds from tiny-cuda-nn modules
+// (DS_NeRF/run_nerf_helpers_tcnn.py:13-117) as ONE kernel per network call:
+//   point generation o + d*z  ->  (x + bound) / (2 bound)  ->  16-level hash-grid encoding (2 features/level)
+//   -> sigma MLP 32-64-16 -> [SH4(viewdir) | 15 geometry features | 1] -> colour MLP 32-64-64-16 -> (r, g, b, sigma).
+// The reference runs this as ~10 launches with [P,32]/[P,64] fp16 tensors in HBM between them.  tiny-cuda-nn is not
+// vendored in the reference and not installed here: the algorithm is restated from its published description in
+// oracle/tcnn_oracle.py ("parity unpinned"), and that restatement is what this kernel is tested against.
+//
+// Bound: the 16 x 8 four-byte gathers per point (512 B/point of random reads).  The whole table is 28 MB of fp16, i.e.
+// L2-resident on B200 (126 MB), so the roofline is L2 gather throughput, not HBM and not the tensor cores: the MLPs
+// are ~20 KFLOP/point and run on warp-level mma.sync (m16n8k16, fp16 in, fp32 accumulate) with activations chained
+// through registers (an accumulator fragment of two n-tiles IS the A fragment of the next layer's k-tile), weights in
+// shared memory.  One lane owns one point for the gathers (128 independent loads in flight per lane), a warp owns 32
+// points for the MLPs.
+#include <cuda_fp16.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace gbn {
+namespace {
+
+constexpr int kLevels = 16;
+constexpr int kTcThreads = 256;
+constexpr int kTcWarps = kTcThreads / 32;
+constexpr uint32_t kGridEntries = 7034832;          // sum over levels of min(round_up(res^3, 8), 2^19)
+// weight image (halves): row-major [out][in + 8] (the +8 keeps B-fragment loads bank-conflict free)
+constexpr int kLd32 = 40, kLd64 = 72;
+constexpr int kOffS1 = 0;                           // sigma_net  64 x 32
+constexpr int kOffS2 = kOffS1 + 64 * kLd32;         // sigma_net  16 x 64
+constexpr int kOffC1 = kOffS2 + 16 * kLd64;         // color_net  64 x 32 (input columns permuted, see prepack)
+constexpr int kOffC2 = kOffC1 + 64 * kLd32;         // color_net  64 x 64
+constexpr int kOffC3 = kOffC2 + 64 * kLd64;         // color_net  16 x 64
+constexpr int kWeightHalves = kOffC3 + 16 * kLd64;  // 12,032 halves = 24,064 B
+constexpr int kTileLd = 56;                         // per-warp A staging tile: 32 rows x (32 features + 16 SH + 8 pad) halves
+constexpr size_t kTableWeightsOff = (size_t)kGridEntries * 4;   // bytes; grid first (half2 per entry)
+constexpr size_t kTableBytes = ((kTableWeightsOff + kWeightHalves * 2 + 255) / 256) * 256;
+
+struct TcLevel {
+  float scale;
+  uint32_t res, size, offset;
+  uint32_t hashed, pad0, pad1, pad2;
+};
+__constant__ TcLevel c_levels[kLevels];
+
+struct TcArgs {
+  const __half2* grid;
+  const __half* weights;
+  const float* rays_o;
+  const float* rays_d;
+  const float* viewdirs;
+  int64_t ray_stride;
+  const float* z;        // [R,S]
+  const float* inp;      // [P,6] explicit (point, direction) rows, or NULL
+  int64_t P;
+  int S;
+  float* raw;            // [P,4]
+  __half* enc_stash;     // [P,32] fp16 hash-grid encodings kept for the backward pass, or NULL
+  const float* g_raw;    // backward: [P,4]
+  float* g_enc;          // backward: [P,32] fp32 gradient of the encodings
+  float* g_sigma_w;      // backward: [3072] accumulates
+  float* g_color_w;      // backward: [7168] accumulates
+  float loss_scale;
+};
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// y[2 m-tiles][NT n-tiles] = A[2][KT k-tiles] x W^T, W in shared memory as fp16 [8*NT rows][ld]
+template <int KT, int NT>
+__device__ __forceinline__ void dense(const uint32_t (&a)[2][KT][4], const __half* __restrict__ W, int ld, float (&c)[2][NT][4], int g,
+                                      int t) {
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[0][nt][i] = c[1][nt][i] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+      const __half* w = W + (nt * 8 + g) * ld + kt * 16 + 2 * t;
+      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(w);
+      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(w + 8);
+      mma16816(c[0][nt], a[0][kt], b0, b1);
+      mma16816(c[1][nt], a[1][kt], b0, b1);
+    }
+  }
+}
+
+// ReLU + fp16 rounding of an accumulator block, re-used as the next layer's A fragments
+template <int NT>
+__device__ __forceinline__ void relu_to_a(const float (&c)[2][NT][4], uint32_t (&a)[2][NT / 2][4]) {
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int kt = 0; kt < NT / 2; ++kt) {
+      a[m][kt][0] = pack_h2(fmaxf(c[m][2 * kt][0], 0.f), fmaxf(c[m][2 * kt][1], 0.f));
+      a[m][kt][1] = pack_h2(fmaxf(c[m][2 * kt][2], 0.f), fmaxf(c[m][2 * kt][3], 0.f));
+      a[m][kt][2] = pack_h2(fmaxf(c[m][2 * kt + 1][0], 0.f), fmaxf(c[m][2 * kt + 1][1], 0.f));
+      a[m][kt][3] = pack_h2(fmaxf(c[m][2 * kt + 1][2], 0.f), fmaxf(c[m][2 * kt + 1][3], 0.f));
+    }
+}
+
+__device__ __forceinline__ float h16(float v) { return __half2float(__float2half_rn(v)); }
+
+__device__ __forceinline__ void hash_encode_point(const __half2* __restrict__ grid, float x, float y, float z, __half* __restrict__ row) {
+#pragma unroll 2
+  for (int l = 0; l < kLevels; ++l) {
+    const TcLevel L = c_levels[l];
+    const float px = __fadd_rn(__fmul_rn(x, L.scale), 0.5f), py = __fadd_rn(__fmul_rn(y, L.scale), 0.5f),
+                pz = __fadd_rn(__fmul_rn(z, L.scale), 0.5f);
+    const float fx0 = floorf(px), fy0 = floorf(py), fz0 = floorf(pz);
+    const float fx = px - fx0, fy = py - fy0, fz = pz - fz0;
+    const uint32_t cx = (uint32_t)(int)fx0, cy = (uint32_t)(int)fy0, cz = (uint32_t)(int)fz0;
+    const __half2* tab = grid + L.offset;
+    float2 v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint32_t ix = cx + (c & 1), iy = cy + ((c >> 1) & 1), iz = cz + ((c >> 2) & 1);
+      uint32_t idx;
+      if (L.hashed) idx = (ix ^ (iy * 2654435761u) ^ (iz * 805459861u)) & (L.size - 1);   // hashed levels hold 2^19 entries
+      else idx = (ix + iy * L.res + iz * L.res * L.res) % L.size;
+      v[c] = __half22float2(__ldg(tab + idx));
+    }
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {   // same blend order as the restatement: w = wx * wy * wz, acc += w * value
+      const float wx = (c & 1) ? fx : 1.f - fx, wy = (c & 2) ? fy : 1.f - fy, wz = (c & 4) ? fz : 1.f - fz;
+      const float w = __fmul_rn(__fmul_rn(wx, wy), wz);
+      a0 = __fadd_rn(a0, __fmul_rn(w, v[c].x));
+      a1 = __fadd_rn(a1, __fmul_rn(w, v[c].y));
+    }
+    *reinterpret_cast<__half2*>(row + 2 * l) = __floats2half2_rn(a0, a1);
+  }
+}
+
+__device__ __forceinline__ void sh4_point(float x, float y, float z, __half* __restrict__ out) {
+  const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+  float s[16];
+  s[0] = 0.28209479177387814f;
+  s[1] = -0.48860251190291987f * y;
+  s[2] = 0.48860251190291987f * z;
+  s[3] = -0.48860251190291987f * x;
+  s[4] = 1.0925484305920792f * xy;
+  s[5] = -1.0925484305920792f * yz;
+  s[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+  s[7] = -1.0925484305920792f * xz;
+  s[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+  s[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
+  s[10] = 2.8906114426405538f * xy * z;
+  s[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
+  s[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
+  s[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
+  s[14] = 1.4453057213202769f * z * (x2 - y2);
+  s[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+#pragma unroll
+  for (int i = 0; i < 16; i += 2) *reinterpret_cast<__half2*>(out + i) = __floats2half2_rn(s[i], s[i + 1]);
+}
+
+// position in [0,1]^3 and the direction the SH encoding sees, for point p
+__device__ __forceinline__ void load_point(const TcArgs& a, int64_t p, float& x, float& y, float& z, float& dx, float& dy, float& dz) {
+  x = y = z = dx = dy = 0.f; dz = 1.f;
+  if (p < a.P) {
+    if (a.inp) {
+      const float* r = a.inp + p * 6;
+      x = __ldg(r); y = __ldg(r + 1); z = __ldg(r + 2); dx = __ldg(r + 3); dy = __ldg(r + 4); dz = __ldg(r + 5);
+    } else {
+      const int64_t ray = p / a.S;
+      const float zz = __ldg(a.z + p);
+      const float* o = a.rays_o + ray * a.ray_stride;
+      const float* d = a.rays_d + ray * a.ray_stride;
+      const float* v = a.viewdirs + ray * a.ray_stride;
+      x = __fadd_rn(__ldg(o), __fmul_rn(__ldg(d), zz));           // pts = rays_o + rays_d * z (run.py:2317)
+      y = __fadd_rn(__ldg(o + 1), __fmul_rn(__ldg(d + 1), zz));
+      z = __fadd_rn(__ldg(o + 2), __fmul_rn(__ldg(d + 2), zz));
+      dx = __ldg(v); dy = __ldg(v + 1); dz = __ldg(v + 2);
+    }
+  }
+  x = __fdiv_rn(__fadd_rn(x, 100.f), 200.f);                      // (x + bound) / (2 bound), bound = 100
+  y = __fdiv_rn(__fadd_rn(y, 100.f), 200.f);
+  z = __fdiv_rn(__fadd_rn(z, 100.f), 200.f);
+  dx = __fsub_rn(__fadd_rn(dx, 1.f), 1.f);                        // (d + 1)/2 in the model, *2 - 1 in the SH encoding
+  dy = __fsub_rn(__fadd_rn(dy, 1.f), 1.f);
+  dz = __fsub_rn(__fadd_rn(dz, 1.f), 1.f);
+}
+
+__global__ void __launch_bounds__(kTcThreads, 2) tcnn_forward_kernel(const TcArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __half* sW = reinterpret_cast<__half*>(smem_raw);
+  __half* sTile = sW + kWeightHalves + (threadIdx.x >> 5) * (32 * kTileLd);
+  for (int i = threadIdx.x; i < kWeightHalves / 8; i += kTcThreads)
+    reinterpret_cast<uint4*>(sW)[i] = __ldg(reinterpret_cast<const uint4*>(a.weights) + i);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int64_t n_tiles = (a.P + 31) >> 5;
+  const int64_t warp0 = (int64_t)blockIdx.x * kTcWarps + (threadIdx.x >> 5), n_warps = (int64_t)gridDim.x * kTcWarps;
+  for (int64_t tile = warp0; tile < n_tiles; tile += n_warps) {
+    // ---- this lane's point: position in [0,1]^3 and view direction ----------------------------------------
+    const int64_t p = tile * 32 + lane;
+    float x, y, z, dx, dy, dz;
+    load_point(a, p, x, y, z, dx, dy, dz);
+    __half* row = sTile + lane * kTileLd;
+    hash_encode_point(a.grid, x, y, z, row);
+    sh4_point(dx, dy, dz, row + 32);
+    if (a.enc_stash && p < a.P) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(a.enc_stash + p * 32)[i] = reinterpret_cast<const uint4*>(row)[i];
+    }
+    __syncwarp();
+    // ---- A fragments of the encodings --------------------------------------------------------------------
+    uint32_t a_enc[2][2][4], a_col[2][2][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int kt = 0; kt < 3; ++kt) {
+        const __half* s = sTile + (m * 16 + g) * kTileLd + kt * 16 + 2 * t;
+        uint32_t f[4] = {*reinterpret_cast<const uint32_t*>(s), *reinterpret_cast<const uint32_t*>(s + 8 * kTileLd),
+                         *reinterpret_cast<const uint32_t*>(s + 8), *reinterpret_cast<const uint32_t*>(s + 8 * kTileLd + 8)};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (kt < 2) a_enc[m][kt][i] = f[i];
+          else a_col[m][0][i] = f[i];
+        }
+      }
+    __syncwarp();
+    // ---- sigma_net: 32 -> 64 (ReLU) -> 16 -----------------------------------------------------------------
+    float sigma[2][2];
+    {
+      float c1[2][8][4];
+      dense<2, 8>(a_enc, sW + kOffS1, kLd32, c1, g, t);
+      uint32_t a_h[2][4][4];
+      relu_to_a<8>(c1, a_h);
+      float c2[2][2][4];
+      dense<4, 2>(a_h, sW + kOffS2, kLd64, c2, g, t);
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        sigma[m][0] = h16(c2[m][0][0]);          // column 0 of rows g / g+8 lives in the t == 0 lanes
+        sigma[m][1] = h16(c2[m][0][2]);
+        // colour input k-tile 1 = [1 | geo_0..geo_14]: column 0 (sigma) is replaced by the constant-one pad column
+        const float one0 = t == 0 ? 1.f : c2[m][0][0], one1 = t == 0 ? 1.f : c2[m][0][2];
+        a_col[m][1][0] = pack_h2(one0, c2[m][0][1]);
+        a_col[m][1][1] = pack_h2(one1, c2[m][0][3]);
+        a_col[m][1][2] = pack_h2(c2[m][1][0], c2[m][1][1]);
+        a_col[m][1][3] = pack_h2(c2[m][1][2], c2[m][1][3]);
+      }
+    }
+    // ---- color_net: 32 -> 64 (ReLU) -> 64 (ReLU) -> 16 (3 used) ----------------------------------------------
+    float c5[2][1][4];
+    {
+      float c3[2][8][4];
+      dense<2, 8>(a_col, sW + kOffC1, kLd32, c3, g, t);
+      uint32_t a_c1[2][4][4];
+      relu_to_a<8>(c3, a_c1);
+      dense<4, 8>(a_c1, sW + kOffC2, kLd64, c3, g, t);
+      relu_to_a<8>(c3, a_c1);
+      dense<4, 1>(a_c1, sW + kOffC3, kLd64, c5, g, t);
+    }
+    // ---- (r, g, b, sigma) rows: lanes t == 0 hold columns 0,1 and sigma; column 2 comes from lane + 1 -----------
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int hrow = 0; hrow < 2; ++hrow) {
+        const float b = __shfl_down_sync(kFullMask, c5[m][0][2 * hrow], 1);
+        const int64_t q = tile * 32 + m * 16 + hrow * 8 + g;
+        if (t == 0 && q < a.P)
+          reinterpret_cast<float4*>(a.raw)[q] = make_float4(h16(c5[m][0][2 * hrow]), h16(c5[m][0][2 * hrow + 1]), h16(b), sigma[m][hrow]);
+      }
+  }
+}
+
+// =========================================================================================================
+// backward (autograd of NeRF_TCNN.forward wrt its parameters; inputs carry no gradient, run.py:2346)
+//   pass 1, tcnn_backward_mlp_kernel: per 32-point warp tile, re-run the two MLPs from the stashed fp16 encodings,
+//     back-propagate (g_rgb, g_sigma) in fp16 with a power-of-two loss scale (what tiny-cuda-nn's bindings do, default
+//     128) and fp32 accumulation, weight gradients as G^T A on the tensor cores (operands transposed by ldmatrix.trans
+//     from shared-memory tiles) summed per CTA in shared memory and flushed once; writes d loss / d encoding [P,32] fp32.
+//   pass 2, tcnn_backward_grid_kernel: one thread per (point, level) scatters w_corner * g into the fp32 grid gradient
+//     with vector reductions (red.global.add.v2.f32) - the same 128 random 8-byte accesses per point as the forward.
+// =========================================================================================================
+constexpr int kBwWarps = 4;
+constexpr int kBwThreads = kBwWarps * 32;
+constexpr int kActLd = 72;                               // halves per row of an activation / gradient tile
+constexpr int kTileHalves = 32 * kActLd;
+constexpr int kBwTiles = 8;                              // per warp: T0..T3 activations, GS (G5 | G2), G4, G3, G1
+constexpr int kDwFloats = 64 * 32 + 16 * 64 + 64 * 32 + 64 * 64 + 16 * 64;   // 10,240 in the reference's flat order
+constexpr int kDwS1 = 0, kDwS2 = 64 * 32, kDwC1 = kDwS2 + 16 * 64, kDwC2 = kDwC1 + 64 * 32, kDwC3 = kDwC2 + 64 * 64;
+constexpr int kWgUnits = 40;                             // (layer, 16 output rows, 16 input columns) blocks of the five dW
+constexpr int kWgPerWarp = kWgUnits / kBwWarps;
+constexpr size_t kBwSmem = (size_t)kWeightHalves * 2 + (size_t)kBwWarps * kBwTiles * kTileHalves * 2;
+
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const __half* addr) {
+  const uint32_t sa = (uint32_t)__cvta_generic_to_shared(addr);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(sa));
+}
+
+// A fragments [2 m-tiles][KT] -> rows of a [32][kActLd] tile, columns col0 ...
+template <int KT>
+__device__ __forceinline__ void frags_to_tile(const uint32_t (&a)[2][KT][4], __half* tile, int col0, int g, int t) {
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+      __half* s = tile + (m * 16 + g) * kActLd + col0 + kt * 16 + 2 * t;
+      *reinterpret_cast<uint32_t*>(s) = a[m][kt][0];
+      *reinterpret_cast<uint32_t*>(s + 8 * kActLd) = a[m][kt][1];
+      *reinterpret_cast<uint32_t*>(s + 8) = a[m][kt][2];
+      *reinterpret_cast<uint32_t*>(s + 8 * kActLd + 8) = a[m][kt][3];
+    }
+}
+
+template <int KT>
+__device__ __forceinline__ void tile_to_frags(const __half* tile, int col0, uint32_t (&a)[2][KT][4], int g, int t) {
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+      const __half* s = tile + (m * 16 + g) * kActLd + col0 + kt * 16 + 2 * t;
+      a[m][kt][0] = *reinterpret_cast<const uint32_t*>(s);
+      a[m][kt][1] = *reinterpret_cast<const uint32_t*>(s + 8 * kActLd);
+      a[m][kt][2] = *reinterpret_cast<const uint32_t*>(s + 8);
+      a[m][kt][3] = *reinterpret_cast<const uint32_t*>(s + 8 * kActLd + 8);
+    }
+}
+
+// data gradient: c[2][NT] = G[2][KT] x W, W in shared memory as fp16 [16*KT out rows][ld], in = 8*NT columns
+template <int KT, int NT>
+__device__ __forceinline__ void dgrad(const uint32_t (&a)[2][KT][4], const __half* __restrict__ W, int ld, float (&c)[2][NT][4], int lane) {
+  const int q = lane >> 3, r = lane & 7;
+#pragma unroll
+  for (int nt = 0; nt < NT; nt += 2) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[0][nt][i] = c[1][nt][i] = c[0][nt + 1][i] = c[1][nt + 1][i] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+      uint32_t b[4];
+      ldsm_x4_trans(b, W + (kt * 16 + (q & 1) * 8 + r) * ld + nt * 8 + (q >> 1) * 8);
+      mma16816(c[0][nt], a[0][kt], b[0], b[1]);
+      mma16816(c[1][nt], a[1][kt], b[0], b[1]);
+      mma16816(c[0][nt + 1], a[0][kt], b[2], b[3]);
+      mma16816(c[1][nt + 1], a[1][kt], b[2], b[3]);
+    }
+  }
+}
+
+// ReLU gate from the stored activations, fp16 rounding, result as A fragments of the next step
+template <int NT>
+__device__ __forceinline__ void gate_to_a(const float (&c)[2][NT][4], const __half* act, uint32_t (&a)[2][NT / 2][4], int g, int t) {
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const __half* s = act + (m * 16 + g) * kActLd + nt * 8 + 2 * t;
+      const __half2 lo = *reinterpret_cast<const __half2*>(s), hi = *reinterpret_cast<const __half2*>(s + 8 * kActLd);
+      const float v0 = __low2float(lo) > 0.f ? c[m][nt][0] : 0.f, v1 = __high2float(lo) > 0.f ? c[m][nt][1] : 0.f;
+      const float v2 = __low2float(hi) > 0.f ? c[m][nt][2] : 0.f, v3 = __high2float(hi) > 0.f ? c[m][nt][3] : 0.f;
+      a[m][nt >> 1][(nt & 1) * 2 + 0] = pack_h2(v0, v1);
+      a[m][nt >> 1][(nt & 1) * 2 + 1] = pack_h2(v2, v3);
+    }
+}
+
+// One 16 x 16 block of one of the five weight gradients: which gradient tile / columns hold G (16 output channels),
+// which activation tile / columns hold A (16 input channels), and where the block lands in the flat gradient.
+struct WgUnit {
+  int gt, gcol, at, acol, dst, ldw, m0, n0;
+};
+__device__ __forceinline__ WgUnit wg_unit(int id) {
+  WgUnit u;
+  if (id < 4) u = WgUnit{4, 0, 3, id * 16, kDwC3, 64, 0, id * 16};                                             // color out   16 x 64
+  else if (id < 20) { const int j = id - 4; u = WgUnit{5, (j >> 2) * 16, 2, (j & 3) * 16, kDwC2, 64, (j >> 2) * 16, (j & 3) * 16}; }   // 64 x 64
+  else if (id < 28) { const int j = id - 20; u = WgUnit{6, (j >> 1) * 16, 0, 32 + (j & 1) * 16, kDwC1, 32, (j >> 1) * 16, (j & 1) * 16}; }   // 64 x 32
+  else if (id < 32) { const int j = id - 28; u = WgUnit{4, 16, 1, j * 16, kDwS2, 64, 0, j * 16}; }            // sigma out   16 x 64
+  else { const int j = id - 32; u = WgUnit{7, (j >> 1) * 16, 0, (j & 1) * 16, kDwS1, 32, (j >> 1) * 16, (j & 1) * 16}; }               // 64 x 32
+  return u;
+}
+
+__global__ void __launch_bounds__(kBwThreads, 1) tcnn_backward_mlp_kernel(const TcArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __half* sW = reinterpret_cast<__half*>(smem_raw);
+  __half* all_tiles = reinterpret_cast<__half*>(smem_raw + (size_t)kWeightHalves * 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  __half* tiles = all_tiles + warp * kBwTiles * kTileHalves;
+  __half* T0 = tiles;                      // [enc 0..31 | SH 32..47 | one, geo 48..63]
+  __half* T1 = tiles + kTileHalves;        // sigma_net hidden
+  __half* T2 = tiles + 2 * kTileHalves;    // color_net hidden 1
+  __half* T3 = tiles + 3 * kTileHalves;    // color_net hidden 2
+  __half* GS = tiles + 4 * kTileHalves;    // columns 0..15: colour output gradient, 16..31: sigma_net output gradient
+  __half* G4 = tiles + 5 * kTileHalves;    // gradient at color_net hidden 2 (pre-activation)
+  __half* G3 = tiles + 6 * kTileHalves;    // ... hidden 1
+  __half* G1 = tiles + 7 * kTileHalves;    // gradient at sigma_net hidden
+  for (int i = threadIdx.x; i < kWeightHalves / 8; i += kBwThreads)
+    reinterpret_cast<uint4*>(sW)[i] = __ldg(reinterpret_cast<const uint4*>(a.weights) + i);
+  __syncthreads();
+  float acc[kWgPerWarp][8];                // this warp's share of the five weight gradients, kept for the whole kernel
+#pragma unroll
+  for (int u = 0; u < kWgPerWarp; ++u)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[u][i] = 0.f;
+  const int64_t n_tiles = (a.P + 31) >> 5;
+  const int64_t n_groups = (n_tiles + kBwWarps - 1) / kBwWarps;
+  const float ls = a.loss_scale, inv_ls = 1.f / a.loss_scale;
+  for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    const int64_t tile = grp * kBwWarps + warp;      // tiles past the end run on zeros (their gradients are zero)
+    // ---- inputs of the two MLPs: stashed hash-grid encoding + SH of this lane's direction ----------------------
+    const int64_t p = tile * 32 + lane;
+    {
+      float x, y, z, dx, dy, dz;
+      load_point(a, p, x, y, z, dx, dy, dz);
+      __half* row = T0 + lane * kActLd;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        reinterpret_cast<uint4*>(row)[i] = p < a.P ? __ldg(reinterpret_cast<const uint4*>(a.enc_stash + p * 32) + i) : make_uint4(0, 0, 0, 0);
+      sh4_point(dx, dy, dz, row + 32);
+    }
+    __syncwarp();
+    // ---- forward again, activations parked in the tiles ------------------------------------------------------
+    {
+      uint32_t a_in[2][2][4];
+      tile_to_frags<2>(T0, 0, a_in, g, t);
+      float c1[2][8][4];
+      dense<2, 8>(a_in, sW + kOffS1, kLd32, c1, g, t);
+      uint32_t a_h[2][4][4];
+      relu_to_a<8>(c1, a_h);
+      frags_to_tile<4>(a_h, T1, 0, g, t);
+      float c2[2][2][4];
+      dense<4, 2>(a_h, sW + kOffS2, kLd64, c2, g, t);
+      uint32_t a_geo[2][1][4];
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        a_geo[m][0][0] = pack_h2(t == 0 ? 1.f : c2[m][0][0], c2[m][0][1]);
+        a_geo[m][0][1] = pack_h2(t == 0 ? 1.f : c2[m][0][2], c2[m][0][3]);
+        a_geo[m][0][2] = pack_h2(c2[m][1][0], c2[m][1][1]);
+        a_geo[m][0][3] = pack_h2(c2[m][1][2], c2[m][1][3]);
+      }
+      frags_to_tile<1>(a_geo, T0, 48, g, t);
+      __syncwarp();
+      tile_to_frags<2>(T0, 32, a_in, g, t);
+      dense<2, 8>(a_in, sW + kOffC1, kLd32, c1, g, t);
+      relu_to_a<8>(c1, a_h);
+      frags_to_tile<4>(a_h, T2, 0, g, t);
+      dense<4, 8>(a_h, sW + kOffC2, kLd64, c1, g, t);
+      relu_to_a<8>(c1, a_h);
+      frags_to_tile<4>(a_h, T3, 0, g, t);
+    }
+    // ---- incoming gradient (r, g, b | sigma), scaled ---------------------------------------------------------------
+    uint32_t g5[2][1][4];
+    float gs[2][2];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int64_t qrow = tile * 32 + m * 16 + h * 8 + g;
+        const float4 v = qrow < a.P ? __ldg(reinterpret_cast<const float4*>(a.g_raw) + qrow) : make_float4(0.f, 0.f, 0.f, 0.f);
+        g5[m][0][h] = t == 0 ? pack_h2(v.x * ls, v.y * ls) : (t == 1 ? pack_h2(v.z * ls, 0.f) : 0u);
+        g5[m][0][2 + h] = 0u;
+        gs[m][h] = v.w * ls;
+      }
+    frags_to_tile<1>(g5, GS, 0, g, t);
+    __syncwarp();   // T3 (written as fragments) is read below in a different thread mapping
+    // ---- data gradients down the colour network, across to the sigma network ------------------------------------
+    uint32_t gk[2][4][4];
+    {
+      float c[2][8][4];
+      dgrad<1, 8>(g5, sW + kOffC3, kLd64, c, lane);
+      gate_to_a<8>(c, T3, gk, g, t);
+      frags_to_tile<4>(gk, G4, 0, g, t);
+      dgrad<4, 8>(gk, sW + kOffC2, kLd64, c, lane);
+      gate_to_a<8>(c, T2, gk, g, t);
+      frags_to_tile<4>(gk, G3, 0, g, t);
+    }
+    uint32_t g2[2][1][4];
+    {
+      float c[2][4][4];
+      dgrad<4, 4>(gk, sW + kOffC1, kLd32, c, lane);
+      // sigma_net output gradient: column 0 = d/d sigma, columns 1..15 = colour-input columns 17..31 (geo_0..14)
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        g2[m][0][0] = pack_h2(t == 0 ? gs[m][0] : c[m][2][0], c[m][2][1]);
+        g2[m][0][1] = pack_h2(t == 0 ? gs[m][1] : c[m][2][2], c[m][2][3]);
+        g2[m][0][2] = pack_h2(c[m][3][0], c[m][3][1]);
+        g2[m][0][3] = pack_h2(c[m][3][2], c[m][3][3]);
+      }
+    }
+    frags_to_tile<1>(g2, GS, 16, g, t);
+    {
+      float c[2][8][4];
+      dgrad<1, 8>(g2, sW + kOffS2, kLd64, c, lane);
+      gate_to_a<8>(c, T1, gk, g, t);
+      frags_to_tile<4>(gk, G1, 0, g, t);
+    }
+    {
+      float c[2][4][4];
+      dgrad<4, 4>(gk, sW + kOffS1, kLd32, c, lane);
+      // d loss / d encoding, [level][point] float2 so that the scatter pass reads it coalesced
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int64_t qrow = tile * 32 + m * 16 + h * 8 + g;
+            if (qrow < a.P)
+              reinterpret_cast<float2*>(a.g_enc)[(int64_t)(nt * 4 + t) * a.P + qrow] = make_float2(c[m][nt][2 * h] * inv_ls, c[m][nt][2 * h + 1] * inv_ls);
+          }
+    }
+    __syncthreads();
+    // ---- weight gradients: every warp owns 10 of the 40 16x16 blocks and sums G^T A over all four warps' tiles ----
+    {
+      const int q = lane >> 3, r = lane & 7;
+#pragma unroll
+      for (int u = 0; u < kWgPerWarp; ++u) {
+        const WgUnit un = wg_unit(u * kBwWarps + warp);
+#pragma unroll
+        for (int wj = 0; wj < kBwWarps; ++wj) {
+          const __half* gt = all_tiles + (wj * kBwTiles + un.gt) * kTileHalves;
+          const __half* at = all_tiles + (wj * kBwTiles + un.at) * kTileHalves;
+#pragma unroll
+          for (int kt = 0; kt < 2; ++kt) {
+            uint32_t fa[4], fb[4];
+            ldsm_x4_trans(fa, gt + (kt * 16 + (q >> 1) * 8 + r) * kActLd + un.gcol + (q & 1) * 8);
+            ldsm_x4_trans(fb, at + (kt * 16 + (q & 1) * 8 + r) * kActLd + un.acol + (q >> 1) * 8);
+            mma16816(*reinterpret_cast<float(*)[4]>(&acc[u][0]), fa, fb[0], fb[1]);
+            mma16816(*reinterpret_cast<float(*)[4]>(&acc[u][4]), fa, fb[2], fb[3]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- flush this CTA's weight gradients (reference flat layout; colour layer 1 columns un-permuted) ----------------
+#pragma unroll
+  for (int u = 0; u < kWgPerWarp; ++u) {
+    const WgUnit un = wg_unit(u * kBwWarps + warp);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float v = acc[u][i] * inv_ls;
+      if (v == 0.f) continue;
+      const int m = un.m0 + g + ((i >> 1) & 1) * 8, n = un.n0 + (i >> 2) * 8 + 2 * t + (i & 1);
+      if (un.dst < kDwC1) atomicAdd(a.g_sigma_w + un.dst + m * un.ldw + n, v);
+      else if (un.dst == kDwC1) atomicAdd(a.g_color_w + m * 32 + (n < 16 ? n : (n == 16 ? 31 : n - 1)), v);
+      else atomicAdd(a.g_color_w + (un.dst - kDwC1) + m * un.ldw + n, v);
+    }
+  }
+}
+
+__device__ __forceinline__ void red_add_v2(float* addr, float x, float y) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(x), "f"(y) : "memory");
+}
+
+// sum (x, y) over the lanes named in `peers` (all holding the same key); every lane ends with its group's total
+__device__ __forceinline__ void reduce_peers(unsigned peers, int lane, float& x, float& y) {
+  int rel = __popc(peers & ((1u << lane) - 1u));   // my rank inside the group
+  unsigned rest = peers & (0xfffffffeu << lane);    // group members above me
+  while (__any_sync(kFullMask, rest != 0u)) {
+    const int next = __ffs(rest);                   // 1-based lane of the next member above me, 0 if none
+    const float tx = __shfl_sync(kFullMask, x, (next - 1) & 31), ty = __shfl_sync(kFullMask, y, (next - 1) & 31);
+    if (next) { x += tx; y += ty; }
+    const unsigned done = __ballot_sync(kFullMask, rel & 1);   // odd-ranked members have been consumed
+    rest &= ~done;
+    rel >>= 1;
+  }
+}
+
+// one warp = 32 consecutive points (neighbouring samples of a ray) at ONE level: at the coarse levels most of them fall
+// into the same cell, so lanes with equal entry indices are summed in registers first (match.any) and one lane issues
+// the reduction; at the fine levels every lane issues its own.
+__global__ void __launch_bounds__(512) tcnn_backward_grid_kernel(const TcArgs a, float* __restrict__ g_grid) {
+  const int lane = threadIdx.x & 31, l = threadIdx.x >> 5;      // 16 warps = the 16 levels of one 32-point tile
+  const int64_t n_tiles = (a.P + 31) >> 5;
+  const TcLevel L = c_levels[l];
+  float* tab = g_grid + (size_t)L.offset * 2;
+  const bool aggregate = L.scale < 20000.f;   // cells wider than ~1e-2 scene units: neighbouring samples share corners
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t p = tile * 32 + lane;
+    float2 gr = make_float2(0.f, 0.f);
+    if (p < a.P) gr = __ldg(reinterpret_cast<const float2*>(a.g_enc) + (int64_t)l * a.P + p);
+    const bool live = gr.x != 0.f || gr.y != 0.f;
+    if (!__any_sync(kFullMask, live)) continue;
+    float x, y, z, dx, dy, dz;
+    load_point(a, p, x, y, z, dx, dy, dz);
+    const float px = __fadd_rn(__fmul_rn(x, L.scale), 0.5f), py = __fadd_rn(__fmul_rn(y, L.scale), 0.5f),
+                pz = __fadd_rn(__fmul_rn(z, L.scale), 0.5f);
+    const float fx0 = floorf(px), fy0 = floorf(py), fz0 = floorf(pz);
+    const float fx = px - fx0, fy = py - fy0, fz = pz - fz0;
+    const uint32_t cx = (uint32_t)(int)fx0, cy = (uint32_t)(int)fy0, cz = (uint32_t)(int)fz0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint32_t ix = cx + (c & 1), iy = cy + ((c >> 1) & 1), iz = cz + ((c >> 2) & 1);
+      uint32_t idx;
+      if (L.hashed) idx = (ix ^ (iy * 2654435761u) ^ (iz * 805459861u)) & (L.size - 1);
+      else idx = (ix + iy * L.res + iz * L.res * L.res) % L.size;
+      const float wx = (c & 1) ? fx : 1.f - fx, wy = (c & 2) ? fy : 1.f - fy, wz = (c & 4) ? fz : 1.f - fz;
+      const float w = wx * wy * wz;
+      float vx = w * gr.x, vy = w * gr.y;
+      if (aggregate) {
+        const unsigned peers = __match_any_sync(kFullMask, idx);
+        reduce_peers(peers, lane, vx, vy);
+        if (lane == __ffs(peers) - 1 && (vx != 0.f || vy != 0.f)) red_add_v2(tab + (size_t)idx * 2, vx, vy);
+      } else if (live) {
+        red_add_v2(tab + (size_t)idx * 2, vx, vy);
+      }
+    }
+  }
+}
+
+// fp32 flat parameter vectors (the torch bindings' layout) -> fp16 device table
+__global__ void tcnn_prepack_kernel(const float* __restrict__ grid, const float* __restrict__ sigma, const float* __restrict__ color,
+                                    uint8_t* __restrict__ table) {
+  __half2* g = reinterpret_cast<__half2*>(table);
+  const uint32_t stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+  for (uint32_t i = tid; i < kGridEntries; i += stride) g[i] = __floats2half2_rn(__ldg(grid + 2 * (size_t)i), __ldg(grid + 2 * (size_t)i + 1));
+  __half* w = reinterpret_cast<__half*>(table + kTableWeightsOff);
+  for (uint32_t i = tid; i < (uint32_t)kWeightHalves; i += stride) {
+    float v = 0.f;
+    if (i < (uint32_t)kOffS2) { const int n = i / kLd32, k = i % kLd32; if (k < 32) v = sigma[n * 32 + k]; }
+    else if (i < (uint32_t)kOffC1) { const int j = i - kOffS2, n = j / kLd64, k = j % kLd64; if (k < 64) v = sigma[64 * 32 + n * 64 + k]; }
+    else if (i < (uint32_t)kOffC2) {
+      // colour layer 1: kernel column 16 is the constant-one pad (reference column 31), columns 17..31 are geo_0..14
+      const int j = i - kOffC1, n = j / kLd32, k = j % kLd32;
+      if (k < 32) v = color[n * 32 + (k < 16 ? k : (k == 16 ? 31 : k - 1))];
+    }
+    else if (i < (uint32_t)kOffC3) { const int j = i - kOffC2, n = j / kLd64, k = j % kLd64; if (k < 64) v = color[64 * 32 + n * 64 + k]; }
+    else { const int j = i - kOffC3, n = j / kLd64, k = j % kLd64; if (k < 64) v = color[64 * 32 + 64 * 64 + n * 64 + k]; }
+    w[i] = __float2half_rn(v);
+  }
+}
+
+std::mutex g_tc_mutex;
+bool g_tc_init[64];
+
+int tcnn_ensure_device(cudaStream_t st) {
+  int dev = 0;
+  GBN_CUDA(cudaGetDevice(&dev));
+  GBN_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
+  std::lock_guard<std::mutex> lk(g_tc_mutex);
+  if (g_tc_init[dev]) return GBN_OK;
+  // level table: scale = 16 * pls^l - 1 in fp32 (exp2f(l * log2f(pls))), resolution = ceil(scale) + 1
+  TcLevel lv[kLevels];
+  const float log2_pls = log2f((float)exp2(log2(2048.0 * 100.0 / 16.0) / 15.0));
+  uint32_t off = 0;
+  for (int l = 0; l < kLevels; ++l) {
+    const float scale = exp2f((float)l * log2_pls) * 16.f - 1.f;
+    const uint32_t res = (uint32_t)ceilf(scale) + 1;
+    const double dense = (double)res * res * res;
+    uint32_t n = dense > 2147483647.0 ? 2147483647u : (uint32_t)dense;
+    n = (n + 7) / 8 * 8;
+    if (n > (1u << 19)) n = 1u << 19;
+    lv[l] = TcLevel{scale, res, n, off, dense > (double)n ? 1u : 0u, 0, 0, 0};
+    off += n;
+  }
+  GBN_REQUIRE(off == kGridEntries, "hash-grid level table sums to %u entries, expected %u", off, kGridEntries);
+  GBN_CUDA(cudaMemcpyToSymbolAsync(c_levels, lv, sizeof(lv), 0, cudaMemcpyHostToDevice, st));
+  GBN_CUDA(cudaStreamSynchronize(st));   // lv is a stack array
+  GBN_CUDA(cudaFuncSetAttribute(tcnn_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)((kWeightHalves + kTcWarps * 32 * kTileLd) * 2)));
+  GBN_CUDA(cudaFuncSetAttribute(tcnn_backward_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwSmem));
+  g_tc_init[dev] = true;
+  return GBN_OK;
+}
+
+}  // namespace
+}  // namespace gbn
+
+using namespace gbn;
+
+extern "C" size_t gbn_tcnn_table_bytes(void) { return kTableBytes; }
+extern "C" size_t gbn_tcnn_grid_params(void) { return (size_t)kGridEntries * 2; }
+
+extern "C" int gbn_tcnn_prepack(const float* grid_params, const float* sigma_params, const float* color_params, void* table,
+                                void* stream) {
+  GBN_REQUIRE(grid_params && sigma_params && color_params && table, "tcnn_prepack: null pointer");
+  GBN_REQUIRE((reinterpret_cast<uintptr_t>(table) & 255) == 0, "tcnn_prepack: table must be 256-byte aligned");
+  int rc = tcnn_ensure_device((cudaStream_t)stream);
+  if (rc != GBN_OK) return rc;
+  tcnn_prepack_kernel<<<kNumSMs * 8, 256, 0, (cudaStream_t)stream>>>(grid_params, sigma_params, color_params, static_cast<uint8_t*>(table));
+  return check_launch("tcnn_prepack_kernel");
+}
+
+extern "C" int gbn_tcnn_forward(const void* table, const float* rays_o, const float* rays_d, const float* viewdirs, int64_t ray_stride,
+                                const float* z_vals, const float* inputs, int64_t R, int S, float* raw, void* enc_stash,
+                                void* stream) {
+  if (R == 0 || S == 0) return GBN_OK;
+  GBN_REQUIRE(table && raw, "tcnn_forward: null pointer");
+  GBN_REQUIRE(R > 0 && S > 0, "tcnn_forward: bad sizes R=%lld S=%d", (long long)R, S);
+  GBN_REQUIRE(inputs || (rays_o && rays_d && viewdirs && z_vals && ray_stride >= 3), "tcnn_forward: give inputs [P,6] or rays + z_vals");
+  int rc = tcnn_ensure_device((cudaStream_t)stream);
+  if (rc != GBN_OK) return rc;
+  TcArgs a{};
+  a.grid = static_cast<const __half2*>(table);
+  a.weights = reinterpret_cast<const __half*>(static_cast<const uint8_t*>(table) + kTableWeightsOff);
+  a.rays_o = rays_o; a.rays_d = rays_d; a.viewdirs = viewdirs; a.ray_stride = ray_stride; a.z = z_vals; a.inp = inputs;
+  a.P = R * S; a.S = S; a.raw = raw; a.enc_stash = static_cast<__half*>(enc_stash);
+  const int64_t tiles = (a.P + 31) / 32, want = (tiles + kTcWarps - 1) / kTcWarps;
+  const int grid = (int)(want < kNumSMs * 2 ? want : kNumSMs * 2);
+  tcnn_forward_kernel<<<grid, kTcThreads, (kWeightHalves + kTcWarps * 32 * kTileLd) * 2, (cudaStream_t)stream>>>(a);
+  return check_launch("tcnn_forward_kernel");
+}
+
+extern "C" int gbn_tcnn_backward(const void* table, const float* rays_o, const float* rays_d, const float* viewdirs,
+                                 int64_t ray_stride, const float* z_vals, const float* inputs, int64_t R, int S,
+                                 const void* enc_stash, const float* g_raw, float loss_scale, float* g_enc, float* g_grid,
+                                 float* g_sigma_params, float* g_color_params, void* stream) {
+  if (R == 0 || S == 0) return GBN_OK;
+  GBN_REQUIRE(table && enc_stash && g_raw && g_enc && g_grid && g_sigma_params && g_color_params, "tcnn_backward: null pointer");
+  GBN_REQUIRE(R > 0 && S > 0, "tcnn_backward: bad sizes R=%lld S=%d", (long long)R, S);
+  GBN_REQUIRE(inputs || (rays_o && rays_d && viewdirs && z_vals && ray_stride >= 3), "tcnn_backward: give inputs [P,6] or rays + z_vals");
+  GBN_REQUIRE(loss_scale > 0.f, "tcnn_backward: loss_scale must be positive");
+  int rc = tcnn_ensure_device((cudaStream_t)stream);
+  if (rc != GBN_OK) return rc;
+  TcArgs a{};
+  a.grid = static_cast<const __half2*>(table);
+  a.weights = reinterpret_cast<const __half*>(static_cast<const uint8_t*>(table) + kTableWeightsOff);
+  a.rays_o = rays_o; a.rays_d = rays_d; a.viewdirs = viewdirs; a.ray_stride = ray_stride; a.z = z_vals; a.inp = inputs;
+  a.P = R * S; a.S = S;
+  a.enc_stash = static_cast<__half*>(const_cast<void*>(enc_stash));
+  a.g_raw = g_raw; a.g_enc = g_enc; a.g_sigma_w = g_sigma_params; a.g_color_w = g_color_params; a.loss_scale = loss_scale;
+  const int64_t tiles = (a.P + 31) / 32, want = (tiles + kBwWarps - 1) / kBwWarps;
+  const int grid = (int)(want < kNumSMs ? want : kNumSMs);
+  tcnn_backward_mlp_kernel<<<grid, kBwThreads, kBwSmem, (cudaStream_t)stream>>>(a);
+  rc = check_launch("tcnn_backward_mlp_kernel");
+  if (rc != GBN_OK) return rc;
+  tcnn_backward_grid_kernel<<<(int)(tiles < kNumSMs * 4 ? tiles : kNumSMs * 4), 512, 0, (cudaStream_t)stream>>>(a, g_grid);
+  return check_launch("tcnn_backward_grid_kernel");
+}

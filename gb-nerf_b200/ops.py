@@ -463,3 +463,82 @@ def loss_seed(rgb, rgb0, disp, target_rgb, target_disp, depth_lambda=0.1, global
     _lib.call("gbn_loss_seed", _ptr(rgb), _ptr(rgb0), _ptr(disp), _ptr(target_rgb), _ptr(target_disp), R,
               int(global_rays or R), float(depth_lambda), _ptr(g_rgb), _ptr(g_rgb0), _ptr(g_disp), _ptr(loss), _stream())
     return loss, g_rgb, g_rgb0, g_disp
+
+
+# ---- NeRF_TCNN (csrc/tcnn_model.cu) ----------------------------------------------------------------------- #
+def tcnn_prepack(grid_params, sigma_params, color_params, out=None):
+    lib = _lib.load()
+    g, sg, co = (_chk(t.detach(), n, 1).contiguous() for t, n in
+                 ((grid_params, "encoder.params"), (sigma_params, "sigma_net.params"), (color_params, "color_net.params")))
+    if g.numel() != lib.gbn_tcnn_grid_params() or sg.numel() != 64 * 32 + 16 * 64 or co.numel() != 64 * 32 + 64 * 64 + 16 * 64:
+        raise ValueError(f"NeRF_TCNN parameter sizes {g.numel()}, {sg.numel()}, {co.numel()} do not match the reference's model")
+    if out is None:
+        out = torch.empty(lib.gbn_tcnn_table_bytes(), device=g.device, dtype=torch.uint8)
+    _lib.call("gbn_tcnn_prepack", _ptr(g), _ptr(sg), _ptr(co), _ptr(out), _stream())
+    return out
+
+
+def tcnn_forward_raw(table, R, S, rays_o=None, rays_d=None, viewdirs=None, z=None, inputs=None, stash=None):
+    dev = table.device
+    raw = torch.empty(R, S, 4, device=dev, dtype=torch.float32)
+    if inputs is not None:
+        _lib.call("gbn_tcnn_forward", _ptr(table), None, None, None, 0, None, _ptr(inputs), R, S, _ptr(raw), _ptr(stash),
+                  _stream())
+    else:
+        (ro, rd, vd), pitch = _ray_views(rays_o, rays_d, viewdirs)
+        _lib.call("gbn_tcnn_forward", _ptr(table), _ptr(ro), _ptr(rd), _ptr(vd), pitch, _ptr(z), None, R, S, _ptr(raw),
+                  _ptr(stash), _stream())
+    return raw
+
+
+class _Tcnn(torch.autograd.Function):
+    """Autograd node of NeRF_TCNN: inputs carry no gradient (run.py:2346), parameters do."""
+
+    @staticmethod
+    def forward(ctx, module, mode, grad_mode, a0, a1, a2, a3, *params):
+        table = module.table()
+        if mode == "rays":
+            z = _chk(a3, "z_vals", 2).contiguous()
+            R, S = z.shape
+        else:
+            a0 = _chk(a0, "input", 2).contiguous()
+            if a0.shape[1] != 6:
+                raise ValueError(f"NeRF_TCNN takes [P,6] rows (point, direction), got {tuple(a0.shape)}")
+            R, S, z = a0.shape[0], 1, None
+        need_grad = grad_mode and any(ctx.needs_input_grad[7:])
+        stash = torch.empty(R * S, 32, device=table.device, dtype=torch.float16) if need_grad else None
+        if mode == "rays":
+            raw = tcnn_forward_raw(table, R, S, rays_o=a0, rays_d=a1, viewdirs=a2, z=z, stash=stash)
+        else:
+            raw = tcnn_forward_raw(table, R, S, inputs=a0, stash=stash).reshape(R, 4)
+        if need_grad:
+            ctx.module, ctx.mode, ctx.shape, ctx.table = module, mode, (R, S), table
+            ctx.save_for_backward(a0, a1, a2, z, stash)
+        return raw
+
+    @staticmethod
+    def backward(ctx, g_raw):
+        module, (R, S), table = ctx.module, ctx.shape, ctx.table
+        a0, a1, a2, z, stash = ctx.saved_tensors
+        g_raw = _chk(g_raw.contiguous(), "g_raw").reshape(R * S, 4)
+        enc, sig, col = module.param_list()
+        dev = table.device
+        g_grid, g_sig, g_col = torch.zeros_like(enc), torch.zeros_like(sig), torch.zeros_like(col)
+        g_enc = torch.empty(R * S, 32, device=dev, dtype=torch.float32)
+        ls = float(module.loss_scale)
+        if ctx.mode == "rays":
+            (ro, rd, vd), pitch = _ray_views(a0, a1, a2)
+            _lib.call("gbn_tcnn_backward", _ptr(table), _ptr(ro), _ptr(rd), _ptr(vd), pitch, _ptr(z), None, R, S, _ptr(stash),
+                      _ptr(g_raw), ls, _ptr(g_enc), _ptr(g_grid), _ptr(g_sig), _ptr(g_col), _stream())
+        else:
+            _lib.call("gbn_tcnn_backward", _ptr(table), None, None, None, 0, None, _ptr(a0), R, S, _ptr(stash), _ptr(g_raw),
+                      ls, _ptr(g_enc), _ptr(g_grid), _ptr(g_sig), _ptr(g_col), _stream())
+        return (None,) * 7 + (g_grid, g_sig, g_col)
+
+
+def tcnn_rays(module, rays_o, rays_d, viewdirs, z_vals):
+    return _Tcnn.apply(module, "rays", torch.is_grad_enabled(), rays_o, rays_d, viewdirs, z_vals, *module.param_list())
+
+
+def tcnn_inputs(module, inputs):
+    return _Tcnn.apply(module, "inputs", torch.is_grad_enabled(), inputs, None, None, None, *module.param_list())

@@ -10,6 +10,7 @@ import torch
 
 from . import helpers, ops
 from .optim import FusedAdam
+from .tcnn import NeRF_TCNN
 from .helpers import NeRF, SingleDeviceParallel, get_embedder, get_rays, ndc_rays, unwrap
 
 DEBUG = False
@@ -53,6 +54,11 @@ def run_network(inputs2, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 6
     return torch.reshape(outputs_flat, list(inputs2.shape[:-1]) + [outputs_flat.shape[-1]])
 
 
+def _identity(inp):
+    """The embedders of create_nerf_tcnn (run.py:2134, 2139): the model encodes its own inputs."""
+    return inp
+
+
 class NetworkQuery:
     """``network_query_fn`` of create_nerf (run.py:2059-2062) as an object: callable like the reference's
     closure, plus ``fused`` which lets render_rays skip materialising the [R,S,3] point tensor."""
@@ -68,6 +74,8 @@ class NetworkQuery:
         net = unwrap(network_fn)
         if isinstance(net, NeRF) and viewdirs is not None and getattr(self.embed_fn, "num_freqs", None) == 10 \
                 and getattr(self.embeddirs_fn, "num_freqs", None) == 4:
+            return net.forward_rays(rays_o, rays_d, viewdirs, z_vals)
+        if isinstance(net, NeRF_TCNN) and viewdirs is not None and self.embed_fn is _identity and self.embeddirs_fn is _identity:
             return net.forward_rays(rays_o, rays_d, viewdirs, z_vals)
         pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]
         return self(pts, viewdirs, network_fn)
@@ -216,6 +224,53 @@ def create_nerf(args):
     return render_kwargs_train, render_kwargs_test, start, grad_vars, optimizer
 
 
+# ---- run.py:2131-2232 ------------------------------------------------------------------------------------ #
+def create_nerf_tcnn(args):
+    """run.py:2131-2232: the hash-grid models (coarse + fine ``NeRF_TCNN``), identity embedders, Adam, kwargs dicts.
+    As in the reference, a checkpoint only restores ``global_step`` (its model/optimizer loads are commented out)."""
+    device = _device()
+    embed_fn = _identity
+    embeddirs_fn = _identity if args.use_viewdirs else None
+    grad_vars = []
+    model = model_fine = None
+    if args.alpha_model_path is None:
+        model = NeRF_TCNN(encoding="hashgrid").to(device)
+        grad_vars = list(model.parameters())
+        model = SingleDeviceParallel(model)
+    if args.N_importance > 0:
+        if args.alpha_model_path is None:
+            model_fine = NeRF_TCNN(encoding="hashgrid").to(device)
+            grad_vars += list(model_fine.parameters())
+            model_fine = SingleDeviceParallel(model_fine)
+    network_query_fn = NetworkQuery(embed_fn, embeddirs_fn, args.netchunk)
+    optimizer = FusedAdam(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999))   # flat vectors: takes the stock Adam path
+    start = 0
+    basedir, expname = args.basedir, args.expname
+    if args.ft_path is not None and args.ft_path != 'None':
+        ckpts = [args.ft_path]
+    else:
+        ckpts = [os.path.join(basedir, expname, f) for f in sorted(os.listdir(os.path.join(basedir, expname))) if 'tar' in f]
+    print('Found ckpts', ckpts)
+    if len(ckpts) > 0 and not args.no_reload:
+        print('Reloading from', ckpts[-1])
+        start = torch.load(ckpts[-1], map_location=device)['global_step']
+    render_kwargs_train = {
+        'network_query_fn': network_query_fn, 'perturb': args.perturb, 'N_importance': args.N_importance,
+        'network_fine': model_fine, 'N_samples': args.N_samples, 'network_fn': model, 'use_viewdirs': args.use_viewdirs,
+        'white_bkgd': args.white_bkgd, 'raw_noise_std': args.raw_noise_std,
+    }
+    if args.dataset_type != 'llff' or args.no_ndc:
+        print('Not ndc!')
+        render_kwargs_train['ndc'] = False
+        render_kwargs_train['lindisp'] = args.lindisp
+    else:
+        render_kwargs_train['ndc'] = True
+    render_kwargs_test = {k: render_kwargs_train[k] for k in render_kwargs_train}
+    render_kwargs_test['perturb'] = False
+    render_kwargs_test['raw_noise_std'] = 0.
+    return render_kwargs_train, render_kwargs_test, start, grad_vars, optimizer
+
+
 # ---- run.py:2235-2381 ------------------------------------------------------------------------------------ #
 def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False, lindisp=False, perturb=0.,
                 N_importance=0, network_fine=None, white_bkgd=False, raw_noise_std=0., pytest=False,
@@ -293,7 +348,7 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     return ret
 
 
-HOT_PATH = ("batchify", "run_network", "batchify_rays", "render", "create_nerf", "render_rays")
+HOT_PATH = ("batchify", "run_network", "batchify_rays", "render", "create_nerf", "create_nerf_tcnn", "render_rays")
 
 
 def install(run_module):
@@ -302,4 +357,5 @@ def install(run_module):
         setattr(run_module, name, globals()[name])
     for name in ("get_embedder", "NeRF", "get_rays", "ndc_rays", "sample_pdf", "raw2outputs"):
         setattr(run_module, name, getattr(helpers, name))
+    run_module.NeRF_TCNN = NeRF_TCNN
     return run_module

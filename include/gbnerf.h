@@ -150,6 +150,32 @@ int gbn_adam_step_repack(void* const* params, const void* const* grads, void* co
                          double lr, double beta1, double beta2, double eps, int64_t step, void* packed_fwd,
                          void* packed_bwd, void* stream);
 
+/* ---- NeRF_TCNN: DS_NeRF/run_nerf_helpers_tcnn.py:13-117 (hash-grid model built from tiny-cuda-nn modules) ------------
+ * Parameters are the flat fp32 vectors the tiny-cuda-nn torch bindings expose: encoder.params
+ * (gbn_tcnn_grid_params() floats: 16 levels x 2 features, level sizes min(round_up(res^3, 8), 2^19)), sigma_net.params
+ * (64x32 + 16x64, row-major [out,in] per layer) and color_net.params (64x32 + 64x64 + 16x64).  gbn_tcnn_prepack
+ * rounds them to fp16 into `table` (gbn_tcnn_table_bytes()); re-run after each optimizer step.
+ * gbn_tcnn_forward evaluates NeRF_TCNN.forward (lines 90-117) for the points o_r + d_r * z[r,s] with direction
+ * viewdirs_r (rays mode), or for explicit rows inputs [R*S, 6] = (point, direction) when `inputs` is non-NULL:
+ * raw [R*S, 4] fp32 = (r, g, b, sigma) before activation, values rounded to fp16 as the reference's modules emit.
+ * enc_stash: NULL, or [R*S, 32] fp16 to keep the hash-grid encodings for gbn_tcnn_backward. */
+size_t gbn_tcnn_table_bytes(void);
+size_t gbn_tcnn_grid_params(void);
+int gbn_tcnn_prepack(const float* grid_params, const float* sigma_params, const float* color_params, void* table, void* stream);
+int gbn_tcnn_forward(const void* table, const float* rays_o, const float* rays_d, const float* viewdirs, int64_t ray_stride,
+                     const float* z_vals, const float* inputs, int64_t R, int S, float* raw, void* enc_stash, void* stream);
+
+/* Backward of the same call wrt the parameters (inputs carry no gradient, run.py:2346).  enc_stash: the [R*S,32] fp16
+ * hash-grid encodings gbn_tcnn_forward wrote when given a non-NULL enc_stash (64 B/point).  g_raw [R*S,4].
+ * Accumulates (atomic adds) into g_grid (gbn_tcnn_grid_params() floats), g_sigma_params (3072) and g_color_params
+ * (7168), all fp32 in the parameters' own flat layout; g_enc [R*S,32] fp32 is workspace (d loss / d encoding).
+ * The MLP part runs in fp16 with fp32 accumulation; loss_scale (a power of two; tiny-cuda-nn's bindings use 128)
+ * multiplies g_raw on the way in and is divided out before anything is written. */
+int gbn_tcnn_backward(const void* table, const float* rays_o, const float* rays_d, const float* viewdirs, int64_t ray_stride,
+                      const float* z_vals, const float* inputs, int64_t R, int S, const void* enc_stash, const float* g_raw,
+                      float loss_scale, float* g_enc, float* g_grid, float* g_sigma_params, float* g_color_params,
+                      void* stream);
+
 /* Diagnostic: one 128x128x64 bf16 tcgen05.mma with the A operand in TMEM (A [128,64] bf16 row-major, Bimg a 16 KB
  * K-major 128B-swizzled tile image, D [128,128] fp32 out).  Used by tests/test_gpu_mlp_render.py to pin the TMEM
  * operand layout the MLP kernel relies on. */
