@@ -213,6 +213,10 @@ def run_ours(args, rank, world, local_rank):
     if args.precision == "bf16" and not args.no_train:
         train = train_step_bench(G, ops, dev, nets, kw, rank, world, timed)
 
+    tcnn = None
+    if not args.no_tcnn:
+        tcnn = tcnn_bench(G, ops, dev, kw, rank, world, timed)
+
     cpu = cpu_baseline(bounded_s=20.0) if rank == 0 and world == 1 and not args.no_cpu else None
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
@@ -225,6 +229,8 @@ def run_ours(args, rank, world, local_rank):
                 "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
         if train is not None:
             line["train_step"] = train
+        if tcnn is not None:
+            line["tcnn"] = tcnn
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -271,6 +277,38 @@ def train_step_bench(G, ops, dev, nets, kw_test, rank, world, timed):
             "mlp_kernels_ms_per_step": {k: v[0] / steps for k, v in per.items()},
             "mlp_tflops_fwd_equivalent": flop / (t_mlp * 1e-3) / 1e12 if t_mlp else None,
             "grad_allreduce_bytes": bucket.flat.numel() * 4, "gpu_launches": launches}
+
+
+def tcnn_bench(G, ops, dev, kw_test, rank, world, timed):
+    """BASELINE configs[4]: 262,144 rays per GPU through the hash-grid model (NeRF_TCNN, coarse 64 + fine 64, test
+    kwargs).  Reported beside the headline metric.  The model's kernel is bound by its 16 x 8 four-byte table reads per
+    point (512 B/point from a 28 MB fp16 table that lives in L2), so the figure given is that gather rate."""
+    R, chunk = 262144, 32768
+    torch.manual_seed(1)
+    nets = [G.NeRF_TCNN(encoding="hashgrid").to(dev) for _ in range(2)]
+    with torch.no_grad():
+        for n in nets:
+            n.encoder.params.normal_(0.0, 0.5)   # tiny-cuda-nn's +-1e-4 start would leave every feature an fp16 subnormal
+    ident = G.run._identity
+    kw = dict(kw_test, network_fn=nets[0], network_fine=nets[1], network_query_fn=G.NetworkQuery(ident, ident, 65536))
+    rays2 = synthetic_frame_rays(rank)
+    idx = torch.randint(0, rays2.shape[1], (R,), generator=torch.Generator().manual_seed(7 + rank))
+    rays = rays2[:, idx].contiguous().to(dev)
+
+    def step():
+        with torch.no_grad():
+            return G.render(H, W, FOCAL, chunk=chunk, rays=rays, **kw)
+
+    steps = 5
+    ms, launches, events, _ = timed(step, steps, 3, kernel_events=True)
+    t = sum(a.elapsed_time(b) for name, a, b, _ in events if name == "tcnn")
+    pts = sum(p for name, _, _, p in events if name == "tcnn")
+    return {"metric": "rays/sec, 262,144-ray inference render through the hash-grid model (coarse64+fine64)",
+            "value": R * world * steps / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms / steps, "rays_per_gpu": R,
+            "scaling": "weak", "gpu_launches": launches,
+            "kernel": {"name": "tcnn_forward_kernel", "bound": "L2 gather (28 MB fp16 table, 512 B/point of 4-byte reads)",
+                       "points_per_s": pts / (t * 1e-3) if t else None, "gather_GBps": pts * 512 / (t * 1e-3) / 1e9 if t else None,
+                       "share_of_step": t / ms if ms else None, "parity": "unpinned (oracle/tcnn_oracle.py restates tiny-cuda-nn)"}}
 
 
 # --------------------------------------------------------------------------------------------------------- #
@@ -343,6 +381,7 @@ def main():
     ap.add_argument("--rays", type=int, default=0, help="debug: cap rays per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-train", action="store_true", help="skip the 4096-ray training-step leg")
+    ap.add_argument("--no-tcnn", action="store_true", help="skip the hash-grid model leg (BASELINE configs[4])")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))

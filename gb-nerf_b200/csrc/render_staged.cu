@@ -2,12 +2,14 @@
 //
 // One warp per ray, but the ray's operands do not go through registers on their way in: every warp keeps a private
 // D-deep ring of whole rays in shared memory, filled with cp.async (SASS LDGSTS, 16 B per lane for raw) D-1 rays
-// ahead of the one being composited.  Bytes in flight per SM are then set by the ring (2 CTAs x 8 warps x D rays,
-// ~160 KB), not by how many warps happen to be stalled on a load, and there is no block-level synchronisation at
+// ahead of the one being composited.  Bytes in flight per SM are then set by the ring (4 CTAs x 8 warps x D rays,
+// ~200 KB), not by how many warps happen to be stalled on a load, and there is no block-level synchronisation at
 // all (cp.async.wait_group + __syncwarp).  Each lane owns K CONSECUTIVE samples of its ray, so one warp shuffle
 // scan covers the whole ray and weights leave as vector stores.
 // (A bulk-TMA ring was measured first: UBLKCP keeps too few DRAM requests in flight per SM for a cold stream.)
 // Reference: raw2outputs, run_nerf_helpers.py:352-406.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gbn {
@@ -34,14 +36,35 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // 1 / (1 + e^-x): two MUFU ops, ~2 ulp (the compositing tolerance is 1e-5 relative)
 __device__ __forceinline__ float fast_sigmoid(float x) { return rcp_approx(1.f + __expf(-x)); }
 
-template <int K, int D, bool NOISE>
+// five per-lane partial sums -> totals, with 10 shuffles instead of 25: the butterfly halves the number of live values
+// at each of its first three steps (which value a lane carries is decided by its lane bits 16, 8, 4), two more steps
+// finish the sum.  Afterwards lane 0 holds sum(a), lane 4: sum(b), lane 8: sum(c), lane 12: sum(d), lane 16: sum(e).
+__device__ __forceinline__ float warp_sum5(float a, float b, float c, float d, float e, int lane) {
+  const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4;
+  // step 16: lower half keeps (a, b, c, d), upper half keeps (e, 0, 0, 0)
+  const float xa = __shfl_xor_sync(kFullMask, u16 ? a : e, 16);
+  const float xb = __shfl_xor_sync(kFullMask, b, 16), xc = __shfl_xor_sync(kFullMask, c, 16), xd = __shfl_xor_sync(kFullMask, d, 16);
+  float v0 = (u16 ? e : a) + xa, v1 = u16 ? 0.f : b + xb, v2 = u16 ? 0.f : c + xc, v3 = u16 ? 0.f : d + xd;
+  // step 8: bit 8 clear keeps (v0, v1), set keeps (v2, v3)
+  const float y0 = __shfl_xor_sync(kFullMask, u8 ? v0 : v2, 8), y1 = __shfl_xor_sync(kFullMask, u8 ? v1 : v3, 8);
+  v0 = (u8 ? v2 : v0) + y0; v1 = (u8 ? v3 : v1) + y1;
+  // step 4: bit 4 clear keeps v0, set keeps v1
+  const float w = __shfl_xor_sync(kFullMask, u4 ? v0 : v1, 4);
+  v0 = (u4 ? v1 : v0) + w;
+  v0 += __shfl_xor_sync(kFullMask, v0, 2);
+  v0 += __shfl_xor_sync(kFullMask, v0, 1);
+  return v0;
+}
+
+template <int K, int D, bool NOISE, bool FULL>
 __global__ void __launch_bounds__(kStThreads) composite_fwd_staged_kernel(
     const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ noise,
-    const float* __restrict__ d, int64_t stride, int64_t R, int S, int white,
+    const float* __restrict__ d, int64_t stride, int64_t R, int S_rt, int white,
     float* __restrict__ rgb, float* __restrict__ disp, float* __restrict__ acc, float* __restrict__ depth,
     float* __restrict__ weights, float* __restrict__ alpha_out) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = FULL ? 32 * K : S_rt;                                  // FULL: every lane owns exactly K samples
   const uint32_t ray_bytes = (uint32_t)S * (NOISE ? 24u : 20u);       // raw | z | noise of one ray
   uint8_t* const ring = smem + (size_t)warp * D * ray_bytes;
   const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
@@ -53,10 +76,21 @@ __global__ void __launch_bounds__(kStThreads) composite_fwd_staged_kernel(
     const int64_t ray = w0 + i * nwarps;
     const uint32_t dst = ring_u32 + (uint32_t)(i % D) * ray_bytes;
     const float4* rsrc = reinterpret_cast<const float4*>(raw) + ray * S;
-    for (int s = lane; s < S; s += 32) {
-      cp_async16(dst + s * 16, rsrc + s);
-      cp_async4(dst + S * 16 + s * 4, z + ray * S + s);
-      if (NOISE) cp_async4(dst + S * 20 + s * 4, noise + ray * S + s);
+    if (FULL && (K % 4 == 0 || K == 2)) {   // rows of z / noise are multiples of 16 bytes: vector copies
+#pragma unroll
+      for (int k = 0; k < K; ++k) cp_async16(dst + (k * 32 + lane) * 16, rsrc + k * 32 + lane);
+#pragma unroll
+      for (int k = 0; k < (K + 3) / 4; ++k)
+        if (K % 4 == 0 || lane < 16) {
+          cp_async16(dst + S * 16 + (k * 32 + lane) * 16, reinterpret_cast<const float4*>(z + ray * S) + k * 32 + lane);
+          if (NOISE) cp_async16(dst + S * 20 + (k * 32 + lane) * 16, reinterpret_cast<const float4*>(noise + ray * S) + k * 32 + lane);
+        }
+    } else {
+      for (int s = lane; s < S; s += 32) {
+        cp_async16(dst + s * 16, rsrc + s);
+        cp_async4(dst + S * 16 + s * 4, z + ray * S + s);
+        if (NOISE) cp_async4(dst + S * 20 + s * 4, noise + ray * S + s);
+      }
     }
   };
 #pragma unroll
@@ -89,12 +123,26 @@ __global__ void __launch_bounds__(kStThreads) composite_fwd_staged_kernel(
     const float* sn = reinterpret_cast<const float*>(st + S * 20);
     float4 rw[K];
     float zz[K], nz[K];
+    if (FULL && K % 4 == 0) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) {   // lanes past the end re-read the last sample (branch-free); masked below
-      const int sidx = min(lane * K + k, S - 1);
-      rw[k] = sraw[sidx];
-      zz[k] = sz[sidx];
-      nz[k] = NOISE ? sn[sidx] : 0.f;
+      for (int k = 0; k < K; ++k) rw[k] = sraw[lane * K + k];
+#pragma unroll
+      for (int k = 0; k < K; k += 4) {
+        const float4 zq = reinterpret_cast<const float4*>(sz)[(lane * K + k) >> 2];
+        zz[k] = zq.x; zz[k + 1] = zq.y; zz[k + 2] = zq.z; zz[k + 3] = zq.w;
+        if (NOISE) {
+          const float4 nq = reinterpret_cast<const float4*>(sn)[(lane * K + k) >> 2];
+          nz[k] = nq.x; nz[k + 1] = nq.y; nz[k + 2] = nq.z; nz[k + 3] = nq.w;
+        } else nz[k] = nz[k + 1] = nz[k + 2] = nz[k + 3] = 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {   // lanes past the end re-read the last sample (branch-free); masked below
+        const int sidx = FULL ? lane * K + k : min(lane * K + k, S - 1);
+        rw[k] = sraw[sidx];
+        zz[k] = sz[sidx];
+        nz[k] = NOISE ? sn[sidx] : 0.f;
+      }
     }
     __syncwarp();   // slot may be refilled by the next iteration's issue
 
@@ -107,7 +155,7 @@ __global__ void __launch_bounds__(kStThreads) composite_fwd_staged_kernel(
       const float zn = (k + 1 < K) ? zz[k + 1 < K ? k + 1 : k] : znext_lane;
       const float dl = (sidx == S - 1) ? 1e10f : (zn - zz[k]);
       const float sigma = fmaxf(rw[k].w + nz[k], 0.f);
-      a[k] = (sidx < S) ? 1.f - __expf(-sigma * (dl * dnorm)) : 0.f;
+      a[k] = (FULL || sidx < S) ? 1.f - __expf(-sigma * (dl * dnorm)) : 0.f;
       tl[k] = prod;                                   // exclusive product inside the lane
       prod *= (1.f - a[k]) + 1e-10f;
     }
@@ -144,16 +192,20 @@ __global__ void __launch_bounds__(kStThreads) composite_fwd_staged_kernel(
       for (int k = 0; k < K; ++k)
         if (lane * K + k < S) { st_stream(wrow + lane * K + k, w[k]); if (arow) st_stream(arow + lane * K + k, a[k]); }
     }
-    sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb); sd = warp_sum(sd); sa = warp_sum(sa);
-    if (lane == 0) {
-      const float bg = white ? (1.f - sa) : 0.f;
-      rgb[ray * 3 + 0] = sr + bg;
-      rgb[ray * 3 + 1] = sg + bg;
-      rgb[ray * 3 + 2] = sb + bg;
-      const float q = __fdividef(sd, sa);   // NaN when acc == 0, as torch.max propagates the NaN of 0/0
-      disp[ray] = __fdividef(1.f, (q != q) ? q : fmaxf(1e-10f, q));
-      acc[ray] = sa;
-      depth[ray] = sd;
+    // totals: lane 0 <- acc, lane 4 <- red, lane 8 <- green, lane 12 <- blue, lane 16 <- depth (warp_sum5's layout)
+    const float tot = warp_sum5(sa, sr, sg, sb, sd, lane);
+    const float tacc = __shfl_sync(kFullMask, tot, 0);
+    if ((lane & 3) == 0 && lane <= 16) {
+      const float bg = white ? (1.f - tacc) : 0.f;
+      if (lane == 0) acc[ray] = tot;
+      else if (lane == 4) rgb[ray * 3 + 0] = tot + bg;
+      else if (lane == 8) rgb[ray * 3 + 1] = tot + bg;
+      else if (lane == 12) rgb[ray * 3 + 2] = tot + bg;
+      else {
+        const float q = __fdividef(tot, tacc);   // NaN when acc == 0, as torch.max propagates the NaN of 0/0
+        disp[ray] = __fdividef(1.f, (q != q) ? q : fmaxf(1e-10f, q));
+        depth[ray] = tot;
+      }
     }
   }
 }
@@ -166,24 +218,30 @@ int64_t launch_composite_fwd_staged(const float* raw, const float* z, const floa
   *rc = GBN_OK;
   const int K = (S + 31) / 32;
   const uintptr_t al = reinterpret_cast<uintptr_t>(raw) | reinterpret_cast<uintptr_t>(weights) | reinterpret_cast<uintptr_t>(alpha);
+  const bool full = S == 32 * K && ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(noise)) & 15) == 0;
   if (R < 1 || S < 2 || K > 8 || K == 5 || K == 7 || (al & 15) != 0) return 0;
   const size_t ray_bytes = (size_t)S * (noise ? 24 : 20);
   const int dmax = (int)(kStagedSmemBudget / (kStWarps * ray_bytes));
   const int D = dmax >= 8 ? 8 : (dmax >= 4 ? 4 : 2);
   if (dmax < 2) return 0;
   const size_t smem = (size_t)kStWarps * D * ray_bytes;
-  const int64_t blocks = (R + kStWarps - 1) / kStWarps, cap = (int64_t)kNumSMs * 2;
+  static const int ctas_per_sm = [] { const char* e = getenv("GBNERF_COMP_CTAS"); const int v = e ? atoi(e) : 4; return v >= 1 && v <= 4 ? v : 4; }();
+  const int64_t blocks = (R + kStWarps - 1) / kStWarps, cap = (int64_t)kNumSMs * ctas_per_sm;
   const int grid = (int)(blocks < cap ? blocks : cap);
-#define GBN_ST_LAUNCH(KK, DD, NN)                                                                                   \
+#define GBN_ST_LAUNCH2(KK, DD, NN, FF)                                                                              \
   do {                                                                                                              \
     static bool attr = false;                                                                                       \
     if (!attr) {                                                                                                    \
-      cudaFuncSetAttribute(composite_fwd_staged_kernel<KK, DD, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+      cudaFuncSetAttribute(composite_fwd_staged_kernel<KK, DD, NN, FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                            kStagedSmemBudget);                                                                      \
       attr = true;                                                                                                  \
     }                                                                                                               \
-    composite_fwd_staged_kernel<KK, DD, NN><<<grid, kStThreads, smem, stream>>>(                                    \
+    composite_fwd_staged_kernel<KK, DD, NN, FF><<<grid, kStThreads, smem, stream>>>(                                \
         raw, z, noise, rays_d, ray_stride, R, S, white, rgb, disp, acc, depth, weights, alpha);                     \
+  } while (0)
+#define GBN_ST_LAUNCH(KK, DD, NN)                                                                                   \
+  do {                                                                                                              \
+    if (full) GBN_ST_LAUNCH2(KK, DD, NN, true); else GBN_ST_LAUNCH2(KK, DD, NN, false);                             \
   } while (0)
 #define GBN_ST_D(KK)                                                                                                \
   do {                                                                                                              \

@@ -481,13 +481,14 @@ def tcnn_prepack(grid_params, sigma_params, color_params, out=None):
 def tcnn_forward_raw(table, R, S, rays_o=None, rays_d=None, viewdirs=None, z=None, inputs=None, stash=None):
     dev = table.device
     raw = torch.empty(R, S, 4, device=dev, dtype=torch.float32)
-    if inputs is not None:
-        _lib.call("gbn_tcnn_forward", _ptr(table), None, None, None, 0, None, _ptr(inputs), R, S, _ptr(raw), _ptr(stash),
-                  _stream())
-    else:
-        (ro, rd, vd), pitch = _ray_views(rays_o, rays_d, viewdirs)
-        _lib.call("gbn_tcnn_forward", _ptr(table), _ptr(ro), _ptr(rd), _ptr(vd), pitch, _ptr(z), None, R, S, _ptr(raw),
-                  _ptr(stash), _stream())
+    with _timed_launch("tcnn", R * S):
+        if inputs is not None:
+            _lib.call("gbn_tcnn_forward", _ptr(table), None, None, None, 0, None, _ptr(inputs), R, S, _ptr(raw), _ptr(stash),
+                      _stream())
+        else:
+            (ro, rd, vd), pitch = _ray_views(rays_o, rays_d, viewdirs)
+            _lib.call("gbn_tcnn_forward", _ptr(table), _ptr(ro), _ptr(rd), _ptr(vd), pitch, _ptr(z), None, R, S, _ptr(raw),
+                      _ptr(stash), _stream())
     return raw
 
 
