@@ -4,6 +4,8 @@
 // All of them are one-warp-per-ray (or one-thread-per-element) streaming kernels: every byte is read once
 // with coalesced (16-byte where the layout allows) accesses, scans run on warp shuffles, nothing is staged
 // through HBM.  Grids are persistent: kNumSMs x resident CTAs, looping over rays.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gbn {
@@ -481,6 +483,179 @@ __global__ void __launch_bounds__(kThreads) sample_merge_kernel(const float* __r
   }
 }
 
+// ---- the same kernel for the shapes the render path uses (S = 32 KS, N = 32 KN): everything a lane owns lives in
+// registers (element lane + 32 k), all loops unroll, searches are fixed-depth and branch-free, the random-u sort is a
+// register bitonic network over shuffles.  Same arithmetic, element for element, as sample_merge_kernel above (the
+// generic kernel took 1013 warp instructions per 64+64 ray, 74 % issue-bound; see profiles/).
+template <int STEPS, bool UPPER>   // #{j < n : a[j] <= v} (UPPER) or #{j < n : a[j] < v}, n < 2^STEPS... n <= 2^STEPS - 1 + 1
+__device__ __forceinline__ int count_below(const float* a, int n, float v) {
+  int lo = 0;
+#pragma unroll
+  for (int s = STEPS - 1; s >= 0; --s) {
+    const int probe = lo + (1 << s);
+    const float x = a[min(probe, n) - 1];
+    const bool take = probe <= n && (UPPER ? x <= v : x < v);
+    lo = take ? probe : lo;
+  }
+  return lo;
+}
+
+template <int KN>
+__device__ __forceinline__ void warp_bitonic_sort_regs(float (&v)[KN], int lane) {
+  constexpr int N = 32 * KN;
+#pragma unroll
+  for (int kk = 2; kk <= N; kk <<= 1) {
+#pragma unroll
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {                       // partner lives in the same lane
+#pragma unroll
+        for (int k = 0; k < KN; ++k) {
+          const int k2 = k ^ (j >> 5);
+          if (k2 > k) {
+            const bool up = ((32 * k) & kk) == 0;   // kk > j >= 32: decided by k alone
+            const float x = v[k], y = v[k2];
+            const bool sw = (x > y) == up;
+            v[k] = sw ? y : x;
+            v[k2] = sw ? x : y;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < KN; ++k) {
+          const float y = __shfl_xor_sync(kFullMask, v[k], j);
+          const bool lower = (lane & j) == 0;
+          const bool up = (((lane + 32 * k) & kk) == 0);
+          v[k] = (lower == up) ? fminf(v[k], y) : fmaxf(v[k], y);
+        }
+      }
+    }
+  }
+}
+
+template <int KS, int KN, bool DET>
+__global__ void __launch_bounds__(kThreads) sample_merge_fast_kernel(const float* __restrict__ z_vals,
+                                                                     const float* __restrict__ weights,
+                                                                     const float* __restrict__ u, int64_t R,
+                                                                     float* __restrict__ z_samples, float* __restrict__ z_merged,
+                                                                     float* __restrict__ z_std) {
+  constexpr int S = 32 * KS, N = 32 * KN, B = S - 1, M = S - 2;
+  constexpr int LOGS = KS == 1 ? 5 : (KS == 2 ? 6 : (KS <= 4 ? 7 : 8));          // B < 2^LOGS
+  constexpr int LOGN1 = KN == 1 ? 6 : (KN == 2 ? 7 : (KN <= 4 ? 8 : 9));         // N < 2^LOGN1
+  constexpr int kPerWarp = 5 * S + 2 * N + 32;
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float* zv = smem + (size_t)wib * kPerWarp;
+  float* cdf = zv + S;
+  float* bn = cdf + S;
+  float* smp = bn + S;
+  float* mrg = smp + N;
+  int* hist = reinterpret_cast<int*>(mrg + S + N);   // S + 32 counters
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (int64_t ray = (int64_t)blockIdx.x * kWarpsPerBlock + wib; ray < R; ray += nwarps) {
+    float zr[KS], pv[KS];
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+      const int j = lane + 32 * k;
+      zr[k] = ld_stream(z_vals + ray * S + j);
+      zv[j] = zr[k];
+      pv[k] = j < M ? __fadd_rn(ld_stream(weights + ray * S + 1 + j), 1e-5f) : 0.f;
+      tot += pv[k];
+      if (DET) hist[j] = 0;
+    }
+    if (DET) hist[S + lane] = 0;
+    tot = warp_sum(tot);
+    float carry = 0.f;
+    if (lane == 0) cdf[0] = 0.f;
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+      const int j = lane + 32 * k;
+      const float p = j < M ? __fdiv_rn(pv[k], tot) : 0.f;
+      const float incl = warp_scan_add(p, lane);
+      if (j < M) cdf[j + 1] = carry + incl;
+      carry += __shfl_sync(kFullMask, incl, 31);
+      float nxt = __shfl_down_sync(kFullMask, zr[k], 1);
+      const float wrap = __shfl_sync(kFullMask, zr[k + 1 < KS ? k + 1 : k], 0);
+      if (lane == 31) nxt = wrap;
+      if (j < B) bn[j] = __fmul_rn(.5f, __fadd_rn(nxt, zr[k]));
+    }
+    __syncwarp();
+    float sv[KN];
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < KN; ++k) {
+      const int n = lane + 32 * k;
+      const float uu = DET ? linspace01(n, N) : ld_stream(u + ray * N + n);
+      const int ind = count_below<LOGS, true>(cdf, B, uu);
+      const int lo = ind - 1 < 0 ? 0 : ind - 1;
+      const int hi = ind > B - 1 ? B - 1 : ind;
+      const float c0 = cdf[lo], c1 = cdf[hi];
+      float den = __fsub_rn(c1, c0);
+      if (den < 1e-5f) den = 1.f;
+      const float t = __fdiv_rn(__fsub_rn(uu, c0), den);
+      const float b0 = bn[lo], b1 = bn[hi];
+      const float v = __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
+      sv[k] = v;
+      sum += v;
+      if (z_samples) st_stream(z_samples + ray * N + n, v);
+      if (DET) {
+        const int c = lo + 1 + (zv[lo + 1] <= v ? 1 : 0);
+        mrg[n + c] = v;
+        atomicAdd(&hist[c], 1);
+      }
+    }
+    if (z_std) {
+      const float mean = warp_sum(sum) / (float)N;
+      float var = 0.f;
+#pragma unroll
+      for (int k = 0; k < KN; ++k) { const float dv = sv[k] - mean; var += dv * dv; }
+      var = warp_sum(var);
+      if (lane == 0) z_std[ray] = sqrtf(var / (float)N);
+    }
+    if (DET) {
+      __syncwarp();
+      int icarry = 0;
+#pragma unroll
+      for (int k = 0; k < KS; ++k) {
+        const int i = lane + 32 * k;
+        int v = hist[i];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(kFullMask, v, o);
+          if (lane >= o) v += t;
+        }
+        mrg[i + icarry + v] = zr[k];
+        icarry += __shfl_sync(kFullMask, v, 31);
+      }
+    } else {
+      warp_bitonic_sort_regs<KN>(sv, lane);
+#pragma unroll
+      for (int k = 0; k < KN; ++k) smp[lane + 32 * k] = sv[k];
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < KS; ++k) mrg[lane + 32 * k + count_below<LOGN1, false>(smp, N, zr[k])] = zr[k];
+#pragma unroll
+      for (int k = 0; k < KN; ++k) mrg[lane + 32 * k + count_below<LOGS + 1, true>(zv, S, sv[k])] = sv[k];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < KS + KN; ++k) st_stream(z_merged + ray * (S + N) + lane + 32 * k, mrg[lane + 32 * k]);
+    __syncwarp();
+  }
+}
+
+template <int KS, int KN>
+static int launch_sample_merge_fast(const float* z_vals, const float* weights, const float* u, int64_t R, float* z_samples,
+                                    float* z_merged, float* z_std, cudaStream_t stream) {
+  constexpr size_t smem = (size_t)kWarpsPerBlock * (5 * 32 * KS + 2 * 32 * KN + 32) * sizeof(float);
+  static_assert(smem <= 48 * 1024, "sample_merge_fast: shared memory above the default limit");
+  const int per_sm = (int)((200 * 1024) / smem);
+  const int grid = persistent_grid(R, per_sm > 8 ? 8 : per_sm);
+  if (u) sample_merge_fast_kernel<KS, KN, false><<<grid, kThreads, smem, stream>>>(z_vals, weights, u, R, z_samples, z_merged, z_std);
+  else sample_merge_fast_kernel<KS, KN, true><<<grid, kThreads, smem, stream>>>(z_vals, weights, u, R, z_samples, z_merged, z_std);
+  return check_launch("sample_merge_fast_kernel");
+}
+
 // =========================================================================================================
 // loss seed — img2mse terms, run.py:1483,1502,1513-1515
 // =========================================================================================================
@@ -638,6 +813,14 @@ extern "C" int gbn_sample_pdf_merge(const float* z_vals, const float* weights, c
   if (R == 0) return GBN_OK;
   GBN_REQUIRE(z_vals && weights && z_merged, "sample_pdf_merge: null pointer");
   GBN_REQUIRE(R >= 0 && S >= 3 && N >= 1, "sample_pdf_merge: need S>=3, N>=1 (S=%d N=%d)", S, N);
+  {
+    static const bool generic_only = [] { const char* e = getenv("GBNERF_SAMPLE_GENERIC"); return e && e[0] == '1'; }();
+    cudaStream_t st = (cudaStream_t)stream;
+#define GBN_SM_FAST(KS, KN) \
+  if (!generic_only && S == 32 * KS && N == 32 * KN) return launch_sample_merge_fast<KS, KN>(z_vals, weights, u, R, z_samples, z_merged, z_std, st)
+    GBN_SM_FAST(2, 2); GBN_SM_FAST(2, 4); GBN_SM_FAST(4, 2); GBN_SM_FAST(4, 4); GBN_SM_FAST(4, 8); GBN_SM_FAST(2, 1); GBN_SM_FAST(1, 1);
+#undef GBN_SM_FAST
+  }
   int npad = 1;
   while (npad < N) npad <<= 1;
   const size_t smem = (size_t)kWarpsPerBlock * (5 * (size_t)S + npad + N + 1) * sizeof(float);

@@ -176,7 +176,8 @@ def test_sample_pdf_golden(G, golden):
 
 
 @pytest.mark.parametrize("det", [True, False])
-@pytest.mark.parametrize("S,N", [(64, 64), (128, 256), (3, 1), (17, 5)])
+# shapes with S, N multiples of 32 take the register-resident kernel, the others the generic one
+@pytest.mark.parametrize("S,N", [(64, 64), (128, 256), (128, 64), (64, 128), (32, 32), (64, 32), (128, 128), (3, 1), (17, 5), (96, 64)])
 def test_sample_pdf_merge(G, det, S, N):
     g = torch.Generator().manual_seed(S * 7 + N)
     R = 131
