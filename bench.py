@@ -197,10 +197,13 @@ def run_ours(args, rank, world, local_rank):
     peak = pk["bf16_tflops_sustained"]
     variant = os.environ.get("GBNERF_MLP", "ts") if args.precision == "bf16" else "ss"   # csrc/mlp_aux.cu mlp_variant()
     mlp_kernel_name = {"ts": "nerf_mlp_ts_kernel", "tq": "nerf_mlp_tq_kernel"}.get(variant, "nerf_mlp_kernel")
+    traffic = profile_traffic_bytes()
     roofline = {"kernel": f"{mlp_kernel_name}<{args.precision}> (fused point generation + posenc + 8x256 MLP)",
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak if achieved else None, "peak_source": pk["source"] + " bf16 sustained",
-                "traffic": None, "launches_timed": len(mlp_ms), "avg_launch_ms": sum(mlp_ms) / max(1, len(mlp_ms)),
+                "traffic": traffic,
+                "traffic_source": "profiles/r1_mlp_ts_ncu_full.md (dram read+write of the 32768x128 fine-pass launch, ncu --set full)"
+                if traffic else None, "launches_timed": len(mlp_ms), "avg_launch_ms": sum(mlp_ms) / max(1, len(mlp_ms)),
                 "share_of_step": sum(mlp_ms) / ms if mlp_ms else None,
                 "flop_per_launch": mlp_pts * FLOP_PER_POINT / max(1, len(mlp_ms))}
 
@@ -277,6 +280,20 @@ def train_step_bench(G, ops, dev, nets, kw_test, rank, world, timed):
             "mlp_kernels_ms_per_step": {k: v[0] / steps for k, v in per.items()},
             "mlp_tflops_fwd_equivalent": flop / (t_mlp * 1e-3) / 1e12 if t_mlp else None,
             "grad_allreduce_bytes": bucket.flat.numel() * 4, "gpu_launches": launches}
+
+
+def profile_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the MLP kernel from the committed ncu --set full summary."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_mlp_ts_ncu_full.md")
+    try:
+        tot = 0.0
+        for line in open(path):
+            cells = [c.strip() for c in line.split("|")]
+            if len(cells) >= 4 and cells[1] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(cells[3]) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[cells[2]]
+        return tot or None
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 def tcnn_bench(G, ops, dev, kw_test, rank, world, timed):
