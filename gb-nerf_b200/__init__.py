@@ -20,6 +20,6 @@ from .loss import SigmaLoss  # noqa: F401
 from .helpers import (NeRF, Embedder, get_embedder, get_rays, get_rays_np, ndc_rays, sample_pdf,  # noqa: F401
                       raw2outputs, img2mse, mse2psnr, to8b)
 from .run import (batchify, run_network, batchify_rays, render, create_nerf, create_nerf_tcnn, render_rays, install,  # noqa: F401
-                  NetworkQuery)  # noqa: F401
+                  NetworkQuery, depth2xyz_torch, depth2normal_geo)  # noqa: F401
 
 __version__ = "0.1.0"

@@ -40,6 +40,8 @@ SIGNATURES = {
     "gbn_debug_ts_mma": (_i, [_p, _p, _p, _i, _i, _p]),
     "gbn_mlp_forward_embedded": (_i, [_p, _i, _p, _i64, _p, _p, _p, _p]),
     "gbn_mlp_variant": (_i, []),
+    "gbn_normals_forward": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
+    "gbn_normals_backward": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p]),
     "gbn_tcnn_table_bytes": (_sz, []),
     "gbn_tcnn_grid_params": (_sz, []),
     "gbn_tcnn_prepack": (_i, [_p, _p, _p, _p, _p]),

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libgbnerf.so")
 STAMP = os.path.join(PKG, ".libgbnerf.stamp")
-SOURCES = ["abi.cu", "render_ops.cu", "mlp_tc.cu", "mlp_aux.cu", "mlp_wgrad.cu", "render_staged.cu", "ray_setup.cu", "tcnn_model.cu", "ts_probe.cu", "mlp_ts.cu", "mlp_tq.cu"]
+SOURCES = ["abi.cu", "render_ops.cu", "mlp_tc.cu", "mlp_aux.cu", "mlp_wgrad.cu", "render_staged.cu", "ray_setup.cu", "tcnn_model.cu", "normals.cu", "ts_probe.cu", "mlp_ts.cu", "mlp_tq.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC,-O2,-Wall", "--expt-relaxed-constexpr"]

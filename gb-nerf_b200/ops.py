@@ -465,6 +465,39 @@ def loss_seed(rgb, rgb0, disp, target_rgb, target_disp, depth_lambda=0.1, global
     return loss, g_rgb, g_rgb0, g_disp
 
 
+# ---- depth -> normal map (csrc/normals.cu) -------------------------------------------------------------- #
+class _Normals(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, k):
+        points = _chk(points, "points", 4).contiguous()
+        B, C, H, W = points.shape
+        if C != 3:
+            raise ValueError(f"points must be [B,3,H,W], got {tuple(points.shape)}")
+        if k < 1 or k > 31 or k % 2 == 0:
+            raise ValueError(f"window k must be odd and <= 31, got {k}")
+        normals = torch.empty_like(points)
+        minv = torch.empty(B, 6, H, W, device=points.device, dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        _lib.call("gbn_normals_forward", _ptr(points), B, H, W, int(k), _ptr(normals), _ptr(minv), _stream())
+        if minv is not None:
+            ctx.k = int(k)
+            ctx.save_for_backward(points, normals, minv)
+        return normals
+
+    @staticmethod
+    def backward(ctx, g):
+        points, normals, minv = ctx.saved_tensors
+        B, _, H, W = points.shape
+        g = _chk(g.contiguous(), "g_normals", 4)
+        out = torch.empty_like(points)
+        _lib.call("gbn_normals_backward", _ptr(points), _ptr(normals), _ptr(minv), _ptr(g), B, H, W, ctx.k, _ptr(out), _stream())
+        return out, None
+
+
+def normals_from_points(points, k=31):
+    """depth2normal_geo (run.py:2458-2474): points [B,3,H,W] -> [B,3,H,W], differentiable wrt the points."""
+    return _Normals.apply(points, k)
+
+
 # ---- NeRF_TCNN (csrc/tcnn_model.cu) ----------------------------------------------------------------------- #
 def tcnn_prepack(grid_params, sigma_params, color_params, out=None):
     lib = _lib.load()

@@ -348,6 +348,26 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     return ret
 
 
+# ---- run.py:2443-2474 ------------------------------------------------------------------------------------ #
+def depth2xyz_torch(depth_map, depth_cam_matrix, depth_scale=1.0):
+    """run.py:2443-2456: depth [h,w] + intrinsics [3,3] -> xyz [h,w,3], on the depth map's device."""
+    dev, dt = depth_map.device, depth_map.dtype
+    cam = torch.as_tensor(depth_cam_matrix, dtype=dt, device=dev)
+    fx, fy, cx, cy = cam[0, 0], cam[1, 1], cam[0, 2], cam[1, 2]
+    h = torch.arange(depth_map.shape[0], device=dev, dtype=dt)[:, None].expand(depth_map.shape)
+    w = torch.arange(depth_map.shape[1], device=dev, dtype=dt)[None, :].expand(depth_map.shape)
+    z = depth_map / depth_scale
+    x = (w - cx) * z / fx
+    y = (h - cy) * z / fy
+    return torch.cat([x.unsqueeze(-1), y.unsqueeze(-1), z.unsqueeze(-1)], axis=-1)
+
+
+def depth2normal_geo(depth, k=31):
+    """run.py:2458-2474: xyz points [b,3,h,w] -> plane-fit normals [b,3,h,w] over k x k windows; one kernel instead of
+    an 11.5 KB/pixel unfold, a batched inverse and two batched matmuls (csrc/normals.cu), differentiable."""
+    return ops.normals_from_points(depth, k)
+
+
 HOT_PATH = ("batchify", "run_network", "batchify_rays", "render", "create_nerf", "create_nerf_tcnn", "render_rays")
 
 
@@ -358,4 +378,5 @@ def install(run_module):
     for name in ("get_embedder", "NeRF", "get_rays", "ndc_rays", "sample_pdf", "raw2outputs"):
         setattr(run_module, name, getattr(helpers, name))
     run_module.NeRF_TCNN = NeRF_TCNN
+    run_module.depth2xyz_torch, run_module.depth2normal_geo = depth2xyz_torch, depth2normal_geo
     return run_module

@@ -150,6 +150,16 @@ int gbn_adam_step_repack(void* const* params, const void* const* grads, void* co
                          double lr, double beta1, double beta2, double eps, int64_t step, void* packed_fwd,
                          void* packed_bwd, void* stream);
 
+/* ---- depth -> normal map: depth2normal_geo, run.py:2458-2474 (called at run.py:1440-1443) ---------------------------
+ * points [B,3,H,W] (xyz per pixel, depth2xyz_torch's output moved to channel-first as the reference does) ->
+ * normals [B,3,H,W]: per pixel the least-squares plane n.p = 1 through its zero-padded k x k window,
+ * n = (A^T A)^-1 A^T 1 (k odd, <= 31; the reference uses 31).  minv: NULL, or [B,6,H,W] to keep (A^T A)^-1 for the
+ * backward pass.  A window whose A^T A is singular yields inf/nan (torch.linalg.inv raises there).
+ * gbn_normals_backward: g_points [B,3,H,W] = d loss / d points given g_normals. */
+int gbn_normals_forward(const float* points, int B, int H, int W, int k, float* normals, float* minv, void* stream);
+int gbn_normals_backward(const float* points, const float* normals, const float* minv, const float* g_normals, int B, int H,
+                         int W, int k, float* g_points, void* stream);
+
 /* ---- NeRF_TCNN: DS_NeRF/run_nerf_helpers_tcnn.py:13-117 (hash-grid model built from tiny-cuda-nn modules) ------------
  * Parameters are the flat fp32 vectors the tiny-cuda-nn torch bindings expose: encoder.params
  * (gbn_tcnn_grid_params() floats: 16 levels x 2 features, level sizes min(round_up(res^3, 8), 2^19)), sigma_net.params

@@ -326,6 +326,30 @@ def reference_loss(ret, target_rgb, target_disp, depth_lambda=0.1):
 
 
 # --------------------------------------------------------------------------- #
+# depth -> normal map (run.py:2443-2474)
+# --------------------------------------------------------------------------- #
+
+def depth2xyz(depth_map, cam, depth_scale=1.0):
+    """run.py:2443-2456: back-project a depth map [H,W] with intrinsics cam [3,3] -> xyz [H,W,3]."""
+    fx, fy, cx, cy = cam[0, 0], cam[1, 1], cam[0, 2], cam[1, 2]
+    hh, ww = torch.meshgrid(torch.arange(depth_map.shape[0], dtype=depth_map.dtype),
+                            torch.arange(depth_map.shape[1], dtype=depth_map.dtype), indexing="ij")
+    z = depth_map / depth_scale
+    return torch.stack([(ww - cx) * z / fx, (hh - cy) * z / fy, z], -1)
+
+
+def depth2normal_geo(points, k=31):
+    """run.py:2458-2474: points [B,3,H,W] -> [B,3,H,W]; per pixel n = (A^T A)^-1 A^T 1 over its zero-padded k x k window
+    of points A [k*k, 3] (least-squares plane n.p = 1)."""
+    B, C, H, W = points.shape
+    cols = torch.nn.functional.unfold(points, (k, k), dilation=1, padding=(k - 1) // 2, stride=1)   # [B, 3*k*k, H*W]
+    A = cols.transpose(1, 2).reshape(B, H, W, C, k * k).transpose(-1, -2)                              # [B,H,W,k*k,3]
+    At = A.transpose(-1, -2)
+    n = torch.matmul(torch.matmul(torch.linalg.inv(torch.matmul(At, A)), At), torch.ones(B, H, W, k * k, 1, dtype=points.dtype))
+    return n.squeeze(-1).permute(0, 3, 1, 2)
+
+
+# --------------------------------------------------------------------------- #
 # synthetic workloads of SURVEY §8d (shared by tests and bench.py)
 # --------------------------------------------------------------------------- #
 

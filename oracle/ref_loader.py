@@ -27,7 +27,8 @@ import types
 
 REFERENCE_ROOT = os.environ.get("GBNERF_REFERENCE_ROOT", "/root/reference")
 
-_WANTED = ("batchify", "run_network", "batchify_rays", "render", "render_rays", "create_nerf")
+_WANTED = ("batchify", "run_network", "batchify_rays", "render", "render_rays", "create_nerf",
+           "depth2xyz_torch", "depth2normal_geo")   # run.py:2443-2474
 
 
 def available() -> bool:

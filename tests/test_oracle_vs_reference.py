@@ -58,3 +58,19 @@ def test_stratified_and_render_rays_lin(ref, tmp_path):
                  (ex["weights"], r["weights"]), (ex["z_vals"], r["z_vals"])):
         torch.testing.assert_close(a, b, rtol=2e-5, atol=2e-6, equal_nan=True)
     assert set(ex) == set(k for k in r if k not in ("rgb_map", "disp_map", "acc_map", "depth_map"))
+
+
+def test_depth_to_normals(ref):
+    """run.py:2443-2474 against the restatement."""
+    g = torch.Generator().manual_seed(4)
+    H, W = 20, 27
+    yy, xx = torch.meshgrid(torch.linspace(0, 1, H), torch.linspace(0, 1, W), indexing="ij")
+    depth = 3.0 + 0.7 * xx - 0.4 * yy + 0.2 * torch.sin(5 * xx) + 0.02 * torch.rand(H, W, generator=g)
+    cam = torch.tensor([[30.0, 0, 13.0], [0, 31.0, 10.0], [0, 0, 1.0]])
+    want = ref["depth2xyz_torch"](depth, cam)
+    got = O.depth2xyz(depth, cam)
+    assert torch.equal(got, want)
+    pts = want.unsqueeze(0).transpose(2, 3).transpose(1, 2)      # 1,3,h,w as at run.py:1441
+    n_ref = ref["depth2normal_geo"](pts, 7)
+    n_got = O.depth2normal_geo(pts.contiguous(), 7)
+    torch.testing.assert_close(n_got, n_ref, rtol=1e-5, atol=1e-6)
