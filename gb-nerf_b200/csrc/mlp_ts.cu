@@ -20,6 +20,16 @@
 
 namespace gbn {
 
+// (a0, a1) + (b0, b1) as one packed fp32x2 instruction (sm_100 FADD2); a* are raw accumulator words
+__device__ __forceinline__ void add_f32x2(uint32_t a0, uint32_t a1, float b0, float b1, float& r0, float& r1) {
+  unsigned long long x, y;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "r"(a0), "r"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(x) : "l"(x), "l"(y));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(x));
+}
+
+
 using namespace tc;
 
 __constant__ TsJob c_tsjobs[2][kTsMaxJobs];
@@ -488,10 +498,10 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
           } else {
             const float4* bp = reinterpret_cast<const float4*>(sbias + st.bias_off + ch0 + 32 * g);
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
+            for (int i = 0; i < 32; i += 4) {   // packed fp32x2 adds (FADD2): two channels per instruction
               const float4 bb = bp[i >> 2];
-              f[i] = __uint_as_float(v[g][i]) + bb.x; f[i + 1] = __uint_as_float(v[g][i + 1]) + bb.y;
-              f[i + 2] = __uint_as_float(v[g][i + 2]) + bb.z; f[i + 3] = __uint_as_float(v[g][i + 3]) + bb.w;
+              add_f32x2(v[g][i], v[g][i + 1], bb.x, bb.y, f[i], f[i + 1]);
+              add_f32x2(v[g][i + 2], v[g][i + 3], bb.z, bb.w, f[i + 2], f[i + 3]);
             }
           }
           uint32_t w[16];
