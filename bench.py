@@ -221,6 +221,8 @@ def run_ours(args, rank, world, local_rank):
         tcnn = tcnn_bench(G, ops, dev, kw, rank, world, timed)
 
     cpu = cpu_baseline(bounded_s=20.0) if rank == 0 and world == 1 and not args.no_cpu else None
+    if cpu is not None:
+        cpu["torch_gpu_fp32"] = torch_gpu_port(dev)
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -346,6 +348,39 @@ def cpu_render(n_rays, threads=None):
         O.render(rays, chunk=CHUNK, p_coarse=pc, p_fine=pf, n_samples=N_SAMPLES, n_importance=N_IMPORTANCE,
                  lindisp=True, white_bkgd=True)
         return time.perf_counter() - t0
+
+
+def torch_gpu_port(dev, n_rays=32768):
+    """Second comparison point of SURVEY §8d: the same oracle port (plain PyTorch ops, fp32, TF32 off as the reference
+    sets it, run.py:37-38) on this GPU - i.e. what the reference's own code path costs on a B200."""
+    from oracle import nerf_oracle as O
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        rays2 = synthetic_frame_rays(0)
+        idx = torch.randint(0, H * W, (n_rays,), generator=torch.Generator().manual_seed(1))
+        rays = O.pack_rays(rays2[0, idx], rays2[1, idx], NEAR, FAR).to(dev)
+        pc = {k: v.to(dev) for k, v in O.init_params(0).items()}
+        pf = {k: v.to(dev) for k, v in O.init_params(None).items()}
+
+        def once():
+            with torch.no_grad(), torch.device(dev):
+                O.render(rays, chunk=CHUNK, p_coarse=pc, p_fine=pf, n_samples=N_SAMPLES, n_importance=N_IMPORTANCE,
+                         lindisp=True, white_bkgd=True)
+
+        once()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            once()
+        e1.record()
+        torch.cuda.synchronize()
+        return {"value": 3 * n_rays / (e0.elapsed_time(e1) * 1e-3), "unit": "rays/s",
+                "sample": f"{n_rays} random pixels, one chunk, oracle port on cuda (PyTorch eager fp32, TF32 off), mean of 3"}
+    except Exception as e:   # a reported comparison point, never a reason to lose the bench line
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
 
 
 def cpu_baseline(bounded_s=20.0, n_rays=1024):
