@@ -210,6 +210,127 @@ __global__ void __launch_bounds__(kStThreads) composite_fwd_staged_kernel(
   }
 }
 
+// ---- S = 64 (the coarse pass): two rays per warp -------------------------------------------------------------------
+// With 64 samples a lane would own only two, and the per-ray fixed cost (scan, reductions, outputs: ~150 of the 316
+// warp instructions per ray) dominates.  Two CONSECUTIVE rays are therefore staged as one 128-sample pseudo-ray (their
+// raw / z / noise rows are contiguous in memory), lanes 0-15 composite the first and lanes 16-31 the second with
+// 16-lane segmented scans and reductions: the warp does the work of one 128-sample ray for two 64-sample rays.
+template <int D, bool NOISE>
+__global__ void __launch_bounds__(kStThreads) composite_fwd_pair64_kernel(
+    const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ noise,
+    const float* __restrict__ d, int64_t stride, int64_t R, int white,
+    float* __restrict__ rgb, float* __restrict__ disp, float* __restrict__ acc, float* __restrict__ depth,
+    float* __restrict__ weights, float* __restrict__ alpha_out) {
+  constexpr int S = 64, P = 128, K = 4;                          // P: samples of the pseudo-ray
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane >> 4, l16 = lane & 15;
+  constexpr uint32_t pair_bytes = (uint32_t)P * (NOISE ? 24u : 20u);
+  uint8_t* const ring = smem + (size_t)warp * D * pair_bytes;
+  const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
+  const int64_t npairs = (R + 1) >> 1;
+  const int64_t nwarps = (int64_t)gridDim.x * kStWarps;
+  const int64_t w0 = (int64_t)blockIdx.x * kStWarps + warp;
+  const int64_t my_pairs = w0 < npairs ? (npairs - w0 + nwarps - 1) / nwarps : 0;
+
+  auto issue = [&](int64_t i) {
+    const int64_t pr = w0 + i * nwarps;
+    const bool both = 2 * pr + 1 < R;                            // the last pair of an odd batch has one ray
+    const uint32_t dst = ring_u32 + (uint32_t)(i % D) * pair_bytes;
+    const float4* rsrc = reinterpret_cast<const float4*>(raw) + pr * P;
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      if (both || k < 2) cp_async16(dst + (k * 32 + lane) * 16, rsrc + k * 32 + lane);
+    if (both || lane < 16) {
+      cp_async16(dst + P * 16 + lane * 16, reinterpret_cast<const float4*>(z + pr * P) + lane);
+      if (NOISE) cp_async16(dst + P * 20 + lane * 16, reinterpret_cast<const float4*>(noise + pr * P) + lane);
+    }
+  };
+#pragma unroll
+  for (int j = 0; j < D - 1; ++j) {
+    if (j < my_pairs) issue(j);
+    cp_async_commit();
+  }
+  float dn_lane = 0.f;   // |d| of ray 2 * (pair i0 + lane / 2) + (lane & 1), refreshed every 16 pairs
+  for (int64_t i = 0; i < my_pairs; ++i) {
+    const int64_t pr = w0 + i * nwarps;
+    const int64_t ray = 2 * pr + sub;
+    const bool valid = ray < R;
+    if (i + D - 1 < my_pairs) issue(i + D - 1);
+    cp_async_commit();
+    if ((i & 15) == 0) {
+      const int64_t ii = i + (lane >> 1);
+      const int64_t r = 2 * (w0 + ii * nwarps) + (lane & 1);
+      dn_lane = 0.f;
+      if (ii < my_pairs && r < R) {
+        const float dx = __ldg(d + r * stride), dy = __ldg(d + r * stride + 1), dz = __ldg(d + r * stride + 2);
+        dn_lane = sqrtf(dx * dx + dy * dy + dz * dz);
+      }
+    }
+    const float dnorm = __shfl_sync(kFullMask, dn_lane, 2 * (int)(i & 15) + sub);
+    cp_async_wait<D - 1>();
+    __syncwarp();
+    const uint8_t* st = ring + (size_t)(i % D) * pair_bytes;
+    float4 rw[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) rw[k] = reinterpret_cast<const float4*>(st)[lane * K + k];
+    const float4 zq = reinterpret_cast<const float4*>(st + P * 16)[lane];
+    float4 nq = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (NOISE) nq = reinterpret_cast<const float4*>(st + P * 20)[lane];
+    __syncwarp();   // slot may be refilled by the next iteration's issue
+    const float zz[K] = {zq.x, zq.y, zq.z, zq.w}, nz[K] = {nq.x, nq.y, nq.z, nq.w};
+    const float znext_lane = __shfl_down_sync(kFullMask, zz[0], 1);
+    float a[K], tl[K];
+    float prod = 1.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float zn = (k + 1 < K) ? zz[k + 1 < K ? k + 1 : k] : znext_lane;
+      const float dl = (k == K - 1 && l16 == 15) ? 1e10f : (zn - zz[k]);      // the ray's last sample (helpers:369-372)
+      const float sigma = fmaxf(rw[k].w + nz[k], 0.f);
+      a[k] = valid ? 1.f - __expf(-sigma * (dl * dnorm)) : 0.f;
+      tl[k] = prod;
+      prod *= (1.f - a[k]) + 1e-10f;
+    }
+    float incl = prod;   // inclusive product scan inside each 16-lane half
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+      const float t = __shfl_up_sync(kFullMask, incl, o);
+      if (l16 >= o) incl *= t;
+    }
+    float excl = __shfl_up_sync(kFullMask, incl, 1);
+    if (l16 == 0) excl = 1.f;
+    float sr = 0.f, sg = 0.f, sb = 0.f, sd = 0.f, sa = 0.f;
+    float w[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      w[k] = a[k] * (excl * tl[k]);
+      sr = fmaf(w[k], fast_sigmoid(rw[k].x), sr);
+      sg = fmaf(w[k], fast_sigmoid(rw[k].y), sg);
+      sb = fmaf(w[k], fast_sigmoid(rw[k].z), sb);
+      sd = fmaf(w[k], zz[k], sd);
+      sa += w[k];
+    }
+    if (valid) {
+      st_stream4(reinterpret_cast<float4*>(weights + pr * P) + lane, make_float4(w[0], w[1], w[2], w[3]));
+      if (alpha_out) st_stream4(reinterpret_cast<float4*>(alpha_out + pr * P) + lane, make_float4(a[0], a[1], a[2], a[3]));
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {   // xor offsets < 16 stay inside the half
+      sr += __shfl_xor_sync(kFullMask, sr, o); sg += __shfl_xor_sync(kFullMask, sg, o); sb += __shfl_xor_sync(kFullMask, sb, o);
+      sd += __shfl_xor_sync(kFullMask, sd, o); sa += __shfl_xor_sync(kFullMask, sa, o);
+    }
+    if (l16 == 0 && valid) {
+      const float bg = white ? (1.f - sa) : 0.f;
+      rgb[ray * 3 + 0] = sr + bg;
+      rgb[ray * 3 + 1] = sg + bg;
+      rgb[ray * 3 + 2] = sb + bg;
+      const float q = __fdividef(sd, sa);   // NaN when acc == 0, as torch.max propagates the NaN of 0/0
+      disp[ray] = __fdividef(1.f, (q != q) ? q : fmaxf(1e-10f, q));
+      acc[ray] = sa;
+      depth[ray] = sd;
+    }
+  }
+}
+
 // Launches the staged kernel when the shapes allow (S <= 256, 16-byte aligned raw); returns how many rays it took
 // (0 = the caller uses the generic kernel).
 int64_t launch_composite_fwd_staged(const float* raw, const float* z, const float* rays_d, int64_t ray_stride,
@@ -220,6 +341,24 @@ int64_t launch_composite_fwd_staged(const float* raw, const float* z, const floa
   const uintptr_t al = reinterpret_cast<uintptr_t>(raw) | reinterpret_cast<uintptr_t>(weights) | reinterpret_cast<uintptr_t>(alpha);
   const bool full = S == 32 * K && ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(noise)) & 15) == 0;
   if (R < 1 || S < 2 || K > 8 || K == 5 || K == 7 || (al & 15) != 0) return 0;
+  static const bool no_pairs = [] { const char* e = getenv("GBNERF_COMP_NOPAIR"); return e && e[0] == '1'; }();
+  if (S == 64 && full && !no_pairs) {   // two rays per warp (composite_fwd_pair64_kernel)
+    constexpr int D = 2;
+    const size_t smem = (size_t)kStWarps * D * 128 * (noise ? 24 : 20);
+    static const int ctas = [] { const char* e = getenv("GBNERF_COMP_CTAS"); const int v = e ? atoi(e) : 4; return v >= 1 && v <= 4 ? v : 4; }();
+    const int64_t blocks = ((R + 1) / 2 + kStWarps - 1) / kStWarps, cap = (int64_t)kNumSMs * ctas;
+    const int grid = (int)(blocks < cap ? blocks : cap);
+    static bool attr = false;   // immutable kernel attribute, set once
+    if (!attr) {
+      cudaFuncSetAttribute(composite_fwd_pair64_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStagedSmemBudget);
+      cudaFuncSetAttribute(composite_fwd_pair64_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStagedSmemBudget);
+      attr = true;
+    }
+    if (noise) composite_fwd_pair64_kernel<D, true><<<grid, kStThreads, smem, stream>>>(raw, z, noise, rays_d, ray_stride, R, white, rgb, disp, acc, depth, weights, alpha);
+    else composite_fwd_pair64_kernel<D, false><<<grid, kStThreads, smem, stream>>>(raw, z, noise, rays_d, ray_stride, R, white, rgb, disp, acc, depth, weights, alpha);
+    *rc = check_launch("composite_fwd_pair64_kernel");
+    return R;
+  }
   const size_t ray_bytes = (size_t)S * (noise ? 24 : 20);
   const int dmax = (int)(kStagedSmemBudget / (kStWarps * ray_bytes));
   const int D = dmax >= 8 ? 8 : (dmax >= 4 ? 4 : 2);

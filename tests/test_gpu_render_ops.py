@@ -102,6 +102,21 @@ def test_composite_vs_oracle(G, R, S):
         rel_close(v, want[k], rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("S", [64, 128])
+def test_composite_many_rays_per_warp(G, S):
+    """Enough rays (odd count) that every persistent warp runs tens of iterations: ring wrap-around, the per-32-ray
+    refresh of the direction norms, the single-ray last pair of the two-rays-per-warp kernel."""
+    R = 3 * 65536 + 1
+    g = torch.Generator().manual_seed(S)
+    raw = torch.randn(R, S, 4, generator=g)
+    z = torch.sort(torch.rand(R, S, generator=g) * 6.8 + 1.2, -1)[0]
+    d = torch.randn(R, 3, generator=g)
+    want = O.composite(raw, z, d, None, False)
+    rgb, disp, acc, w, depth, _ = G.ops.composite(dev(raw), dev(z), dev(d), None, False)
+    for k, v in (("rgb", rgb), ("disp", disp), ("acc", acc), ("weights", w), ("depth", depth)):
+        rel_close(v, want[k], rtol=1e-5, atol=1e-6)
+
+
 def test_composite_backward_golden(G, golden):
     g = golden("raw2outputs.npz")
     R = g["raw"].shape[0]
