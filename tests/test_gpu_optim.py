@@ -35,6 +35,7 @@ def test_fused_adam_matches_torch_adam_and_repacks_in_place(G):
     ref = torch.optim.Adam(a.parameters(), lr=3e-3, betas=(0.9, 0.999))
     opt = G.FusedAdam(b.parameters(), lr=3e-3, betas=(0.9, 0.999))
     assert isinstance(opt, torch.optim.Adam)
+    in_place = G._lib.load().gbn_mlp_variant() == 1   # env GBNERF_MLP=ss/tq: other image layouts, re-packed lazily
     n0 = G._lib.kernel_launches()
     b.packed_weights(), b.packed_weights_bwd()
     n_pack = G._lib.kernel_launches() - n0
@@ -58,7 +59,7 @@ def test_fused_adam_matches_torch_adam_and_repacks_in_place(G):
         # the weight images were patched in place: byte-identical to a fresh re-pack of the new parameters
         n2 = G._lib.kernel_launches()
         fwd, bwd = b.packed_weights(), b.packed_weights_bwd()
-        assert G._lib.kernel_launches() == n2, "no re-pack pass after a fused step"
+        assert not in_place or G._lib.kernel_launches() == n2, "no re-pack pass after a fused step"
         # (re-packing over a copy: bytes the packer never writes - alignment gaps - keep their old content)
         assert torch.equal(fwd, ops.prepack_weights(b.param_list(), "bf16", out=fwd.clone()))
         assert torch.equal(bwd, ops.prepack_weights(b.param_list(), "bf16_bwd", out=bwd.clone()))
