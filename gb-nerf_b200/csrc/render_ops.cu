@@ -694,6 +694,10 @@ __global__ void __launch_bounds__(256) loss_seed_kernel(const float* __restrict_
 int64_t launch_composite_fwd_staged(const float* raw, const float* z, const float* rays_d, int64_t ray_stride,
                                     const float* noise, int64_t R, int S, int white, float* rgb, float* disp, float* acc,
                                     float* depth, float* weights, float* alpha, cudaStream_t stream, int* rc);  // render_staged.cu
+int launch_composite_bwd_staged(const float* raw, const float* z, const float* rays_d, int64_t ray_stride, const float* noise,
+                                int64_t R, int S, int white, int detach_w, const float* g_rgb, const float* g_disp,
+                                const float* g_acc, const float* g_depth, const float* g_w, float* g_raw, cudaStream_t stream,
+                                int* rc);  // render_staged.cu
 }  // namespace gbn
 
 // =========================================================================================================
@@ -769,6 +773,12 @@ extern "C" int gbn_composite_backward(const float* raw, const float* z, const fl
   GBN_REQUIRE(R >= 0 && S >= 1 && S <= 1024, "composite_backward: S=%d outside [1,1024]", S);
   GBN_REQUIRE(((reinterpret_cast<uintptr_t>(raw) | reinterpret_cast<uintptr_t>(g_raw)) & 15) == 0,
               "composite_backward: raw/g_raw must be 16-byte aligned");
+  {
+    int rc = GBN_OK;
+    if (launch_composite_bwd_staged(raw, z, rays_d, ray_stride, noise, R, S, white_bkgd, detach_weights, g_rgb, g_disp, g_acc,
+                                    g_depth, g_weights, g_raw, (cudaStream_t)stream, &rc))
+      return rc;
+  }
   const int grid = persistent_grid(R, 6);
 #define CALL(N) composite_bwd_kernel<N><<<grid, kThreads, 0, (cudaStream_t)stream>>>(                   \
       raw, z, rays_d, ray_stride, noise, R, S, white_bkgd, detach_weights, g_rgb, g_disp, g_acc, g_depth, \

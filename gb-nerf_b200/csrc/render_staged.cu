@@ -331,6 +331,191 @@ __global__ void __launch_bounds__(kStThreads) composite_fwd_pair64_kernel(
   }
 }
 
+// ---- compositing backward, staged ---------------------------------------------------------------------------------
+// Same staging and ownership as the forward (a lane owns K consecutive samples of its ray, operands arrive through a
+// per-warp cp.async ring), so the transmittance is one forward product scan and the "sum of G_k w_k over later samples"
+// one reverse sum scan per ray; the generic kernel (lane-strided samples) needs one pair of scans per 32-sample chunk
+// and ran 1017 warp instructions per 128-sample ray.  Gradient formulas: SURVEY §8a row 13 (checked against autograd
+// of the reference raw2outputs).  The forward quantities are recomputed, nothing is stashed.
+template <int K, int D, bool NOISE, bool GW>
+__global__ void __launch_bounds__(kStThreads, K <= 2 ? 4 : 3) composite_bwd_staged_kernel(
+    const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ noise,
+    const float* __restrict__ d, int64_t stride, int64_t R, int white, int detach_w,
+    const float* __restrict__ g_rgb, const float* __restrict__ g_disp, const float* __restrict__ g_acc,
+    const float* __restrict__ g_depth, const float* __restrict__ g_w, float* __restrict__ g_raw) {
+  constexpr int S = 32 * K;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t ray_bytes = (uint32_t)S * (20u + (NOISE ? 4u : 0u) + (GW ? 4u : 0u));   // raw | z | noise | g_w
+  constexpr uint32_t off_z = S * 16, off_n = S * 20, off_g = S * (NOISE ? 24 : 20);
+  uint8_t* const ring = smem + (size_t)warp * D * ray_bytes;
+  const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
+  const int64_t nwarps = (int64_t)gridDim.x * kStWarps;
+  const int64_t w0 = (int64_t)blockIdx.x * kStWarps + warp;
+  const int64_t my_rays = w0 < R ? (R - w0 + nwarps - 1) / nwarps : 0;
+
+  auto issue = [&](int64_t i) {
+    const int64_t ray = w0 + i * nwarps;
+    const uint32_t dst = ring_u32 + (uint32_t)(i % D) * ray_bytes;
+    const float4* rsrc = reinterpret_cast<const float4*>(raw) + ray * S;
+#pragma unroll
+    for (int k = 0; k < K; ++k) cp_async16(dst + (k * 32 + lane) * 16, rsrc + k * 32 + lane);
+    if (K % 4 == 0 || lane < 8 * K) {      // S floats = S/4 sixteen-byte pieces
+#pragma unroll
+      for (int k = 0; k < (K + 3) / 4; ++k) {
+        cp_async16(dst + off_z + (k * 32 + lane) * 16, reinterpret_cast<const float4*>(z + ray * S) + k * 32 + lane);
+        if (NOISE) cp_async16(dst + off_n + (k * 32 + lane) * 16, reinterpret_cast<const float4*>(noise + ray * S) + k * 32 + lane);
+        if (GW) cp_async16(dst + off_g + (k * 32 + lane) * 16, reinterpret_cast<const float4*>(g_w + ray * S) + k * 32 + lane);
+      }
+    }
+  };
+#pragma unroll
+  for (int j = 0; j < D - 1; ++j) {
+    if (j < my_rays) issue(j);
+    cp_async_commit();
+  }
+  // per-ray scalars (|d| and the six incoming gradients) are fetched for 32 rays at a time, one ray per lane
+  float dn_l = 0.f, gr_l = 0.f, gg_l = 0.f, gb_l = 0.f, gdisp_l = 0.f, gacc_l = 0.f, gdep_l = 0.f;
+  for (int64_t i = 0; i < my_rays; ++i) {
+    const int64_t ray = w0 + i * nwarps;
+    if (i + D - 1 < my_rays) issue(i + D - 1);
+    cp_async_commit();
+    if ((i & 31) == 0) {
+      const int64_t ii = i + lane;
+      if (ii < my_rays) {
+        const int64_t r = w0 + ii * nwarps;
+        const float dx = __ldg(d + r * stride), dy = __ldg(d + r * stride + 1), dz = __ldg(d + r * stride + 2);
+        dn_l = sqrtf(dx * dx + dy * dy + dz * dz);
+        gr_l = g_rgb ? __ldg(g_rgb + r * 3) : 0.f; gg_l = g_rgb ? __ldg(g_rgb + r * 3 + 1) : 0.f; gb_l = g_rgb ? __ldg(g_rgb + r * 3 + 2) : 0.f;
+        gdisp_l = g_disp ? __ldg(g_disp + r) : 0.f; gacc_l = g_acc ? __ldg(g_acc + r) : 0.f; gdep_l = g_depth ? __ldg(g_depth + r) : 0.f;
+      }
+    }
+    const int src = (int)(i & 31);
+    const float dnorm = __shfl_sync(kFullMask, dn_l, src);
+    const float gr = __shfl_sync(kFullMask, gr_l, src), gg = __shfl_sync(kFullMask, gg_l, src), gb = __shfl_sync(kFullMask, gb_l, src);
+    const float gdisp = __shfl_sync(kFullMask, gdisp_l, src);
+    float gacc = __shfl_sync(kFullMask, gacc_l, src), gdep = __shfl_sync(kFullMask, gdep_l, src);
+    cp_async_wait<D - 1>();
+    __syncwarp();
+    const uint8_t* st = ring + (size_t)(i % D) * ray_bytes;
+    float4 rw[K];
+    float zz[K], nz[K], gw[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      rw[k] = reinterpret_cast<const float4*>(st)[lane * K + k];
+      zz[k] = reinterpret_cast<const float*>(st + off_z)[lane * K + k];
+      nz[k] = NOISE ? reinterpret_cast<const float*>(st + off_n)[lane * K + k] : 0.f;
+      gw[k] = GW ? reinterpret_cast<const float*>(st + off_g)[lane * K + k] : 0.f;
+    }
+    __syncwarp();   // slot may be refilled by the next iteration's issue
+    // ---- forward again: alpha, e = exp(-sigma delta), delta, transmittance T -------------------------------------------
+    const float znext_lane = __shfl_down_sync(kFullMask, zz[0], 1);
+    float a[K], e[K], dlt[K], T[K];
+    float prod = 1.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float zn = (k + 1 < K) ? zz[k + 1 < K ? k + 1 : k] : znext_lane;
+      const float dl = (lane == 31 && k == K - 1) ? 1e10f : (zn - zz[k]);
+      dlt[k] = dl * dnorm;
+      const float sigma = fmaxf(rw[k].w + nz[k], 0.f);
+      e[k] = __expf(-sigma * dlt[k]);
+      a[k] = 1.f - e[k];
+      T[k] = prod;
+      prod *= (1.f - a[k]) + 1e-10f;
+    }
+    const float incl = warp_scan_mul(prod, lane);
+    float excl = __shfl_up_sync(kFullMask, incl, 1);
+    if (lane == 0) excl = 1.f;
+    float sd = 0.f, sa = 0.f;
+    float w[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      T[k] *= excl;
+      w[k] = a[k] * T[k];
+      sd = fmaf(w[k], zz[k], sd);
+      sa += w[k];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sd += __shfl_xor_sync(kFullMask, sd, o); sa += __shfl_xor_sync(kFullMask, sa, o); }
+    // disp = 1 / max(1e-10, depth / acc): above the clamp disp = acc / depth
+    if (gdisp != 0.f) {
+      const float q = sd / sa;
+      if (!(q <= 1e-10f)) {   // also taken for NaN, which then propagates as in autograd
+        gdep += -gdisp * sa / (sd * sd);
+        gacc += gdisp / sd;
+      }
+    }
+    if (white) gacc -= gr + gg + gb;
+    // ---- G_k, suffix sums of G_k w_k, gradients --------------------------------------------------------------------
+    constexpr bool kKeepColours = K <= 2;   // K = 4: recomputing three sigmoids is cheaper than 12 more live registers
+    float G[K], suf[K], c3[kKeepColours ? K : 1][3];
+    float run = 0.f;
+#pragma unroll
+    for (int k = K - 1; k >= 0; --k) {
+      const float cr = fast_sigmoid(rw[k].x), cg = fast_sigmoid(rw[k].y), cb = fast_sigmoid(rw[k].z);
+      if (kKeepColours) { c3[k][0] = cr; c3[k][1] = cg; c3[k][2] = cb; }
+      G[k] = gdep * zz[k] + gacc + gw[k];
+      if (!detach_w) G[k] += gr * cr + gg * cg + gb * cb;
+      suf[k] = run;                 // later samples inside this lane
+      run = fmaf(G[k], w[k], run);
+    }
+    const float rincl = warp_rscan_add(run, lane);
+    float later = __shfl_down_sync(kFullMask, rincl, 1);   // lanes above this one
+    if (lane == 31) later = 0.f;
+    float4* out = reinterpret_cast<float4*>(g_raw) + ray * S + lane * K;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float f = (1.f - a[k]) + 1e-10f;
+      const float dalpha = G[k] * T[k] - __fdividef(suf[k] + later, f);
+      const float pre = rw[k].w + nz[k];
+      const float cr = kKeepColours ? c3[k][0] : fast_sigmoid(rw[k].x), cg = kKeepColours ? c3[k][1] : fast_sigmoid(rw[k].y),
+                  cb = kKeepColours ? c3[k][2] : fast_sigmoid(rw[k].z);
+      float4 o;
+      o.x = w[k] * gr * cr * (1.f - cr);
+      o.y = w[k] * gg * cg * (1.f - cg);
+      o.z = w[k] * gb * cb * (1.f - cb);
+      o.w = (pre > 0.f) ? dalpha * dlt[k] * e[k] : 0.f;
+      st_stream4(out + k, o);
+    }
+  }
+}
+
+// returns 1 when it launched (shape S = 64 or 128, 16-byte aligned operands), 0 when the caller must use the generic kernel
+int launch_composite_bwd_staged(const float* raw, const float* z, const float* rays_d, int64_t ray_stride, const float* noise,
+                                int64_t R, int S, int white, int detach_w, const float* g_rgb, const float* g_disp,
+                                const float* g_acc, const float* g_depth, const float* g_w, float* g_raw, cudaStream_t stream,
+                                int* rc) {
+  *rc = GBN_OK;
+  static const bool off = [] { const char* e = getenv("GBNERF_COMP_BWD_GENERIC"); return e && e[0] == '1'; }();
+  const uintptr_t al = reinterpret_cast<uintptr_t>(raw) | reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(noise) |
+                       reinterpret_cast<uintptr_t>(g_w) | reinterpret_cast<uintptr_t>(g_raw);
+  if (off || R < 1 || (S != 64 && S != 128) || (al & 15) != 0) return 0;
+  const int64_t blocks = (R + kStWarps - 1) / kStWarps, cap = (int64_t)kNumSMs * 4;
+  const int grid = (int)(blocks < cap ? blocks : cap);
+#define GBN_BW_LAUNCH(KK, NN, GG)                                                                                       \
+  do {                                                                                                                  \
+    constexpr int DD = 2;                                                                                               \
+    constexpr size_t smem = (size_t)kStWarps * DD * 32 * KK * (20 + (NN ? 4 : 0) + (GG ? 4 : 0));                       \
+    static bool attr = false;                                                                                           \
+    if (!attr) {                                                                                                        \
+      cudaFuncSetAttribute(composite_bwd_staged_kernel<KK, DD, NN, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      attr = true;                                                                                                      \
+    }                                                                                                                   \
+    composite_bwd_staged_kernel<KK, DD, NN, GG><<<grid, kStThreads, smem, stream>>>(                                    \
+        raw, z, noise, rays_d, ray_stride, R, white, detach_w, g_rgb, g_disp, g_acc, g_depth, g_w, g_raw);              \
+  } while (0)
+#define GBN_BW_K(KK)                                                                                                    \
+  do {                                                                                                                  \
+    if (noise) { if (g_w) GBN_BW_LAUNCH(KK, true, true); else GBN_BW_LAUNCH(KK, true, false); }                         \
+    else { if (g_w) GBN_BW_LAUNCH(KK, false, true); else GBN_BW_LAUNCH(KK, false, false); }                             \
+  } while (0)
+  if (S == 64) GBN_BW_K(2); else GBN_BW_K(4);
+#undef GBN_BW_K
+#undef GBN_BW_LAUNCH
+  *rc = check_launch("composite_bwd_staged_kernel");
+  return 1;
+}
+
 // Launches the staged kernel when the shapes allow (S <= 256, 16-byte aligned raw); returns how many rays it took
 // (0 = the caller uses the generic kernel).
 int64_t launch_composite_fwd_staged(const float* raw, const float* z, const float* rays_d, int64_t ray_stride,
