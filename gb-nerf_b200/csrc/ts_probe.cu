@@ -6,6 +6,9 @@
 namespace gbn {
 using namespace tc;
 
+// F16: fp16 operands and an fp16 accumulator (idesc c_format = a_format = b_format = 0); D then receives the RAW
+// 32-bit TMEM cells of columns [0,128) so that the host can establish how 16-bit accumulators are laid out.
+template <bool F16>
 __global__ void __launch_bounds__(128, 1) ts_probe_kernel(const uint16_t* __restrict__ A, const uint8_t* __restrict__ Bimg,
                                                           float* __restrict__ D, int a_col, int col_per_kstep) {
   extern __shared__ uint8_t smem_raw[];
@@ -41,7 +44,7 @@ __global__ void __launch_bounds__(128, 1) ts_probe_kernel(const uint16_t* __rest
   tc_fence_after_sync();
   if (warp == 0) {
     const uint64_t bdesc = smem_desc_sw128(base);
-    const uint32_t idesc = make_idesc(1, 128, 128);
+    const uint32_t idesc = F16 ? (((128u >> 3) << 17) | ((128u >> 4) << 24)) : make_idesc(1, 128, 128);
     if (elect_one()) {
       for (int k = 0; k < 4; ++k) {
         const uint32_t a_t = tmem + a_col + k * col_per_kstep;
@@ -73,8 +76,19 @@ extern "C" int gbn_debug_ts_mma(const void* A, const void* Bimg, float* D, int a
   using namespace gbn;
   GBN_REQUIRE(A && Bimg && D, "debug_ts_mma: null pointer");
   static bool attr = false;
-  if (!attr) { GBN_CUDA(cudaFuncSetAttribute(ts_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 20480)); attr = true; }
-  ts_probe_kernel<<<1, 128, 16384 + 64 + 1024, (cudaStream_t)stream>>>(static_cast<const uint16_t*>(A),
-                                                                        static_cast<const uint8_t*>(Bimg), D, a_col, col_per_kstep);
+  if (!attr) { GBN_CUDA(cudaFuncSetAttribute(ts_probe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 20480)); attr = true; }
+  ts_probe_kernel<false><<<1, 128, 16384 + 64 + 1024, (cudaStream_t)stream>>>(static_cast<const uint16_t*>(A),
+                                                                               static_cast<const uint8_t*>(Bimg), D, a_col, col_per_kstep);
   return check_launch("ts_probe_kernel");
+}
+
+extern "C" int gbn_debug_ts_mma_f16(const void* A, const void* Bimg, void* D_raw, int a_col, int col_per_kstep, void* stream) {
+  using namespace gbn;
+  GBN_REQUIRE(A && Bimg && D_raw, "debug_ts_mma_f16: null pointer");
+  static bool attr = false;
+  if (!attr) { GBN_CUDA(cudaFuncSetAttribute(ts_probe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 20480)); attr = true; }
+  ts_probe_kernel<true><<<1, 128, 16384 + 64 + 1024, (cudaStream_t)stream>>>(static_cast<const uint16_t*>(A),
+                                                                              static_cast<const uint8_t*>(Bimg),
+                                                                              static_cast<float*>(D_raw), a_col, col_per_kstep);
+  return check_launch("ts_probe_kernel<f16>");
 }
