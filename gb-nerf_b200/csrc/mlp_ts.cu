@@ -63,7 +63,8 @@ struct TsSmemT {
   static constexpr uint32_t m_empty = m_full + 16;                  // [2]
   static constexpr uint32_t dir_full = m_empty + 16;
   static constexpr uint32_t dir_empty = dir_full + 8;
-  static constexpr uint32_t tmem_ptr = dir_empty + 8;
+  static constexpr uint32_t acc1_empty = dir_empty + 8;
+  static constexpr uint32_t tmem_ptr = acc1_empty + 8;
   static constexpr uint32_t abort_flag = tmem_ptr + 4;
   static constexpr uint32_t total = abort_flag + 4;
   static constexpr uint32_t alloc = total + 1024;
@@ -84,6 +85,7 @@ struct TsArgs {
   int S, njobs, nsteps;
   int ready_per_tile[4];
   int order_per_tile;
+  int empty1_per_tile;
 };
 
 __device__ __forceinline__ void ts_wait(uint32_t bar, uint32_t parity, uint32_t abort_addr, int* err, int code) {
@@ -161,6 +163,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
     for (int i = 0; i < 2; ++i) { mbar_init(base + L::m_full + 8 * i, 1); mbar_init(base + L::m_empty + 8 * i, 256); }
     mbar_init(base + L::dir_full, 128);
     mbar_init(base + L::dir_empty, 1);
+    mbar_init(base + L::acc1_empty, 256);
     *reinterpret_cast<volatile uint32_t*>(gen + L::abort_flag) = 0;
     mbar_init_fence();
   }
@@ -224,6 +227,10 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
             const uint32_t seq = (uint32_t)t * a.ready_per_tile[b] + ((jb.wait_buf >> 4) & 7);
             ts_wait(base + L::a_ready + 8 * b, seq & 1, abort_addr, a.err, 0x21800000 | j);
           }
+        }
+        if (jb.flags & TJ_WAIT_EMPTY1) {
+          const uint32_t seq = (uint32_t)t * a.empty1_per_tile + ((jb.wait_buf >> 7) & 1);
+          ts_wait(base + L::acc1_empty, seq & 1, abort_addr, a.err, 0x25000000 | j);
         }
         if (jb.flags & TJ_WAIT_ORDER) {
           const uint32_t seq = (uint32_t)t * a.order_per_tile + ((jb.ksteps >> 4) & 7);
@@ -477,6 +484,12 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
         tmem_ld32(lane_addr + acc_col, v[0]);
         tmem_ld32(lane_addr + acc_col + 32, v[1]);
         tmem_ld_wait();
+        if constexpr (!BWD) {
+          if (st.acc == 1) {          // acc1 is in registers: the next layer's half-1 MMAs may overwrite it
+            tc_fence_before_sync();
+            mbar_arrive(base + L::acc1_empty);
+          }
+        }
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           float f[32];
@@ -598,8 +611,12 @@ const TsPlan& ts_plan(int bwd) {
   std::call_once(g_ts_once, [] {
     const char* e = getenv("GBNERF_TS_STAGGER");
     const bool stagger = e && e[0] == '1';
-    g_ts_plan[0] = make_ts_plan(kTsFwd, stagger);
-    g_ts_plan[1] = make_ts_plan(kTsBwd, stagger);
+    const char* ee = getenv("GBNERF_TS_EARLY");
+    const bool early = !(ee && ee[0] == '0');
+    const char* ko = getenv("GBNERF_TS_KHI_ORDER");
+    const bool khi = ko && ko[0] == '1';   // measured slower (1030 vs 1052-1064 TFLOP/s): off unless asked for
+    g_ts_plan[0] = make_ts_plan(kTsFwd, stagger, early, khi);
+    g_ts_plan[1] = make_ts_plan(kTsBwd, stagger, early, khi);
   });
   return g_ts_plan[bwd ? 1 : 0];
 }
@@ -781,6 +798,7 @@ int ts_forward(const void* packed, const float* ro, const float* rd, const float
   a.njobs = (int)p.jobs.size(); a.nsteps = (int)p.steps.size();
   for (int i = 0; i < 4; ++i) a.ready_per_tile[i] = p.ready_per_tile[i];
   a.order_per_tile = p.order_per_tile;
+  a.empty1_per_tile = p.empty1_per_tile;
   mlp_get_trace(&a.trace, &a.trace_tile);
   const int64_t ntiles = (a.P + kTileRows - 1) / kTileRows;
   const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
@@ -804,6 +822,7 @@ int ts_backward_data(const void* packed_bwd, const float* g_raw, int64_t P, cons
   a.njobs = (int)p.jobs.size(); a.nsteps = (int)p.steps.size();
   for (int i = 0; i < 4; ++i) a.ready_per_tile[i] = p.ready_per_tile[i];
   a.order_per_tile = p.order_per_tile;
+  a.empty1_per_tile = p.empty1_per_tile;
   const int64_t ntiles = (P + kTileRows - 1) / kTileRows;
   const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
   nerf_mlp_ts_kernel<true><<<grid, kTsThreads, TsSmemT<true>::alloc, stream>>>(a);

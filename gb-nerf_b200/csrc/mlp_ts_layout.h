@@ -32,7 +32,10 @@ enum : uint16_t {
   // its half, so half 0 finishes first and is drained/converted while half 1's MMAs run
   TJ_SIGNAL_ORDER = 512, TJ_WAIT_ORDER = 1024,
   // the view-direction encoding block in shared memory as A operand (direction columns of views_linears.0)
-  TJ_A_DIR = 2048, TJ_WAIT_DIR = 4096, TJ_COMMIT_DIR = 8192
+  TJ_A_DIR = 2048, TJ_WAIT_DIR = 4096, TJ_COMMIT_DIR = 8192,
+  // acc1 has been read out by the epilogue (signalled right after its tcgen05.ld, ~600 cycles before the converted
+  // activations are handed over): lets the first MMAs of the next layer's half 1 overlap the rest of that epilogue step
+  TJ_WAIT_EMPTY1 = 16384
 };
 constexpr int kTsBiasViews = kBiasFloats;            // b_views appended to the bias block (128 floats)
 constexpr int kTsBiasFloats = kBiasFloats + 128;
@@ -80,19 +83,21 @@ struct TsPlan {
   int id;
   int ready_per_tile[4];   // completions of a_ready[buf][half] per tile
   int order_per_tile;      // issue-order signals per tile
+  int empty1_per_tile;     // acc1-drained signals per tile (forward program)
   std::vector<TsJob> jobs;
   std::vector<TsStep> steps;
   std::vector<TsPackJob> pack;
   uint32_t off_bias, off_wdir, off_bdir, total_bytes;
 };
 
-inline TsPlan make_ts_plan(int id, bool stagger = false) {
+inline TsPlan make_ts_plan(int id, bool stagger = false, bool early_empty = true, bool khi_order = false) {
   TsPlan p;
   p.id = id;
   uint32_t off = 256;
   const bool tr = (id == kTsBwd);
   int done[4] = {0, 0, 0, 0};   // completions of a_ready[buf*2+half] emitted so far (steps are added in program order)
   int order = 0;                // issue-order signals emitted so far
+  int empty1 = 0;               // acc1-drained signals emitted so far (one per epilogue step on acc1)
   // forward slab(n, k)  = W[row0 + n][col0 + k - koff]
   // backward slab(n, k) = W[row0 + k - koff][col0 + n]      (transposed: N = layer input, K = layer output)
   auto job = [&](int layer, int ld, int row0, int rows_valid, int rows, int col0, int cols_valid, int koff, int nkb,
@@ -101,7 +106,8 @@ inline TsPlan make_ts_plan(int id, bool stagger = false) {
     j.w_off = off; j.w_bytes16 = (uint16_t)(nkb * rows * 8); j.flags = (uint16_t)flags; j.d_col = (uint16_t)d_col;
     j.a_col = (uint16_t)a_col; j.n16 = (uint8_t)(rows / 16); j.nkb = (uint8_t)nkb; j.ksteps = (uint8_t)ksteps;
     const int s0 = done[wait_buf * 2] - 1, s1 = done[wait_buf * 2 + 1] - 1;
-    j.wait_buf = (uint8_t)(wait_buf | ((s0 < 0 ? 0 : s0) << 1) | ((s1 < 0 ? 0 : s1) << 4));
+    j.wait_buf = (uint8_t)(wait_buf | ((s0 < 0 ? 0 : s0) << 1) | ((s1 < 0 ? 0 : s1) << 4) |
+                           ((flags & TJ_WAIT_EMPTY1) ? (((empty1 - 1) & 1) << 7) : 0));
     p.jobs.push_back(j);
     TsPackJob q{};
     q.w_off = off; q.layer = (uint16_t)layer; q.ld = (uint16_t)ld; q.row0 = (uint16_t)row0; q.rows_valid = (uint16_t)rows_valid;
@@ -115,6 +121,7 @@ inline TsPlan make_ts_plan(int id, bool stagger = false) {
     s.acc = (uint8_t)acc; s.mode = (uint8_t)mode; s.out_buf = (uint8_t)out_buf; s.out_half = (uint8_t)out_half;
     s.no_act = (uint8_t)no_act; s.mask_blk = (uint8_t)mask_blk; s.out_blk = (uint8_t)out_blk; s.bias_off = (uint16_t)bias_off;
     if (!no_act && mode != EPI_OUT) ++done[out_buf * 2 + out_half];
+    if (acc == 1 && mode != EPI_OUT) ++empty1;
     p.steps.push_back(s);
   };
   const uint32_t abuf[2] = {kTsA0, kTsA1}, accc[2] = {kTsAcc0, kTsAcc1};
@@ -129,11 +136,21 @@ inline TsPlan make_ts_plan(int id, bool stagger = false) {
         // K-blocks 0-1 as soon as input half 0 is back (that also certifies acc0 drained) and needs input half 1
         // for K-blocks 2-3; half 1 needs input half 0 (operand) and input half 1 (= acc1 drained) before its first MMA
         if (h == 0) fl |= (kp == 0) ? TJ_WAIT_A0 : TJ_WAIT_A1;
-        else if (kp == 0) fl |= TJ_WAIT_A0 | TJ_WAIT_A1;
+        else if (tr || !early_empty) fl |= (kp == 0) ? (TJ_WAIT_A0 | TJ_WAIT_A1) : 0;
+        else fl |= (kp == 0) ? (TJ_WAIT_A0 | TJ_WAIT_EMPTY1) : TJ_WAIT_A1;   // forward: acc1 is free before input half 1 is back
         if (kp == 0) fl |= TJ_FIRST;
         if (kp == 1 && !extra) fl |= commit[h];
         if (!tr) job(layer, ld, 128 * h, 128, 128, col0 + 128 * kp, 128, 0, 2, 4, fl, accc[h], abuf[in] + 64 * kp, in);
         else job(layer, ld, 128 * kp, 128, 128, col0 + 128 * h, 128, 0, 2, 4, fl, accc[h], abuf[in] + 64 * kp, in);
+        // Both K-high jobs become ready at the same moment (input half 1 handed over).  Half 0's gates the next
+        // epilogue step, half 1's has a whole epilogue step of slack: half 1's issuer lets half 0's go first, so that
+        // it gets the tensor pipe to itself instead of sharing it.  (Experiment, GBNERF_TS_KHI_ORDER=1: measured 2-3 % slower.)
+        if (!tr && khi_order && !stagger && kp == 1) {
+          TsJob& jb = p.jobs.back();
+          jb.flags |= (h == 0) ? TJ_SIGNAL_ORDER : TJ_WAIT_ORDER;
+          jb.ksteps |= (uint8_t)((order & 7) << 4);
+          if (h == 1) ++order;
+        }
       }
   };
 
@@ -177,7 +194,8 @@ inline TsPlan make_ts_plan(int id, bool stagger = false) {
     // views_linears.0: the feature (K = 256) from TMEM + the 27 direction columns on the direction block in smem
     for (int kp = 0; kp < 2; ++kp)
       job(LIN_VIEWS, 283, 0, 128, 128, 128 * kp, 128, 0, 2, 4,
-          kp == 0 ? (TJ_WAIT_A0 | TJ_WAIT_A1 | TJ_FIRST) : 0, kTsAcc1, abuf[0] + 64 * kp, 0);
+          kp == 0 ? (TJ_WAIT_A0 | (early_empty ? TJ_WAIT_EMPTY1 : TJ_WAIT_A1) | TJ_FIRST) : (early_empty ? TJ_WAIT_A1 : 0), kTsAcc1,
+          abuf[0] + 64 * kp, 0);
     job(LIN_VIEWS, 283, 0, 128, 128, 256, 27, 0, 1, 2, TJ_A_SMEM | TJ_A_DIR | TJ_WAIT_DIR | TJ_COMMIT_DIR | TJ_COMMIT_ACC1, kTsAcc1,
         0, 0);
     step(1, EPI_BIAS_RELU, 1, 0, 0, 0xff, kHHv, kTsBiasViews);
@@ -234,6 +252,7 @@ inline TsPlan make_ts_plan(int id, bool stagger = false) {
     }
   }
   p.order_per_tile = order;
+  p.empty1_per_tile = empty1;
   for (int i = 0; i < 4; ++i) p.ready_per_tile[i] = done[i];
   p.off_bias = off;
   off += kTsBiasFloats * 4;
