@@ -484,11 +484,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
         tmem_ld32(lane_addr + acc_col, v[0]);
         tmem_ld32(lane_addr + acc_col + 32, v[1]);
         tmem_ld_wait();
-        if constexpr (!BWD) {
-          if (st.acc == 1) {          // acc1 is in registers: the next layer's half-1 MMAs may overwrite it
-            tc_fence_before_sync();
-            mbar_arrive(base + L::acc1_empty);
-          }
+        if (st.acc == 1) {            // acc1 is in registers: the next layer's half-1 MMAs may overwrite it
+          tc_fence_before_sync();
+          mbar_arrive(base + L::acc1_empty);
         }
 #pragma unroll
         for (int g = 0; g < 2; ++g) {

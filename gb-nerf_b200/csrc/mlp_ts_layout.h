@@ -136,8 +136,8 @@ inline TsPlan make_ts_plan(int id, bool stagger = false, bool early_empty = true
         // K-blocks 0-1 as soon as input half 0 is back (that also certifies acc0 drained) and needs input half 1
         // for K-blocks 2-3; half 1 needs input half 0 (operand) and input half 1 (= acc1 drained) before its first MMA
         if (h == 0) fl |= (kp == 0) ? TJ_WAIT_A0 : TJ_WAIT_A1;
-        else if (tr || !early_empty) fl |= (kp == 0) ? (TJ_WAIT_A0 | TJ_WAIT_A1) : 0;
-        else fl |= (kp == 0) ? (TJ_WAIT_A0 | TJ_WAIT_EMPTY1) : TJ_WAIT_A1;   // forward: acc1 is free before input half 1 is back
+        else if (!early_empty) fl |= (kp == 0) ? (TJ_WAIT_A0 | TJ_WAIT_A1) : 0;
+        else fl |= (kp == 0) ? (TJ_WAIT_A0 | TJ_WAIT_EMPTY1) : TJ_WAIT_A1;   // acc1 is free before input half 1 is back
         if (kp == 0) fl |= TJ_FIRST;
         if (kp == 1 && !extra) fl |= commit[h];
         if (!tr) job(layer, ld, 128 * h, 128, 128, col0 + 128 * kp, 128, 0, 2, 4, fl, accc[h], abuf[in] + 64 * kp, in);
