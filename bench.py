@@ -312,7 +312,9 @@ def train_step_bench(G, ops, dev, nets, kw_test, rank, world, timed):
         return loss
 
     steps = 10
-    ms, launches, events, _ = timed(step, steps, 3, kernel_events=True)
+    passes = [timed(step, steps, 3 if i == 0 else 0, kernel_events=True) for i in range(2)]   # see run_ours: idle gaps
+    ms, launches, events, _ = min(passes, key=lambda r: r[0])
+    both_ms = [round(r[0] / steps, 3) for r in passes]
     per = {}
     for name, a, b, pts in events:
         d = per.setdefault(name, [0.0, 0])
@@ -324,7 +326,7 @@ def train_step_bench(G, ops, dev, nets, kw_test, rank, world, timed):
             "unit": "rays/s", "ms_per_step": ms / steps, "rays_per_gpu": R, "scaling": "weak",
             "mlp_kernels_ms_per_step": {k: v[0] / steps for k, v in per.items()},
             "mlp_tflops_fwd_equivalent": flop / (t_mlp * 1e-3) / 1e12 if t_mlp else None,
-            "grad_allreduce_bytes": bucket.flat.numel() * 4, "gpu_launches": launches}
+            "grad_allreduce_bytes": bucket.flat.numel() * 4, "gpu_launches": launches, "passes_ms_per_step": both_ms}
 
 
 def profile_traffic_bytes():
@@ -362,12 +364,14 @@ def tcnn_bench(G, ops, dev, kw_test, rank, world, timed):
             return G.render(H, W, FOCAL, chunk=chunk, rays=rays, **kw)
 
     steps = 5
-    ms, launches, events, _ = timed(step, steps, 3, kernel_events=True)
+    passes = [timed(step, steps, 3 if i == 0 else 0, kernel_events=True) for i in range(2)]   # see run_ours: idle gaps
+    ms, launches, events, _ = min(passes, key=lambda r: r[0])
+    both_ms = [round(r[0] / steps, 3) for r in passes]
     t = sum(a.elapsed_time(b) for name, a, b, _ in events if name == "tcnn")
     pts = sum(p for name, _, _, p in events if name == "tcnn")
     return {"metric": "rays/sec, 262,144-ray inference render through the hash-grid model (coarse64+fine64)",
             "value": R * world * steps / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms / steps, "rays_per_gpu": R,
-            "scaling": "weak", "gpu_launches": launches,
+            "scaling": "weak", "gpu_launches": launches, "passes_ms_per_step": both_ms,
             "kernel": {"name": "tcnn_forward_kernel", "bound": "L2 gather (28 MB fp16 table, 512 B/point of 4-byte reads)",
                        "points_per_s": pts / (t * 1e-3) if t else None, "gather_GBps": pts * 512 / (t * 1e-3) / 1e9 if t else None,
                        "share_of_step": t / ms if ms else None, "parity": "unpinned (oracle/tcnn_oracle.py restates tiny-cuda-nn)"}}
