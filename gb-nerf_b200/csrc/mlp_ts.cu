@@ -64,7 +64,8 @@ struct TsSmemT {
   static constexpr uint32_t dir_full = m_empty + 16;
   static constexpr uint32_t dir_empty = dir_full + 8;
   static constexpr uint32_t acc1_empty = dir_empty + 8;
-  static constexpr uint32_t tmem_ptr = acc1_empty + 8;
+  static constexpr uint32_t a_ready_b = acc1_empty + 8;             // [buf]: second 32-channel groups of input half 1
+  static constexpr uint32_t tmem_ptr = a_ready_b + 16;
   static constexpr uint32_t abort_flag = tmem_ptr + 4;
   static constexpr uint32_t total = abort_flag + 4;
   static constexpr uint32_t alloc = total + 1024;
@@ -86,6 +87,7 @@ struct TsArgs {
   int ready_per_tile[4];
   int order_per_tile;
   int empty1_per_tile;
+  int no_split;            // debug (GBNERF_TS_SPLIT=0): K-high jobs wait for both instalments of input half 1 up front
 };
 
 __device__ __forceinline__ void ts_wait(uint32_t bar, uint32_t parity, uint32_t abort_addr, int* err, int code) {
@@ -143,6 +145,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
   using L = TsSmemT<BWD>;
   constexpr int kTsStages = L::NST;
   constexpr int PROG = BWD ? 1 : 0;
+  constexpr bool kSplit = BWD;            // two-instalment hand-over of input half 1
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* const gen = smem_raw + (base - smem_u32(smem_raw));
@@ -164,6 +167,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
     mbar_init(base + L::dir_full, 128);
     mbar_init(base + L::dir_empty, 1);
     mbar_init(base + L::acc1_empty, 256);
+    mbar_init(base + L::a_ready_b, 256); mbar_init(base + L::a_ready_b + 8, 256);
     *reinterpret_cast<volatile uint32_t*>(gen + L::abort_flag) = 0;
     mbar_init_fence();
   }
@@ -213,6 +217,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
         if ((jb.d_col >= kTsAcc1) != second) { ++cnt; continue; }
         unsigned long long* tr = (a.trace && blockIdx.x == 0 && t == a.trace_tile && lane == 0) ? a.trace : nullptr;
         if (tr) tr[4 * j] = clock64();
+        bool split = false;
+        uint32_t split_par = 0, split_bar = 0;
         if (jb.flags & kAnyWait) {
           if (jb.flags & TJ_WAIT_ENC) ts_wait(base + L::enc_full, t & 1, abort_addr, a.err, 0x20000000 | j);
           if (jb.flags & TJ_WAIT_DIR) ts_wait(base + L::dir_full, t & 1, abort_addr, a.err, 0x20800000 | j);
@@ -223,9 +229,19 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
             ts_wait(base + L::a_ready + 8 * b, seq & 1, abort_addr, a.err, 0x21000000 | j);
           }
           if (jb.flags & TJ_WAIT_A1) {
+            // (dgrad program only - its epilogue steps are long; measured -4 % on the forward kernel, +8 % on dgrad)
+            // Input half 1 comes back in two instalments: every epilogue thread hands over its first 32 channels
+            // (barrier a_ready[buf][1]: K 128-159 and 192-223), then its second 32 (a_ready_b[buf]).  The common
+            // 8-MMA job starts on the first instalment and waits for the second in mid-issue (below).
             const int b = (jb.wait_buf & 1) * 2 + 1;
             const uint32_t seq = (uint32_t)t * a.ready_per_tile[b] + ((jb.wait_buf >> 4) & 7);
             ts_wait(base + L::a_ready + 8 * b, seq & 1, abort_addr, a.err, 0x21800000 | j);
+            if constexpr (kSplit) {
+              split_par = seq & 1;
+              split_bar = base + L::a_ready_b + 8 * (jb.wait_buf & 1);
+              if ((jb.flags & TJ_A_SMEM) || jb.nkb != 2 || a.no_split) ts_wait(split_bar, split_par, abort_addr, a.err, 0x21c00000 | j);
+              else split = true;
+            }
           }
         }
         if (jb.flags & TJ_WAIT_EMPTY1) {
@@ -250,8 +266,24 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
         const uint32_t first = (jb.flags & TJ_FIRST) ? 0u : 1u;
         const bool a_smem = (jb.flags & TJ_A_SMEM) != 0;
         const uint64_t adesc = (jb.flags & TJ_A_DIR) ? adesc_dir : adesc_enc;
+        if (split) {   // K-high job: the four MMAs whose K ranges arrived first, then the rest
+          if (elect_one()) {
+            umma_bf16_ts(d, a_t, bd0, idesc, first);
+            umma_bf16_ts(d, a_t + 8, bd0 + 2, idesc, 1u);
+            umma_bf16_ts(d, a_t + 32, bd1, idesc, 1u);
+            umma_bf16_ts(d, a_t + 40, bd1 + 2, idesc, 1u);
+          }
+          __syncwarp();
+          ts_wait(split_bar, split_par, abort_addr, a.err, 0x21e00000 | j);
+          tc_fence_after_sync();
+        }
         if (elect_one()) {
-          if (!a_smem && jb.nkb == 2) {          // the common job: 8 back-to-back MMAs, A from TMEM
+          if (split) {
+            umma_bf16_ts(d, a_t + 16, bd0 + 4, idesc, 1u);
+            umma_bf16_ts(d, a_t + 24, bd0 + 6, idesc, 1u);
+            umma_bf16_ts(d, a_t + 48, bd1 + 4, idesc, 1u);
+            umma_bf16_ts(d, a_t + 56, bd1 + 6, idesc, 1u);
+          } else if (!a_smem && jb.nkb == 2) {          // the common job: 8 back-to-back MMAs, A from TMEM
             umma_bf16_ts(d, a_t, bd0, idesc, first);
             umma_bf16_ts(d, a_t + 8, bd0 + 2, idesc, 1u);
             umma_bf16_ts(d, a_t + 16, bd0 + 4, idesc, 1u);
@@ -518,7 +550,14 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
           uint32_t w[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) w[i] = relu ? pack_bf16_relu(f[2 * i], f[2 * i + 1]) : pack_bf16(f[2 * i], f[2 * i + 1]);
-          if (!st.no_act) tmem_st16(lane_addr + out_col + 16 * g, w);
+          if (!st.no_act) {
+            tmem_st16(lane_addr + out_col + 16 * g, w);
+            if (kSplit && st.out_half == 1 && g == 0) {   // first instalment of input half 1 (see the issuer's TJ_WAIT_A1)
+              tmem_st_wait();
+              tc_fence_before_sync();
+              mbar_arrive(base + L::a_ready + 8 * (st.out_buf * 2 + 1));
+            }
+          }
           if (gout != nullptr) {
 #pragma unroll
             for (int c = 0; c < 4; ++c)
@@ -534,7 +573,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
         if (!st.no_act) {
           tmem_st_wait();
           tc_fence_before_sync();
-          mbar_arrive(base + L::a_ready + 8 * (st.out_buf * 2 + st.out_half));
+          mbar_arrive((kSplit && st.out_half == 1) ? base + L::a_ready_b + 8 * st.out_buf
+                                                   : base + L::a_ready + 8 * (st.out_buf * 2 + st.out_half));
         }
         if (tr) tr[si * 4 + 2] = clock64();
       }
@@ -797,6 +837,7 @@ int ts_forward(const void* packed, const float* ro, const float* rd, const float
   for (int i = 0; i < 4; ++i) a.ready_per_tile[i] = p.ready_per_tile[i];
   a.order_per_tile = p.order_per_tile;
   a.empty1_per_tile = p.empty1_per_tile;
+  { static const bool ns = [] { const char* e = getenv("GBNERF_TS_SPLIT"); return e && e[0] == '0'; }(); a.no_split = ns; }
   mlp_get_trace(&a.trace, &a.trace_tile);
   const int64_t ntiles = (a.P + kTileRows - 1) / kTileRows;
   const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
@@ -821,6 +862,7 @@ int ts_backward_data(const void* packed_bwd, const float* g_raw, int64_t P, cons
   for (int i = 0; i < 4; ++i) a.ready_per_tile[i] = p.ready_per_tile[i];
   a.order_per_tile = p.order_per_tile;
   a.empty1_per_tile = p.empty1_per_tile;
+  { static const bool ns = [] { const char* e = getenv("GBNERF_TS_SPLIT"); return e && e[0] == '0'; }(); a.no_split = ns; }
   const int64_t ntiles = (P + kTileRows - 1) / kTileRows;
   const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
   nerf_mlp_ts_kernel<true><<<grid, kTsThreads, TsSmemT<true>::alloc, stream>>>(a);
