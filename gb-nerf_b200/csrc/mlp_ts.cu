@@ -3,12 +3,15 @@
 // run.py:2317 / run_nerf_helpers.py:23-53); see mlp_ts_layout.h for why this layout exists and for the job tables.
 //
 //   warp 0      weight producer: 32 KB slabs ([128 out x 128 in] bf16, K-major 128B-swizzle) L2 -> smem ring, bulk TMA
-//   warp 1      MMA issuer: per job 8 x tcgen05.mma (M=128, N=128, K=16), A from TMEM (or the shared-memory
-//               encoding block), B = weight slab, D = accumulator half in TMEM
-//   warp 2      TMEM allocator
-//   warps 4-7   per-tile input block (forward: points + positional encoding, backward: padded g_raw) -> smem
+//   warps 1, 3  MMA issuers (warp 1: jobs into accumulator half 0, warp 3: half 1): per job 8 x tcgen05.mma (M=128,
+//               N=128, K=16), A from TMEM (or the shared-memory encoding / direction block), B = weight slab
+//   warp 2      TMEM allocator; dgrad: gate producer (bulk-loads the H-stash blocks that gate the next step)
+//   warps 4-7   per-tile input block (forward: points + positional + direction encoding, backward: padded g_raw) -> smem
 //   warps 8-15  epilogue: accumulator half -> registers (tcgen05.ld) -> +bias/ReLU (or ReLU gate) -> bf16 ->
 //               tcgen05.st into the other A buffer (the next layer's operand) [+ training stash to HBM]
+// Hand-overs (mbarriers): acc_full[h] (commit of a half's last MMA -> epilogue), a_ready[buf][h] (epilogue -> issuers:
+// input half h of the next layer is in TMEM), acc1_empty (half 1 has been read out, ~600 cycles before a_ready), and in
+// the dgrad program a_ready_b[buf] (second 32-channel instalment of input half 1).
 #include <cmath>
 #include <stdlib.h>
 
