@@ -20,10 +20,11 @@ e10, _ = G.get_embedder(10, 0)
 e4, _ = G.get_embedder(4, 0)
 kw = dict(network_query_fn=G.NetworkQuery(e10, e4, 65536), perturb=1.0, N_importance=64, network_fine=nets[1], N_samples=64,
           network_fn=nets[0], use_viewdirs=True, white_bkgd=True, raw_noise_std=1.0, ndc=False, lindisp=True, near=1.2, far=8.0)
-rays2 = bench.synthetic_frame_rays(0)
-idx = torch.randint(0, rays2.shape[1], (R,), generator=torch.Generator().manual_seed(1))
+RANK = int(os.environ.get('EMUL_RANK', 0))   # reproduce the data bench.py gives to that rank
+rays2 = bench.synthetic_frame_rays(RANK)
+idx = torch.randint(0, rays2.shape[1], (R,), generator=torch.Generator().manual_seed(1 + RANK))
 rays = rays2[:, idx].contiguous().to(dev)
-g = torch.Generator().manual_seed(2)
+g = torch.Generator().manual_seed(2 + RANK)
 tgt, tgd = torch.rand(R, 3, generator=g).to(dev), torch.rand(R, generator=g).to(dev)
 params = [p for n in nets for p in n.parameters()]
 opt = (torch.optim.Adam if os.environ.get('STOCK_ADAM') else G.FusedAdam)(params, lr=3e-3)
