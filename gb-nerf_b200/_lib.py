@@ -37,6 +37,7 @@ SIGNATURES = {
     "gbn_mlp_wgrad_workspace_bytes": (_sz, [_i64]),
     "gbn_mlp_backward_weights": (_i, [_p, _p, _p, _p, _i64, _i64, _i, C.POINTER(_p), _p, _p]),
     "gbn_mlp_set_trace": (_i, [_p, _i]),
+    "gbn_watchdog_report": (_i, [_p, _i]),
     "gbn_debug_ts_mma": (_i, [_p, _p, _p, _i, _i, _p]),
     "gbn_debug_ts_mma_f16": (_i, [_p, _p, _p, _i, _i, _p]),
     "gbn_mlp_forward_embedded": (_i, [_p, _i, _p, _i64, _p, _p, _p, _p]),
@@ -57,6 +58,18 @@ def kernel_launches():
     """Kernels the library has launched in this process so far (counted at every launch site in csrc/; bench.py
     reports the difference over its timed region as ``gpu_launches``)."""
     return int(load().gbn_kernel_launches())
+
+
+def watchdog_report():
+    """First barrier-watchdog expiry of the MLP kernels in this process (host memory: readable after the CUDA context
+    died), or None.  See gbn_watchdog_report in include/gbnerf.h."""
+    buf = (C.c_uint32 * 256)()
+    n = load().gbn_watchdog_report(buf, 256)
+    if n < 4 or buf[3] == 0:
+        return None
+    return {"code": hex(buf[0]), "cta": buf[1], "thread": buf[2],
+            "barriers_from_end": [hex(buf[8 + 2 * i] | (buf[9 + 2 * i] << 32)) for i in range(32)],
+            "warp_waits": {w: (hex(buf[128 + w]), buf[160 + w]) for w in range(16) if buf[128 + w]}}
 
 
 _lib = None

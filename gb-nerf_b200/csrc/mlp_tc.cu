@@ -599,6 +599,12 @@ extern "C" int gbn_mlp_set_trace(void* buf, int tile) {
   return GBN_OK;
 }
 
+namespace gbn { int ts_watchdog_report(unsigned int* out, int words); }  // mlp_ts.cu
+extern "C" int gbn_watchdog_report(unsigned int* out, int words) {
+  if (out == nullptr || words <= 0) return 0;
+  return gbn::ts_watchdog_report(out, words);
+}
+
 extern "C" size_t gbn_mlp_workspace_bytes(int64_t R) { return 256 + (size_t)(R < 0 ? 0 : R) * 128 * sizeof(float); }
 
 extern "C" size_t gbn_mlp_stash_bytes(int64_t P) {

@@ -12,8 +12,11 @@
 // Hand-overs (mbarriers): acc_full[h] (commit of a half's last MMA -> epilogue), a_ready[buf][h] (epilogue -> issuers:
 // input half h of the next layer is in TMEM), acc1_empty (half 1 has been read out, ~600 cycles before a_ready), and in
 // the dgrad program a_ready_b[buf] (second 32-channel instalment of input half 1).
+// The two issuers share the weight ring; ts_wait_progress() keeps either from testing a stage's full barrier before
+// the other's previous fill of that stage has landed (mbarrier waits see phase parity only).
 #include <cmath>
 #include <stdlib.h>
+#include <string.h>
 
 #include <mutex>
 
@@ -70,7 +73,8 @@ struct TsSmemT {
   static constexpr uint32_t a_ready_b = acc1_empty + 8;             // [buf]: second 32-channel groups of input half 1
   static constexpr uint32_t tmem_ptr = a_ready_b + 16;
   static constexpr uint32_t abort_flag = tmem_ptr + 4;
-  static constexpr uint32_t total = abort_flag + 4;
+  static constexpr uint32_t prog = abort_flag + 4;                  // [2]: ring slots whose fill issuer 0 / 1 has seen land
+  static constexpr uint32_t total = prog + 8;
   static constexpr uint32_t alloc = total + 1024;
 };
 static_assert(TsSmemT<false>::alloc <= 232448 && TsSmemT<true>::alloc <= 232448, "shared memory budget");
@@ -90,8 +94,40 @@ struct TsArgs {
   int ready_per_tile[4];
   int order_per_tile;
   int empty1_per_tile;
-  int no_split;            // debug (GBNERF_TS_SPLIT=0): K-high jobs wait for both instalments of input half 1 up front
+  unsigned long long prev_other;   // bit j: the job kTsStages slots before job j (same ring stage) belongs to the OTHER issuer
+  int no_gstash;           // debug (GBNERF_TS_DBG_NO_GSTASH=1): the dgrad program skips its G-stash stores (wrong results)
+  int late_empty;          // debug (GBNERF_TS_DBG_LATE_EMPTY=1): acc1_empty is signalled at the end of the step
+  int no_split;            // GBNERF_TS_SPLIT=0: K-high jobs wait for both instalments of input half 1 up front
 };
+
+// Post-mortem of a watchdog expiry, in host-mapped memory so that it survives a dead context
+// (gbn_watchdog_report): [0] code of the first wait that expired, [1] CTA, [2] thread, [3] 1,
+// [8 + 2i, 9 + 2i] raw mbarrier word i counted backwards from the last barrier of the layout,
+// [128 + warp] the wait each warp of that CTA was parked in when the abort flag went up.
+__device__ unsigned int* g_ts_wd_host = nullptr;
+static unsigned int* g_ts_wd_host_ptr = nullptr;
+constexpr int kWdWords = 256, kWdBarriers = 32;
+
+__device__ __noinline__ void ts_wd_dump(uint32_t abort_addr, int code) {
+  unsigned int* h = g_ts_wd_host;
+  if (h == nullptr) return;
+  volatile unsigned int* v = h;
+  v[0] = (unsigned)code; v[1] = blockIdx.x; v[2] = threadIdx.x; v[3] = 1u;
+  for (int i = 0; i < kWdBarriers; ++i) {
+    unsigned long long w;
+    asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(w) : "r"(abort_addr - 4u - 8u * (uint32_t)(i + 1)));
+    v[8 + 2 * i] = (unsigned)w; v[9 + 2 * i] = (unsigned)(w >> 32);
+  }
+  __threadfence_system();
+}
+__device__ __noinline__ void ts_wd_note(int code) {
+  unsigned int* h = g_ts_wd_host;
+  if (h == nullptr || (threadIdx.x & 31) != 0) return;
+  volatile unsigned int* v = h;
+  v[128 + (threadIdx.x >> 5)] = (unsigned)code;
+  v[160 + (threadIdx.x >> 5)] = blockIdx.x;
+  __threadfence_system();
+}
 
 __device__ __forceinline__ void ts_wait(uint32_t bar, uint32_t parity, uint32_t abort_addr, int* err, int code) {
   if (mbar_try_wait(bar, parity)) return;
@@ -99,13 +135,42 @@ __device__ __forceinline__ void ts_wait(uint32_t bar, uint32_t parity, uint32_t 
   while (!mbar_try_wait(bar, parity)) {
     uint32_t ab;
     asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(ab) : "r"(abort_addr));
-    if (ab) return;
+    if (ab) { ts_wd_note(code); return; }
     if (clock64() - t0 > kWatchdogCycles) {
-      atomicCAS(err, 0, code);
+      if (atomicCAS(err, 0, code) == 0) ts_wd_dump(abort_addr, code);
       asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(abort_addr), "r"(1u));
+      ts_wd_note(code);
       return;
     }
   }
+}
+
+// The two issuing warps share one weight ring, and an mbarrier only exposes the parity of its phase: a warp that waits
+// for fill #m of a stage without having seen fill #m-1 (the other warp's job) would pass on the wrong phase if that
+// earlier fill is still in flight (a cold weight image: L2 misses of > 1 us).  Each issuer therefore publishes how many
+// ring slots it has seen land, and a warp about to wait on a stage last used by the other one first waits for that
+// count to cover the previous fill.  (Seen as an intermittent launch failure of the dgrad program, whose 3-stage ring
+// puts half 1's K-high job on the stage of half 0's K-low job of the same layer)
+__device__ __forceinline__ void ts_wait_progress(uint32_t addr, uint32_t need, uint32_t abort_addr, int* err, int code) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  if (v < need) {
+    const long long t0 = clock64();
+    for (;;) {
+      asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+      if (v >= need) break;
+      uint32_t ab;
+      asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(ab) : "r"(abort_addr));
+      if (ab) { ts_wd_note(code); return; }
+      if (clock64() - t0 > kWatchdogCycles) {
+        if (atomicCAS(err, 0, code) == 0) ts_wd_dump(abort_addr, code);
+        asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(abort_addr), "r"(1u));
+        ts_wd_note(code);
+        return;
+      }
+    }
+  }
+  __threadfence_block();
 }
 
 __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -148,7 +213,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
   using L = TsSmemT<BWD>;
   constexpr int kTsStages = L::NST;
   constexpr int PROG = BWD ? 1 : 0;
-  constexpr bool kSplit = false;          // two-instalment hand-over of input half 1 (dgrad experiment, see ts_plan())
+  constexpr bool kSplit = BWD;            // two-instalment hand-over of input half 1 (dgrad program only)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* const gen = smem_raw + (base - smem_u32(smem_raw));
@@ -172,6 +237,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
     mbar_init(base + L::acc1_empty, 256);
     mbar_init(base + L::a_ready_b, 256); mbar_init(base + L::a_ready_b + 8, 256);
     *reinterpret_cast<volatile uint32_t*>(gen + L::abort_flag) = 0;
+    *reinterpret_cast<volatile uint32_t*>(gen + L::prog) = 0;
+    *reinterpret_cast<volatile uint32_t*>(gen + L::prog + 4) = 0;
     mbar_init_fence();
   }
   if (warp == 2) tmem_alloc(base + L::tmem_ptr, kTmemCols);
@@ -257,7 +324,13 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
         }
         const uint32_t s = cnt % kTsStages, par = (cnt / kTsStages) & 1;
         if (tr) tr[4 * j + 1] = clock64();
+        if (cnt >= (uint32_t)kTsStages && ((a.prev_other >> j) & 1ull))
+          ts_wait_progress(base + L::prog + (second ? 0u : 4u), cnt - kTsStages + 1, abort_addr, a.err, 0x26000000 | j);
         ts_wait(base + L::w_full + 8 * s, par, abort_addr, a.err, 0x22000000 | j);
+        if (lane == 0) {
+          __threadfence_block();
+          asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(base + L::prog + (second ? 4u : 0u)), "r"(cnt + 1) : "memory");
+        }
         if (tr) tr[4 * j + 2] = clock64();
         tc_fence_after_sync();
         const uint32_t N = (uint32_t)jb.n16 * 16;
@@ -495,7 +568,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
         const uint32_t out_col = (st.out_buf ? kTsA1 : kTsA0) + 64u * st.out_half + 32u * wg;
         uint8_t* gout = nullptr;   // this warpgroup's 16 KB block image of the result in the stash
         if (st.out_blk != 0xff) {
-          if constexpr (BWD) gout = a.stash_g + (size_t)tile * kStashTileBytes + (size_t)(st.out_blk + wg) * kBlkBytes;
+          if constexpr (BWD) gout = a.no_gstash ? nullptr : a.stash_g + (size_t)tile * kStashTileBytes + (size_t)(st.out_blk + wg) * kBlkBytes;
           else if (a.stash_h != nullptr) gout = a.stash_h + (size_t)tile * kStashTileBytes + (size_t)(st.out_blk + wg) * kBlkBytes;
         }
         if (gout != nullptr) {       // the previous bulk store must have finished reading the staging block
@@ -519,7 +592,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
         tmem_ld32(lane_addr + acc_col, v[0]);
         tmem_ld32(lane_addr + acc_col + 32, v[1]);
         tmem_ld_wait();
-        if (st.acc == 1) {            // acc1 is in registers: the next layer's half-1 MMAs may overwrite it
+        if (st.acc == 1 && !a.late_empty) {   // acc1 is in registers: the next layer's half-1 MMAs may overwrite it
           tc_fence_before_sync();
           mbar_arrive(base + L::acc1_empty);
         }
@@ -578,6 +651,10 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
           tc_fence_before_sync();
           mbar_arrive((kSplit && st.out_half == 1) ? base + L::a_ready_b + 8 * st.out_buf
                                                    : base + L::a_ready + 8 * (st.out_buf * 2 + st.out_half));
+        }
+        if (st.acc == 1 && a.late_empty) {
+          tc_fence_before_sync();
+          mbar_arrive(base + L::acc1_empty);
         }
         if (tr) tr[si * 4 + 2] = clock64();
       }
@@ -657,11 +734,21 @@ const TsPlan& ts_plan(int bwd) {
     const char* ko = getenv("GBNERF_TS_KHI_ORDER");
     const bool khi = ko && ko[0] == '1';   // measured slower (1030 vs 1052-1064 TFLOP/s): off unless asked for
     g_ts_plan[0] = make_ts_plan(kTsFwd, stagger, early, khi);
-    // dgrad: the early acc1 release and the two-instalment hand-over (GBNERF_TS_BWD_EARLY=1 / kSplit) made the step
-    // 3 % faster but produced an intermittent launch failure in long multi-rank runs (about one run of 13 steps in
-    // three on some inputs); not understood yet, so the dgrad program keeps the plain hand-overs.
+    // dgrad: early acc1 release as in the forward program (GBNERF_TS_BWD_EARLY=0 switches it off).  An intermittent
+    // launch failure first seen with it was the ring-stage parity alias described at ts_wait_progress(), not this.
     const char* be = getenv("GBNERF_TS_BWD_EARLY");
-    g_ts_plan[1] = make_ts_plan(kTsBwd, stagger, be && be[0] == '1', khi);
+    g_ts_plan[1] = make_ts_plan(kTsBwd, stagger, !(be && be[0] == '0'), khi);
+    // debug: early plan, but the K-low jobs of half 1 whose bit is clear in GBNERF_TS_DBG_EARLY_MASK (hex; bit i = the
+    // i-th such job of the tile; GBNERF_TS_BWD_EARLY=2 clears all) also wait for input half 1, i.e. do not overlap
+    const char* em = getenv("GBNERF_TS_DBG_EARLY_MASK");
+    unsigned long mask = em ? strtoul(em, nullptr, 16) : ~0ul;
+    if (be && be[0] == '2') mask = 0;
+    int ei = 0;
+    for (auto& j : g_ts_plan[1].jobs)
+      if (j.flags & TJ_WAIT_EMPTY1) {
+        if (!((mask >> ei) & 1)) j.flags |= TJ_WAIT_A1;
+        ++ei;
+      }
   });
   return g_ts_plan[bwd ? 1 : 0];
 }
@@ -675,12 +762,27 @@ static int ts_ensure_device(cudaStream_t stream) {
   for (int pr = 0; pr < 2; ++pr) {
     const TsPlan& p = ts_plan(pr);
     GBN_REQUIRE((int)p.jobs.size() <= kTsMaxJobs && (int)p.steps.size() <= kTsMaxSteps, "TS table overflow");
+    GBN_REQUIRE(p.jobs.size() <= 64, "TS job table exceeds the 64-bit ring-ownership mask");
     GBN_CUDA(cudaMemcpyToSymbolAsync(c_tsjobs, p.jobs.data(), p.jobs.size() * sizeof(TsJob), pr * kTsMaxJobs * sizeof(TsJob),
                                      cudaMemcpyHostToDevice, stream));
     GBN_CUDA(cudaMemcpyToSymbolAsync(c_tssteps, p.steps.data(), p.steps.size() * sizeof(TsStep),
                                      pr * kTsMaxSteps * sizeof(TsStep), cudaMemcpyHostToDevice, stream));
     GBN_CUDA(cudaMemcpyToSymbolAsync(c_tspack, p.pack.data(), p.pack.size() * sizeof(TsPackJob),
                                      pr * kTsMaxJobs * sizeof(TsPackJob), cudaMemcpyHostToDevice, stream));
+  }
+  if (g_ts_wd_host_ptr == nullptr) {   // watchdog post-mortem record (zero-copy host memory, one per process)
+    void* hp = nullptr;
+    if (cudaHostAlloc(&hp, kWdWords * sizeof(unsigned int), cudaHostAllocMapped) == cudaSuccess) {
+      memset(hp, 0, kWdWords * sizeof(unsigned int));
+      g_ts_wd_host_ptr = static_cast<unsigned int*>(hp);
+    } else {
+      (void)cudaGetLastError();
+    }
+  }
+  if (g_ts_wd_host_ptr != nullptr) {
+    unsigned int* dp = nullptr;
+    GBN_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dp), g_ts_wd_host_ptr, 0));
+    GBN_CUDA(cudaMemcpyToSymbolAsync(g_ts_wd_host, &dp, sizeof(dp), 0, cudaMemcpyHostToDevice, stream));
   }
   GBN_CUDA(cudaFuncSetAttribute(nerf_mlp_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TsSmemT<false>::alloc));
   GBN_CUDA(cudaFuncSetAttribute(nerf_mlp_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TsSmemT<true>::alloc));
@@ -828,6 +930,16 @@ void mlp_get_trace(unsigned long long** buf, int* tile);   // mlp_tc.cu
 int launch_view_bias_raw(const float* wdir, const float* bdir, const float* viewdirs, int64_t stride, const float* emb,
                          int64_t n, float* out, cudaStream_t stream);  // mlp_aux.cu
 
+static unsigned long long ts_prev_other_mask(const TsPlan& p, int nst) {
+  const int n = (int)p.jobs.size();
+  unsigned long long m = 0;
+  for (int j = 0; j < n; ++j) {
+    const int jp = ((j - nst) % n + n) % n;
+    if ((p.jobs[j].d_col >= kTsAcc1) != (p.jobs[jp].d_col >= kTsAcc1)) m |= 1ull << j;
+  }
+  return m;
+}
+
 int ts_forward(const void* packed, const float* ro, const float* rd, const float* vd, int64_t stride, const float* z,
                const float* pts, const float* emb, int64_t R, int S, float* raw, void* workspace, void* stash,
                cudaStream_t stream) {
@@ -844,6 +956,7 @@ int ts_forward(const void* packed, const float* ro, const float* rd, const float
   for (int i = 0; i < 4; ++i) a.ready_per_tile[i] = p.ready_per_tile[i];
   a.order_per_tile = p.order_per_tile;
   a.empty1_per_tile = p.empty1_per_tile;
+  a.prev_other = ts_prev_other_mask(p, TsSmemT<false>::NST);
   { static const bool ns = [] { const char* e = getenv("GBNERF_TS_SPLIT"); return e && e[0] == '0'; }(); a.no_split = ns; }
   mlp_get_trace(&a.trace, &a.trace_tile);
   const int64_t ntiles = (a.P + kTileRows - 1) / kTileRows;
@@ -869,11 +982,21 @@ int ts_backward_data(const void* packed_bwd, const float* g_raw, int64_t P, cons
   for (int i = 0; i < 4; ++i) a.ready_per_tile[i] = p.ready_per_tile[i];
   a.order_per_tile = p.order_per_tile;
   a.empty1_per_tile = p.empty1_per_tile;
+  a.prev_other = ts_prev_other_mask(p, TsSmemT<true>::NST);
   { static const bool ns = [] { const char* e = getenv("GBNERF_TS_SPLIT"); return e && e[0] == '0'; }(); a.no_split = ns; }
+  { static const bool le = [] { const char* e = getenv("GBNERF_TS_DBG_LATE_EMPTY"); return e && e[0] == '1'; }(); a.late_empty = le; }
+  { static const bool ng = [] { const char* e = getenv("GBNERF_TS_DBG_NO_GSTASH"); return e && e[0] == '1'; }(); a.no_gstash = ng; }
   const int64_t ntiles = (P + kTileRows - 1) / kTileRows;
   const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
   nerf_mlp_ts_kernel<true><<<grid, kTsThreads, TsSmemT<true>::alloc, stream>>>(a);
   return check_launch("nerf_mlp_ts_kernel<bwd>");
+}
+
+int ts_watchdog_report(unsigned int* out, int words) {
+  if (g_ts_wd_host_ptr == nullptr) return 0;
+  const int n = words < kWdWords ? words : kWdWords;
+  for (int i = 0; i < n; ++i) out[i] = reinterpret_cast<volatile unsigned int*>(g_ts_wd_host_ptr)[i];
+  return n;
 }
 
 }  // namespace gbn

@@ -135,6 +135,15 @@ size_t gbn_mlp_stash_bytes(int64_t P);
  * (layout: tools/mlp_trace.py).  NULL switches tracing off.  Not part of the reference-facing surface. */
 int gbn_mlp_set_trace(void* buf, int tile);
 
+/* Post-mortem of the MLP kernels' barrier watchdog.  Every mbarrier wait in nerf_mlp_ts_kernel is bounded (~4 s);
+ * the first wait that expires writes a record into zero-copy HOST memory, so it can be read after the CUDA context
+ * has died: out[0] = wait code (role << 24 | job/step), out[1] = CTA, out[2] = thread, out[3] = 1 if a record exists,
+ * out[8 + 2i .. 9 + 2i] = raw 64-bit state of the i-th barrier counted back from the end of the kernel's barrier block,
+ * out[128 + w] = wait code warp w of that CTA was parked in, out[160 + w] = its CTA.  Copies up to `words` (<= 256)
+ * 32-bit words and returns the number copied (0 before the first MLP launch).  Makes no CUDA call.
+ * Not part of the reference-facing surface. */
+int gbn_watchdog_report(unsigned int* out, int words);
+
 /* Which bf16 kernel family this process uses (env GBNERF_MLP): 0 = operands in shared memory ("ss"), 1 = activations
  * in tensor memory ("ts", default), 2 = quarter-pipelined experiment ("tq").  The packed weight images differ. */
 int gbn_mlp_variant(void);

@@ -40,18 +40,36 @@ def step(with_opt=True):
     return loss
 
 
-for _ in range(3):
-    l = step()
-torch.cuda.synchronize()
+def _report_and_die(exc):
+    from gbnerf_b200 import _lib
+    import traceback
+    print("FAILED:", str(exc).splitlines()[0], flush=True)
+    print("   at:", " <- ".join(f"{f.name}:{f.lineno}" for f in reversed(traceback.extract_tb(exc.__traceback__)[-6:])), flush=True)
+    print("watchdog report:", _lib.watchdog_report(), flush=True)
+    os._exit(3)
+
+
+try:
+    for _ in range(3):
+        l = step()
+    torch.cuda.synchronize()
+except Exception as exc:  # a dead context: the barrier watchdog's host-side record says which wait expired
+    _report_and_die(exc)
 print("loss", l.item(), "watchdogs", ops.mlp_error_code(nets[1].last_workspace), ops.mlp_error_code(nets[1].last_workspace_bwd))
 for with_opt in (False, True):
     ops.KERNEL_EVENTS = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(iters):
-        step(with_opt)
-    e1.record()
-    torch.cuda.synchronize()
+    try:
+        for it in range(iters):
+            l = step(with_opt)
+            if os.environ.get("STEP_SYNC"):
+                torch.cuda.synchronize()
+                print(f"  [{'on' if with_opt else 'off'} {it}] loss {l.item():.5f}", flush=True)
+        e1.record()
+        torch.cuda.synchronize()
+    except Exception as exc:
+        _report_and_die(exc)
     ms = e0.elapsed_time(e1) / iters
     ev, ops.KERNEL_EVENTS = ops.KERNEL_EVENTS, None
     print(f"train step R={R} (optimizer {'on' if with_opt else 'off'}): {ms:.3f} ms/step -> {R / ms * 1e3:.0f} rays/s")
