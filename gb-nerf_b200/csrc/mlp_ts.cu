@@ -94,9 +94,6 @@ struct TsArgs {
   int ready_per_tile[4];
   int order_per_tile;
   int empty1_per_tile;
-  unsigned long long prev_other;   // bit j: the job kTsStages slots before job j (same ring stage) belongs to the OTHER issuer
-  int no_gstash;           // debug (GBNERF_TS_DBG_NO_GSTASH=1): the dgrad program skips its G-stash stores (wrong results)
-  int late_empty;          // debug (GBNERF_TS_DBG_LATE_EMPTY=1): acc1_empty is signalled at the end of the step
   int no_split;            // GBNERF_TS_SPLIT=0: K-high jobs wait for both instalments of input half 1 up front
 };
 
@@ -170,7 +167,6 @@ __device__ __forceinline__ void ts_wait_progress(uint32_t addr, uint32_t need, u
       }
     }
   }
-  __threadfence_block();
 }
 
 __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -324,13 +320,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
         }
         const uint32_t s = cnt % kTsStages, par = (cnt / kTsStages) & 1;
         if (tr) tr[4 * j + 1] = clock64();
-        if (cnt >= (uint32_t)kTsStages && ((a.prev_other >> j) & 1ull))
+        if ((jb.flags & TJ_PREV_OTHER) && cnt >= (uint32_t)kTsStages)
           ts_wait_progress(base + L::prog + (second ? 0u : 4u), cnt - kTsStages + 1, abort_addr, a.err, 0x26000000 | j);
         ts_wait(base + L::w_full + 8 * s, par, abort_addr, a.err, 0x22000000 | j);
-        if (lane == 0) {
-          __threadfence_block();
-          asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(base + L::prog + (second ? 4u : 0u)), "r"(cnt + 1) : "memory");
-        }
         if (tr) tr[4 * j + 2] = clock64();
         tc_fence_after_sync();
         const uint32_t N = (uint32_t)jb.n16 * 16;
@@ -389,6 +381,11 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
           if (jb.flags & TJ_SIGNAL_ORDER) mbar_arrive(base + L::order);
         }
         __syncwarp();
+        // this stage's next job is the other issuer's: tell it that the fill just consumed has landed (after the MMAs
+        // have been issued, off the critical path; shared memory is coherent within the CTA and both sides use volatile
+        // accesses in program order after / before their mbarrier tests)
+        if ((jb.ksteps & kTjNextOther) && lane == 0)
+          asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(base + L::prog + (second ? 4u : 0u)), "r"(cnt + 1) : "memory");
         if (tr) tr[4 * j + 3] = clock64();
         ++cnt;
       }
@@ -568,7 +565,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
         const uint32_t out_col = (st.out_buf ? kTsA1 : kTsA0) + 64u * st.out_half + 32u * wg;
         uint8_t* gout = nullptr;   // this warpgroup's 16 KB block image of the result in the stash
         if (st.out_blk != 0xff) {
-          if constexpr (BWD) gout = a.no_gstash ? nullptr : a.stash_g + (size_t)tile * kStashTileBytes + (size_t)(st.out_blk + wg) * kBlkBytes;
+          if constexpr (BWD) gout = a.stash_g + (size_t)tile * kStashTileBytes + (size_t)(st.out_blk + wg) * kBlkBytes;
           else if (a.stash_h != nullptr) gout = a.stash_h + (size_t)tile * kStashTileBytes + (size_t)(st.out_blk + wg) * kBlkBytes;
         }
         if (gout != nullptr) {       // the previous bulk store must have finished reading the staging block
@@ -592,7 +589,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
         tmem_ld32(lane_addr + acc_col, v[0]);
         tmem_ld32(lane_addr + acc_col + 32, v[1]);
         tmem_ld_wait();
-        if (st.acc == 1 && !a.late_empty) {   // acc1 is in registers: the next layer's half-1 MMAs may overwrite it
+        if (st.acc == 1) {   // acc1 is in registers: the next layer's half-1 MMAs may overwrite it
           tc_fence_before_sync();
           mbar_arrive(base + L::acc1_empty);
         }
@@ -651,10 +648,6 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
           tc_fence_before_sync();
           mbar_arrive((kSplit && st.out_half == 1) ? base + L::a_ready_b + 8 * st.out_buf
                                                    : base + L::a_ready + 8 * (st.out_buf * 2 + st.out_half));
-        }
-        if (st.acc == 1 && a.late_empty) {
-          tc_fence_before_sync();
-          mbar_arrive(base + L::acc1_empty);
         }
         if (tr) tr[si * 4 + 2] = clock64();
       }
@@ -749,6 +742,18 @@ const TsPlan& ts_plan(int bwd) {
         if (!((mask >> ei) & 1)) j.flags |= TJ_WAIT_A1;
         ++ei;
       }
+    // ring-stage ownership (see ts_wait_progress): mark the jobs whose stage was last / is next used by the other
+    // issuer; the job sequence repeats every tile, so the neighbour `stages` slots away wraps around the table
+    const char* ng = getenv("GBNERF_TS_DBG_NO_RING_GUARD");   // timing A/B only: without the guard the kernel can fail
+    for (int pr = 0; pr < 2 && !(ng && ng[0] == '1'); ++pr) {
+      std::vector<TsJob>& jobs = g_ts_plan[pr].jobs;
+      const int n = (int)jobs.size(), nst = pr ? TsSmemT<true>::NST : TsSmemT<false>::NST;
+      for (int j = 0; j < n; ++j) {
+        const bool mine = jobs[j].d_col >= kTsAcc1;
+        if ((jobs[((j - nst) % n + n) % n].d_col >= kTsAcc1) != mine) jobs[j].flags |= TJ_PREV_OTHER;
+        if ((jobs[(j + nst) % n].d_col >= kTsAcc1) != mine) jobs[j].ksteps |= kTjNextOther;
+      }
+    }
   });
   return g_ts_plan[bwd ? 1 : 0];
 }
@@ -762,7 +767,6 @@ static int ts_ensure_device(cudaStream_t stream) {
   for (int pr = 0; pr < 2; ++pr) {
     const TsPlan& p = ts_plan(pr);
     GBN_REQUIRE((int)p.jobs.size() <= kTsMaxJobs && (int)p.steps.size() <= kTsMaxSteps, "TS table overflow");
-    GBN_REQUIRE(p.jobs.size() <= 64, "TS job table exceeds the 64-bit ring-ownership mask");
     GBN_CUDA(cudaMemcpyToSymbolAsync(c_tsjobs, p.jobs.data(), p.jobs.size() * sizeof(TsJob), pr * kTsMaxJobs * sizeof(TsJob),
                                      cudaMemcpyHostToDevice, stream));
     GBN_CUDA(cudaMemcpyToSymbolAsync(c_tssteps, p.steps.data(), p.steps.size() * sizeof(TsStep),
@@ -930,16 +934,6 @@ void mlp_get_trace(unsigned long long** buf, int* tile);   // mlp_tc.cu
 int launch_view_bias_raw(const float* wdir, const float* bdir, const float* viewdirs, int64_t stride, const float* emb,
                          int64_t n, float* out, cudaStream_t stream);  // mlp_aux.cu
 
-static unsigned long long ts_prev_other_mask(const TsPlan& p, int nst) {
-  const int n = (int)p.jobs.size();
-  unsigned long long m = 0;
-  for (int j = 0; j < n; ++j) {
-    const int jp = ((j - nst) % n + n) % n;
-    if ((p.jobs[j].d_col >= kTsAcc1) != (p.jobs[jp].d_col >= kTsAcc1)) m |= 1ull << j;
-  }
-  return m;
-}
-
 int ts_forward(const void* packed, const float* ro, const float* rd, const float* vd, int64_t stride, const float* z,
                const float* pts, const float* emb, int64_t R, int S, float* raw, void* workspace, void* stash,
                cudaStream_t stream) {
@@ -956,7 +950,6 @@ int ts_forward(const void* packed, const float* ro, const float* rd, const float
   for (int i = 0; i < 4; ++i) a.ready_per_tile[i] = p.ready_per_tile[i];
   a.order_per_tile = p.order_per_tile;
   a.empty1_per_tile = p.empty1_per_tile;
-  a.prev_other = ts_prev_other_mask(p, TsSmemT<false>::NST);
   { static const bool ns = [] { const char* e = getenv("GBNERF_TS_SPLIT"); return e && e[0] == '0'; }(); a.no_split = ns; }
   mlp_get_trace(&a.trace, &a.trace_tile);
   const int64_t ntiles = (a.P + kTileRows - 1) / kTileRows;
@@ -982,10 +975,7 @@ int ts_backward_data(const void* packed_bwd, const float* g_raw, int64_t P, cons
   for (int i = 0; i < 4; ++i) a.ready_per_tile[i] = p.ready_per_tile[i];
   a.order_per_tile = p.order_per_tile;
   a.empty1_per_tile = p.empty1_per_tile;
-  a.prev_other = ts_prev_other_mask(p, TsSmemT<true>::NST);
   { static const bool ns = [] { const char* e = getenv("GBNERF_TS_SPLIT"); return e && e[0] == '0'; }(); a.no_split = ns; }
-  { static const bool le = [] { const char* e = getenv("GBNERF_TS_DBG_LATE_EMPTY"); return e && e[0] == '1'; }(); a.late_empty = le; }
-  { static const bool ng = [] { const char* e = getenv("GBNERF_TS_DBG_NO_GSTASH"); return e && e[0] == '1'; }(); a.no_gstash = ng; }
   const int64_t ntiles = (P + kTileRows - 1) / kTileRows;
   const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
   nerf_mlp_ts_kernel<true><<<grid, kTsThreads, TsSmemT<true>::alloc, stream>>>(a);

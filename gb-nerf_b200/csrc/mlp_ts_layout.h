@@ -35,8 +35,12 @@ enum : uint16_t {
   TJ_A_DIR = 2048, TJ_WAIT_DIR = 4096, TJ_COMMIT_DIR = 8192,
   // acc1 has been read out by the epilogue (signalled right after its tcgen05.ld, ~600 cycles before the converted
   // activations are handed over): lets the first MMAs of the next layer's half 1 overlap the rest of that epilogue step
-  TJ_WAIT_EMPTY1 = 16384
+  TJ_WAIT_EMPTY1 = 16384,
+  // the weight-ring stage of this job was last used by a job of the OTHER issuing warp: wait until that warp has seen
+  // its fill land before testing the stage's full barrier (set by ts_plan() for the kernel's stage count)
+  TJ_PREV_OTHER = 32768
 };
+constexpr uint8_t kTjNextOther = 8;   // TsJob::ksteps bit 3: the stage's next job is the other issuer's (publish progress)
 constexpr int kTsBiasViews = kBiasFloats;            // b_views appended to the bias block (128 floats)
 constexpr int kTsBiasFloats = kBiasFloats + 128;
 
@@ -48,7 +52,7 @@ struct TsJob {
   uint16_t a_col;       // TMEM column of the first K-block of A (ignored for TJ_A_SMEM)
   uint8_t n16;          // N >> 4
   uint8_t nkb;          // K-blocks (64 K each) in this job: 1 or 2
-  uint8_t ksteps;       // bits 0-2: 16-wide MMA steps per K-block (4, or 1 for the padded g_raw block);
+  uint8_t ksteps;       // bits 0-2: 16-wide MMA steps per K-block (4, or 1 for the padded g_raw block); bit 3: kTjNextOther;
                         // bits 4-6: index within the tile of the issue-order signal this job raises / waits for
   uint8_t wait_buf;     // bit 0: A buffer whose ready barriers TJ_WAIT_A0/A1 refer to; bits 1-3 / 4-6: which completion
                         // of that barrier within the tile the job waits for (half 0 / half 1), so that each of the

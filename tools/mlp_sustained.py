@@ -5,7 +5,10 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import gbnerf_b200 as G
-from gbnerf_b200 import ops
+from gbnerf_b200 import ops, _lib
+if os.environ.get("AB_LIB"):          # timing A/B against another build of the library (tools only)
+    _lib.LIB_PATH = os.path.abspath(os.environ["AB_LIB"])
+    _lib.SIGNATURES.pop("gbn_watchdog_report", None)   # older builds do not export it
 prec = sys.argv[1] if len(sys.argv) > 1 else "bf16"
 windows = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 R, S = 32768, 128
