@@ -599,7 +599,15 @@ extern "C" int gbn_mlp_set_trace(void* buf, int tile) {
   return GBN_OK;
 }
 
-namespace gbn { int ts_watchdog_report(unsigned int* out, int words); }  // mlp_ts.cu
+namespace gbn {
+int ts_watchdog_report(unsigned int* out, int words);                                             // mlp_ts.cu
+int ts_debug_plan(int bwd, void* jobs, int max_jobs, void* steps, int max_steps, int* meta);     // mlp_ts.cu
+}
+extern "C" int gbn_debug_ts_plan(int bwd, void* jobs, int max_jobs, void* steps, int max_steps, int* meta) {
+  GBN_REQUIRE(jobs && steps && meta, "debug_ts_plan: null pointer");
+  GBN_REQUIRE(gbn::ts_debug_plan(bwd, jobs, max_jobs, steps, max_steps, meta) == 0, "debug_ts_plan: buffers too small");
+  return GBN_OK;
+}
 extern "C" int gbn_watchdog_report(unsigned int* out, int words) {
   if (out == nullptr || words <= 0) return 0;
   return gbn::ts_watchdog_report(out, words);

@@ -982,6 +982,22 @@ int ts_backward_data(const void* packed_bwd, const float* g_raw, int64_t P, cons
   return check_launch("nerf_mlp_ts_kernel<bwd>");
 }
 
+// host only: the job / step tables the kernels run (for the protocol model of tests/test_ts_protocol_cpu.py)
+int ts_debug_plan(int bwd, void* jobs, int max_jobs, void* steps, int max_steps, int* meta) {
+  const TsPlan& p = ts_plan(bwd);
+  const int nj = (int)p.jobs.size(), ns = (int)p.steps.size();
+  if (nj > max_jobs || ns > max_steps) return -1;
+  memcpy(jobs, p.jobs.data(), nj * sizeof(TsJob));
+  memcpy(steps, p.steps.data(), ns * sizeof(TsStep));
+  meta[0] = nj; meta[1] = ns;
+  for (int i = 0; i < 4; ++i) meta[2 + i] = p.ready_per_tile[i];
+  meta[6] = p.order_per_tile; meta[7] = p.empty1_per_tile;
+  meta[8] = bwd ? TsSmemT<true>::NST : TsSmemT<false>::NST;
+  const char* e = getenv("GBNERF_TS_SPLIT");
+  meta[9] = (bwd && !(e && e[0] == '0')) ? 1 : 0;      // two-instalment hand-over of input half 1 in use
+  return 0;
+}
+
 int ts_watchdog_report(unsigned int* out, int words) {
   if (g_ts_wd_host_ptr == nullptr) return 0;
   const int n = words < kWdWords ? words : kWdWords;

@@ -144,6 +144,13 @@ int gbn_mlp_set_trace(void* buf, int tile);
  * Not part of the reference-facing surface. */
 int gbn_watchdog_report(unsigned int* out, int words);
 
+/* Diagnostic, host only (no CUDA call): the job and epilogue-step tables of the bf16 TMEM-operand kernels, as the
+ * kernels read them from constant memory (forward: bwd = 0, dgrad: bwd = 1).  jobs: 16-byte TsJob records, steps:
+ * 12-byte TsStep records (csrc/mlp_ts_layout.h); meta[0..9] = jobs, steps, a_ready completions per tile [4],
+ * issue-order signals per tile, acc1_empty completions per tile, weight-ring stages, split hand-over in use.
+ * tests/test_ts_protocol_cpu.py replays the barrier protocol of these tables under random latencies. */
+int gbn_debug_ts_plan(int bwd, void* jobs, int max_jobs, void* steps, int max_steps, int* meta);
+
 /* Which bf16 kernel family this process uses (env GBNERF_MLP): 0 = operands in shared memory ("ss"), 1 = activations
  * in tensor memory ("ts", default), 2 = quarter-pipelined experiment ("tq").  The packed weight images differ. */
 int gbn_mlp_variant(void);
