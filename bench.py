@@ -265,6 +265,11 @@ def run_ours(args, rank, world, local_rank):
     cpu = cpu_baseline(bounded_s=20.0) if rank == 0 and world == 1 and not args.no_cpu else None
     if cpu is not None:
         cpu["torch_gpu_fp32"] = torch_gpu_port(dev)
+        if train is not None:
+            try:
+                train["cpu_baseline"] = cpu_train_step()
+            except Exception as e:   # a reported comparison point, never a reason to lose the bench line
+                train["cpu_baseline"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -428,6 +433,33 @@ def torch_gpu_port(dev, n_rays=32768):
         return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+def cpu_train_step(n_rays=512):
+    """the reference's training arithmetic (oracle port: render_rays with train kwargs, loss of §8a row 12,
+    autograd backward) on the host cores; returns rays/s over a bounded sample of the 4096-ray batch."""
+    from oracle import nerf_oracle as O
+    rays2 = synthetic_frame_rays(0)
+    idx = torch.randint(0, H * W, (n_rays,), generator=torch.Generator().manual_seed(1))
+    rays = O.pack_rays(rays2[0, idx], rays2[1, idx], NEAR, FAR)
+    g = torch.Generator().manual_seed(2)
+    tgt, tgd = torch.rand(n_rays, 3, generator=g), torch.rand(n_rays, generator=g)
+    rnd = dict(t_rand=torch.rand(n_rays, N_SAMPLES, generator=g), noise0=torch.randn(n_rays, N_SAMPLES, generator=g),
+               u=torch.rand(n_rays, N_IMPORTANCE, generator=g),
+               noise1=torch.randn(n_rays, N_SAMPLES + N_IMPORTANCE, generator=g))
+    torch.manual_seed(0)
+    prm = [{k: v.clone().requires_grad_(True) for k, v in p.items()} for p in (O.init_params(0), O.init_params(None))]
+    best = None
+    for it in range(3):                                  # first pass = warm-up
+        t0 = time.perf_counter()
+        ret = O.render_rays(rays, prm[0], prm[1], N_SAMPLES, N_IMPORTANCE, lindisp=True, white_bkgd=True, **rnd)
+        O.reference_loss(ret, tgt, tgd, 0.1).backward()
+        dt = time.perf_counter() - t0
+        if it > 0:
+            best = dt if best is None else min(best, dt)
+    return {"value": n_rays / best, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n_rays} rays of the 4096-ray batch, forward + loss + autograd backward of oracle/nerf_oracle.py "
+                      f"(torch CPU fp32), no optimizer step, best of 2"}
 
 
 def cpu_baseline(bounded_s=20.0, n_rays=1024):
