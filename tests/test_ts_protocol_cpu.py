@@ -55,3 +55,19 @@ def test_model_reproduces_the_ring_alias_when_the_guard_is_off(plans):
         errs = M.simulate(plans[1], tiles=4, seed=seed, cold=1.0, guard=False)
         hits += any(e.split(": ", 1)[1].startswith(("alias", "rearm")) or "weight stage" in e for e in errs)
     assert hits >= 3, hits
+
+
+@pytest.mark.parametrize("env", [{"GBNERF_TS_EARLY": "0", "GBNERF_TS_BWD_EARLY": "0"}, {"GBNERF_TS_SPLIT": "0"},
+                                 {"GBNERF_TS_BWD_EARLY": "0", "GBNERF_TS_SPLIT": "0"}])
+def test_alternative_plans_are_clean_too(plans, env):
+    """The plans behind the runtime switches (late acc1 release, no split hand-over) are read once per process: replay
+    them in a child process."""
+    import subprocess
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import ts_protocol_model as M\nfrom gbnerf_b200 import _lib\nlib = _lib.load()\nbad = []\n"
+            "for bwd in (0, 1):\n    p = M.Plan(lib, bwd)\n    for seed in range(6):\n"
+            "        bad += M.simulate(p, tiles=3, seed=seed, cold=0.4)\nprint('ERRORS', len(bad), bad[:3])\n"
+            % (os.path.dirname(os.path.abspath(__file__)), os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "ERRORS 0 " in out.stdout, out.stdout[-2000:]
