@@ -39,6 +39,17 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_WD = (C.c_uint32 * 4)()
+
+
+def _raise_if_watchdog_fired():
+    """Fail loudly, and without a device synchronisation, if an earlier MLP launch of this process ran into its barrier
+    watchdog: the kernels write that fact to host memory (gbn_watchdog_report), and results after it are meaningless."""
+    if _lib.load().gbn_watchdog_report(_WD, 4) >= 4 and _WD[3]:
+        raise _lib.GbnError(f"an MLP kernel hit its barrier watchdog (wait code {hex(_WD[0])}, CTA {_WD[1]}, thread "
+                            f"{_WD[2]}); outputs since then are invalid - _lib.watchdog_report() has the full record")
+
+
 def _chk(t, name, dim=None, allow_none=False):
     if t is None:
         if allow_none:
@@ -291,6 +302,7 @@ def mlp_forward_raw(packed, precision, viewdirs, R, S, rays_o=None, rays_d=None,
         z = _dense(z, "z", 2)
     raw = torch.empty(R, S, 4, device=viewdirs.device, dtype=torch.float32)
     ws = _workspace(R, viewdirs.device)
+    _raise_if_watchdog_fired()
     with _timed_launch("mlp", R * S):
         _lib.call("gbn_mlp_forward", _ptr(packed), PRECISION[precision], _ptr(rays_o), _ptr(rays_d), _ptr(viewdirs),
                   pitch, _ptr(z), _ptr(pts), R, S, _ptr(raw), _ptr(ws), _ptr(stash), _stream())
@@ -316,6 +328,7 @@ def mlp_backward_raw(packed_bwd, g_raw, stash_h, viewdirs, R, S, param_shapes):
     dev = g_raw.device
     stash_g = _stash(R * S, dev)
     ws = torch.empty(512, device=dev, dtype=torch.uint8)
+    _raise_if_watchdog_fired()
     with _timed_launch("mlp_dgrad", R * S):
         _lib.call("gbn_mlp_backward_data", _ptr(packed_bwd), _ptr(g_raw), R * S, _ptr(stash_h), _ptr(stash_g), _ptr(ws),
                   _stream())

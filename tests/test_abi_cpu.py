@@ -107,3 +107,11 @@ def test_argument_validation(lib):
     assert l.gbn_adam_step_repack(None, None, None, None, 1e-3, 0.9, 0.999, 1e-8, 1, None, None, None) == 1
     assert l.gbn_mlp_variant() in (0, 1, 2) and l.gbn_kernel_launches() >= 0
     assert l.gbn_composite_forward(None, None, None, 3, None, 0, 64, 1, None, None, None, None, None, None, None) == 0
+
+
+def test_watchdog_record_is_empty_before_any_launch(lib):
+    """gbn_watchdog_report makes no CUDA call: on a machine without a GPU it reports that nothing was recorded, and the
+    per-launch check of ops.py passes."""
+    assert lib.watchdog_report() is None
+    from gbnerf_b200 import ops
+    ops._raise_if_watchdog_fired()
