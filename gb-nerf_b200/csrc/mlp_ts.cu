@@ -742,6 +742,10 @@ const TsPlan& ts_plan(int bwd) {
         if (!((mask >> ei) & 1)) j.flags |= TJ_WAIT_A1;
         ++ei;
       }
+    // test hook for the watchdog path (tests/test_gpu_watchdog.py, opt-in): forward job 3 waits for an issue-order signal
+    // that nobody raises, so issuer 0 runs into the bounded wait (code 0x24000003) and the CTA aborts
+    const char* hang = getenv("GBNERF_TS_DBG_HANG");
+    if (hang && hang[0] == '1') g_ts_plan[0].jobs[3].flags |= TJ_WAIT_ORDER;
     // ring-stage ownership (see ts_wait_progress): mark the jobs whose stage was last / is next used by the other
     // issuer; the job sequence repeats every tile, so the neighbour `stages` slots away wraps around the table
     const char* ng = getenv("GBNERF_TS_DBG_NO_RING_GUARD");   // timing A/B only: without the guard the kernel can fail
