@@ -100,7 +100,8 @@ struct TsArgs {
 // Post-mortem of a watchdog expiry, in host-mapped memory so that it survives a dead context
 // (gbn_watchdog_report): [0] code of the first wait that expired, [1] CTA, [2] thread, [3] 1,
 // [8 + 2i, 9 + 2i] raw mbarrier word i counted backwards from the last barrier of the layout,
-// [128 + warp] the wait each warp of that CTA was parked in when the abort flag went up.
+// [128 + warp] the last wait that warp left through the abort path (after the abort every wait returns at once, so
+// this is where the warp was when the kernel wound down, not where it was parked; first-write-wins is a TODO).
 __device__ unsigned int* g_ts_wd_host = nullptr;
 static unsigned int* g_ts_wd_host_ptr = nullptr;
 constexpr int kWdWords = 256, kWdBarriers = 32;

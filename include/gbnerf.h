@@ -139,7 +139,7 @@ int gbn_mlp_set_trace(void* buf, int tile);
  * the first wait that expires writes a record into zero-copy HOST memory, so it can be read after the CUDA context
  * has died: out[0] = wait code (role << 24 | job/step), out[1] = CTA, out[2] = thread, out[3] = 1 if a record exists,
  * out[8 + 2i .. 9 + 2i] = raw 64-bit state of the i-th barrier counted back from the end of the kernel's barrier block,
- * out[128 + w] = wait code warp w of that CTA was parked in, out[160 + w] = its CTA.  Copies up to `words` (<= 256)
+ * out[128 + w] = code of the last wait warp w (of any aborting CTA, out[160 + w]) left through the abort path.  Copies up to `words` (<= 256)
  * 32-bit words and returns the number copied (0 before the first MLP launch).  Makes no CUDA call.
  * Not part of the reference-facing surface. */
 int gbn_watchdog_report(unsigned int* out, int words);
