@@ -8,7 +8,7 @@ mbarriers that expose only the PARITY of their phase, as the hardware does.  It 
   * overflow  - more arrivals on a barrier than its phase expects,
   * deadlock  - a role never finished,
   * hazards   - a tensor-memory / shared-memory operand read or overwritten out of order (accumulator halves, the
-                activation buffers A0/A1 at 16-column granularity, encoding blocks, weight stages), from access logs.
+                activation buffers A0/A1 at 16-column granularity, encoding blocks, weight stages, gate staging), from access logs.
 
 The kernel is the product; this model only checks its protocol (it found nothing the GPU did not: it reproduces the
 weight-ring alias of DESIGN.md §3.1 when the ring guard is switched off, which is how it is itself validated).
@@ -153,7 +153,7 @@ def simulate(plan, tiles=4, seed=0, guard=True, cold=0.25, no_split=False):
     m_empty = [B(f"m_empty[{i}]", 256) for i in range(2)]
     prog = [{"v": 0, "w": []}, {"v": 0, "w": []}]
     pipe = {"free": 0}
-    log = dict(fill=[], wread=[], accw=[], accr=[], ast=[], ard=[], sw=[], sr=[])
+    log = dict(fill=[], wread=[], accw=[], accr=[], ast=[], ard=[], sw=[], sr=[], gfill=[], gread=[])
     stage_busy = [False] * NST
     njobs = len(P.jobs)
     # ordinal of the acc1_empty completion each EMPTY1 job waits for, and commit group of every job / step
@@ -301,7 +301,9 @@ def simulate(plan, tiles=4, seed=0, guard=True, cold=0.25, no_split=False):
                 if BWD and st.mode == EPI_MASK:
                     b = mc & 1
                     yield wait(m_full[b], mc >> 1, mc >> 1, f"gates of step {si}")
+                    t0 = sim.now
                     yield ("delay", rng.randint(30, 90))
+                    log["gread"].append((b, mc, t0, sim.now, warp))
                     m_empty[b].arrive(32)
                     mc += 1
                 t0 = sim.now
@@ -353,7 +355,12 @@ def simulate(plan, tiles=4, seed=0, guard=True, cold=0.25, no_split=False):
                 b, n = mc & 1, mc >> 1
                 yield wait(m_empty[b], (n & 1) ^ 1, n - 1 if n > 0 else None, "gate buffer free")
                 lat = rng.randint(400, 3000)
-                sim.at(sim.now + lat, m_full[b].arrive)
+                t0 = sim.now
+
+                def gland(b=b, mc=mc, t0=t0):
+                    log["gfill"].append((b, mc, t0, sim.now))
+                    m_full[b].arrive()
+                sim.at(sim.now + lat, gland)
                 yield ("delay", rng.randint(20, 60))
                 mc += 1
 
@@ -427,6 +434,18 @@ def check_logs(log):
             if not full or max(full) != exp or (started and max(started) != exp):
                 add(f"job {j} read A{buf} columns {16 * cg}.. expecting version {exp}, found complete {max(full) if full else None}"
                     f" / started {max(started) if started else None}")
+    # gate staging (dgrad): a warp reads the gates loaded for its step, and no load is landing on the buffer meanwhile
+    gf = {}
+    for b, mc, t0, t1 in log["gfill"]:
+        gf.setdefault(b, []).append((t1, t0, mc))
+    for b in gf:
+        gf[b].sort()
+    for b, mc, t0, t1, warp in log["gread"]:
+        landed = [f for f in gf.get(b, []) if f[0] <= t0]
+        if not landed or landed[-1][2] != mc:
+            add(f"epilogue warp {warp} read gate buffer {b} holding step {landed[-1][2] if landed else None}, wanted {mc}")
+        if any(f[1] < t1 and f[0] > t0 for f in gf.get(b, [])):
+            add(f"epilogue warp {warp} read gate buffer {b} while a load was landing on it")
     # encoding / direction blocks in shared memory
     sw = {}
     for name, t, w, t0, t1 in log["sw"]:
