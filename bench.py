@@ -5,10 +5,13 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-A step = one full-frame inference render (1008x756 SPIn-NeRF images_4 shape = 762,048 rays, chunk 32,768,
-coarse 64 + fine 64 samples, aconfig_1 test kwargs) per GPU through `gbnerf_b200.render`.  With N ranks each
-rank renders its own contiguous block of an N-frame ray set (weak scaling: rays are independent) and
-the 24 B/ray image outputs are gathered on rank 0 inside the timed region.
+A step = ONE full-frame inference render (1008x756 SPIn-NeRF images_4 shape = 762,048 rays, chunk 32,768,
+coarse 64 + fine 64 samples, aconfig_1 test kwargs) through `gbnerf_b200.render`.  With N ranks the frame is
+ray-sharded (BASELINE configs[1]): rank g renders rays [g R/N, (g+1) R/N) and the 24 B/ray image outputs
+are gathered on rank 0 inside the timed region - strong scaling, total work fixed.  Secondary legs on the same line:
+`train_step` (BASELINE configs[2]: ONE 4096-ray batch sharded over the ranks, CUDA-graphed step with NCCL gradient
+all-reduce and Adam), `stress` (configs[3]: 65,536 rays, 128 + 256 samples, the bandwidth-bound kernels against the
+HBM roofline), `tcnn` (configs[4]).
 
 One JSON line is printed by rank 0; see DESIGN.md §Measurement for every key.
 """
@@ -131,13 +134,15 @@ def run_ours(args, rank, world, local_rank):
               network_fine=nets[1], N_samples=N_SAMPLES, network_fn=nets[0], use_viewdirs=True, white_bkgd=True,
               raw_noise_std=0., ndc=False, lindisp=True, near=NEAR, far=FAR)
 
-    rays_host = synthetic_frame_rays(rank).pin_memory()          # this rank's frame: [2, R, 3]
-    R = rays_host.shape[1]
+    frame = synthetic_frame_rays(0)                               # ONE frame for the whole job: [2, R_total, 3]
+    R_total = frame.shape[1]
     if args.rays:
-        R = min(R, args.rays)
-        rays_host = rays_host[:, :R].contiguous().pin_memory()
+        R_total = min(R_total, args.rays)
+    lo, hi = G.dist.shard_bounds(R_total, rank, world)            # this rank's contiguous block
+    R = hi - lo
+    rays_host = frame[:, lo:hi].contiguous().pin_memory()
     rays_dev = rays_host.to(dev)
-    out_host = torch.empty(R, 6, pin_memory=True)
+    out_host = torch.empty(R_total if rank == 0 else 1, 6, pin_memory=True)   # the gathered image lands on rank 0
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     stream = torch.cuda.current_stream()
 
@@ -146,15 +151,19 @@ def run_ours(args, rank, world, local_rank):
             rgb, disp, acc, depth, _ = G.render(H, W, FOCAL, chunk=CHUNK, rays=rays_dev, **kw)
             packed = torch.cat([rgb, disp[:, None], acc[:, None], depth[:, None]], 1)
             if world > 1:
-                return G.dist.gather_rows(packed, R * world, dst=0)
+                return G.dist.gather_rows(packed, R_total, dst=0)
             return packed
 
     def step_e2e():
+        # host rays -> device, render this rank's block, gather the image on rank 0, image -> host (rank 0)
         with torch.no_grad():
             r = rays_host.to(dev, non_blocking=True)
             rgb, disp, acc, depth, _ = G.render(H, W, FOCAL, chunk=CHUNK, rays=r, **kw)
             packed = torch.cat([rgb, disp[:, None], acc[:, None], depth[:, None]], 1)
-            out_host.copy_(packed, non_blocking=True)
+            if world > 1:
+                packed = G.dist.gather_rows(packed, R_total, dst=0)
+            if rank == 0:
+                out_host.copy_(packed, non_blocking=True)
             return packed
 
     def barrier():
@@ -207,28 +216,16 @@ def run_ours(args, rank, world, local_rank):
     # untimed frames precede the timed region; `warmup` in the JSON line stays the requested W.
     for _ in range(5):
         step_resident()
-    # On some boxes the GPU sits idle between kernels for part of a pass (the kernels themselves run at their usual
-    # speed, the host has the whole pass enqueued within tens of ms, and an identical pass a second later is clean;
-    # seen as 180 vs 250-300 ms/step on the same box).  A pass whose GPU-busy share shows such gaps is therefore
-    # re-measured, at most twice; every attempt is reported in `attempts_ms_per_step`, the cleanest one is the value.
-    attempts = []
-    best = None
+    # Three passes of K steps each, always; the headline is the MEDIAN pass (not the best), every pass is listed in
+    # `attempts_ms_per_step`.  (Round 1 kept the fastest of up to three; on some boxes the first pass after start-up
+    # shows GPU-idle gaps between kernels - 180 vs 200-300 ms/step - which the median absorbs without hiding them.)
+    passes = []
     for attempt in range(3):
-        res = timed(step_resident, args.steps, args.warmup if attempt == 0 else 0, sample_clocks=True, kernel_events=True)
-        busy = sum(a.elapsed_time(b) for (_, a, b, _) in (res[2] or [])) / res[0] if res[0] else 0.0
-        attempts.append(round(res[0] / args.steps, 3))
-        if best is None or res[0] < best[0]:
-            best = res
-        if world > 1:   # every rank must take the same decision
-            flag = torch.tensor([1.0 if busy < 0.93 else 0.0], device=dev)
-            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-            again = flag.item() > 0
-        else:
-            again = busy < 0.93
-        if not again:
-            break
-    ms, launches, events, clocks = best
-    rays_total = R * world * args.steps
+        passes.append(timed(step_resident, args.steps, args.warmup if attempt == 0 else 0, sample_clocks=True,
+                            kernel_events=True))
+    attempts = [round(r[0] / args.steps, 3) for r in passes]
+    ms, launches, events, clocks = sorted(passes, key=lambda r: r[0])[1]
+    rays_total = R_total * args.steps
     value = rays_total / (ms * 1e-3)
 
     # dominant kernel: the fused encode+MLP kernel, timed per launch with CUDA events inside the timed region
@@ -238,7 +235,7 @@ def run_ours(args, rank, world, local_rank):
     achieved = mlp_pts * FLOP_PER_POINT / (sum(mlp_ms) * 1e-3) / 1e12 if mlp_ms else None
     peak = pk["bf16_tflops_sustained"]
     variant = os.environ.get("GBNERF_MLP", "ts") if args.precision == "bf16" else "ss"   # csrc/mlp_aux.cu mlp_variant()
-    mlp_kernel_name = {"ts": "nerf_mlp_ts_kernel", "tq": "nerf_mlp_tq_kernel"}.get(variant, "nerf_mlp_kernel")
+    mlp_kernel_name = {"ts": "nerf_mlp_ts_kernel"}.get(variant, "nerf_mlp_kernel")
     traffic = profile_traffic_bytes()
     roofline = {"kernel": f"{mlp_kernel_name}<{args.precision}> (fused point generation + posenc + 8x256 MLP)",
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
@@ -251,12 +248,18 @@ def run_ours(args, rank, world, local_rank):
 
     e2e_steps = max(2, min(args.steps, 5))
     ms_e2e, _, _, _ = timed(step_e2e, e2e_steps, 1)
-    e2e = {"value": R * world * e2e_steps / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": R * 6 * 4,
-           "d2h_bytes_per_step": R * 6 * 4, "api": "gbnerf_b200.render(H, W, focal, chunk, rays=<pinned host>)"}
+    e2e = {"value": R_total * e2e_steps / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": R_total * 6 * 4,
+           "d2h_bytes_per_step": R_total * 6 * 4,
+           "api": "gbnerf_b200.render(H, W, focal, chunk, rays=<pinned host block of this rank>) + dist.gather_rows -> "
+                  "pinned host image on rank 0 (H2D summed over ranks, D2H on rank 0)"}
 
     train = None
     if args.precision == "bf16" and not args.no_train:
         train = train_step_bench(G, ops, dev, nets, kw, rank, world, timed)
+
+    stress = None
+    if args.precision == "bf16" and not args.no_stress:
+        stress = stress_bench(G, ops, dev, kw, rank, world, timed, pk)
 
     tcnn = None
     if not args.no_tcnn:
@@ -272,16 +275,20 @@ def run_ours(args, rank, world, local_rank):
                 train["cpu_baseline"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-                "config": {"workload": "full-frame inference render 1008x756 (762,048 rays/GPU), coarse 64 + fine 64, "
+                "config": {"workload": "ONE full-frame inference render 1008x756 (762,048 rays), coarse 64 + fine 64, "
                                        "chunk 32768, lindisp, white_bkgd, viewdirs, random-init 8x256 MLPs (seed 0)",
-                           "rays_per_gpu": R, "parallelism": f"ray-sharded x{world}",
+                           "rays_total": R_total, "rays_per_gpu": R,
+                           "parallelism": f"one frame ray-sharded x{world} (contiguous blocks), image gathered on rank 0",
                            "l2": "256 MiB memset between steps (inside the timed region)",
-                           "extra_untimed_warmup_steps": 5, "attempts_ms_per_step": attempts},
+                           "extra_untimed_warmup_steps": 5, "attempts_ms_per_step": attempts,
+                           "value_is": "median of the three passes"},
                 "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
         if train is not None:
             line["train_step"] = train
+        if stress is not None:
+            line["stress"] = stress
         if tcnn is not None:
             line["tcnn"] = tcnn
         if cpu is not None:
@@ -292,46 +299,138 @@ def run_ours(args, rank, world, local_rank):
 
 
 def train_step_bench(G, ops, dev, nets, kw_test, rank, world, timed):
-    """BASELINE configs[2]: 4096-ray training step (weak scaling: 4096 rays per GPU), train kwargs (perturb=1,
-    raw_noise_std=1), loss of SURVEY §8a row 12 over the GLOBAL batch, backward through the native kernels, one flat
-    gradient all-reduce over NCCL, Adam step.  Reported beside the headline metric, not instead of it."""
+    """BASELINE configs[2]: ONE 4096-ray training batch sharded over the ranks (512 rays/GPU at N=8), train
+    kwargs (perturb=1, raw_noise_std=1), loss of SURVEY §8a row 12 over the global batch, backward through the native
+    kernels, NCCL gradient all-reduce, Adam.  Headline of this leg: `gbnerf_b200.TrainStep`, the whole step as one CUDA
+    graph.  Beside it: the same step through the drop-in API (`render` + autograd + `GradBucket` + `FusedAdam.step()`,
+    ~150 eager launches), whose per-launch CUDA events give the MLP kernel split."""
+    import torch.distributed as dist
     R = 4096
     kw = dict(kw_test, perturb=1.0, raw_noise_std=1.0)
-    rays2 = synthetic_frame_rays(rank)
-    idx = torch.randint(0, rays2.shape[1], (R,), generator=torch.Generator().manual_seed(1 + rank))
-    rays = rays2[:, idx].contiguous().to(dev)
-    g = torch.Generator().manual_seed(2 + rank)
+    rays2 = synthetic_frame_rays(0)
+    idx = torch.randint(0, rays2.shape[1], (R,), generator=torch.Generator().manual_seed(1))
+    o, d = rays2[0, idx], rays2[1, idx]
+    vd = d / d.norm(dim=-1, keepdim=True)
+    batch = torch.cat([o, d, torch.full((R, 1), NEAR), torch.full((R, 1), FAR), vd], 1).to(dev)   # [R, 11]
+    g = torch.Generator().manual_seed(2)
     tgt, tgd = torch.rand(R, 3, generator=g).to(dev), torch.rand(R, generator=g).to(dev)
+    lo, hi = G.dist.shard_bounds(R, rank, world)
     params = [p for n in nets for p in n.parameters()]
-    bucket = G.dist.GradBucket(params)
-    opt = G.FusedAdam(params, lr=3e-3, betas=(0.9, 0.999))   # what create_nerf returns: a torch.optim.Adam, one launch/net
-    inv_world = 1.0 / world
+    opt = G.FusedAdam(params, lr=3e-3, betas=(0.9, 0.999))   # what create_nerf returns
+    steps = 20
 
-    def step():
-        rgb, disp, acc, depth, ex = G.render(H, W, FOCAL, chunk=CHUNK, rays=rays, **kw)
-        loss = (G.img2mse(rgb, tgt) + G.img2mse(ex["rgb0"], tgt) + 0.1 * G.img2mse(disp, tgd)) * inv_world
+    # ---- drop-in API, eager: this rank's block of the batch, losses scaled to the global mean -------------------------
+    bucket = G.dist.GradBucket(params)
+    scale = (hi - lo) / R
+    rays_mine = torch.stack([batch[lo:hi, 0:3], batch[lo:hi, 3:6]], 0).contiguous()
+
+    def eager_step():
+        rgb, disp, acc, depth, ex = G.render(H, W, FOCAL, chunk=CHUNK, rays=rays_mine, **kw)
+        loss = (G.img2mse(rgb, tgt[lo:hi]) + G.img2mse(ex["rgb0"], tgt[lo:hi]) + 0.1 * G.img2mse(disp, tgd[lo:hi])) * scale
         bucket.zero()
         loss.backward()
         bucket.all_reduce()
         opt.step()
         return loss
 
-    steps = 10
-    passes = [timed(step, steps, 3 if i == 0 else 0, kernel_events=True) for i in range(2)]   # see run_ours: idle gaps
-    ms, launches, events, _ = min(passes, key=lambda r: r[0])
-    both_ms = [round(r[0] / steps, 3) for r in passes]
+    ms_e, launches_e, events, _ = timed(eager_step, steps, 3, kernel_events=True)
     per = {}
     for name, a, b, pts in events:
-        d = per.setdefault(name, [0.0, 0])
-        d[0] += a.elapsed_time(b)
-        d[1] += pts
-    flop = sum(d[1] for d in per.values()) * FLOP_PER_POINT           # forward + dgrad + wgrad ~ 3 x forward
-    t_mlp = sum(d[0] for d in per.values())
-    return {"metric": "rays/sec, 4096-ray training step (fwd + bwd + grad all-reduce + Adam)", "value": R * world * steps / (ms * 1e-3),
-            "unit": "rays/s", "ms_per_step": ms / steps, "rays_per_gpu": R, "scaling": "weak",
-            "mlp_kernels_ms_per_step": {k: v[0] / steps for k, v in per.items()},
-            "mlp_tflops_fwd_equivalent": flop / (t_mlp * 1e-3) / 1e12 if t_mlp else None,
-            "grad_allreduce_bytes": bucket.flat.numel() * 4, "gpu_launches": launches, "passes_ms_per_step": both_ms}
+        if not name.startswith("mlp"):
+            continue
+        dd = per.setdefault(name, [0.0, 0])
+        dd[0] += a.elapsed_time(b)
+        dd[1] += pts
+    flop = sum(v[1] for v in per.values()) * FLOP_PER_POINT           # forward + dgrad + wgrad ~ 3 x forward
+    t_mlp = sum(v[0] for v in per.values())
+
+    # ---- the graphed step ------------------------------------------------------------------------------------------
+    ts = G.TrainStep(kw, opt, R, depth_lambda=0.1)
+
+    def graph_step():
+        return ts.step(batch, tgt, tgd)
+
+    passes = [timed(graph_step, steps, 3 if i == 0 else 0) for i in range(3)]
+    ms = sorted(r[0] for r in passes)[1]
+    codes = ts.error_codes()
+    loss = ts.loss.clone()
+    if world > 1:
+        dist.all_reduce(loss)
+    return {"metric": "rays/sec, ONE 4096-ray training step (fwd + bwd + grad all-reduce + Adam) sharded over the ranks",
+            "value": R * steps / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms / steps, "rays_total": R, "rays_per_gpu": hi - lo,
+            "scaling": "strong", "api": "gbnerf_b200.TrainStep(render_kwargs_train, optimizer, 4096).step(rays, rgb, disp): one CUDA graph",
+            "passes_ms_per_step": [round(r[0] / steps, 4) for r in passes], "value_is": "median of the three passes",
+            "gpu_launches": (ts.launches_per_step or 0) * steps, "kernels_per_step_in_graph": ts.launches_per_step,
+            "watchdog_words": codes, "loss_after": float(loss.item()),
+            "tflops_fwd_bwd": R * 683.6e6 * steps / (ms * 1e-3) / 1e12 / world,
+            "grad_allreduce_bytes": sum(f.numel() for f in ts.flat) * 4,
+            "allreduce": "NCCL, one per network; the fine network's overlaps the coarse network's backward",
+            "eager_dropin": {"api": "render + loss.backward() + GradBucket.all_reduce() + FusedAdam.step()",
+                             "ms_per_step": ms_e / steps, "value": R * steps / (ms_e * 1e-3), "gpu_launches": launches_e,
+                             "mlp_kernels_ms_per_step": {k: v[0] / steps for k, v in per.items()},
+                             "mlp_tflops_fwd_equivalent": flop / (t_mlp * 1e-3) / 1e12 if t_mlp else None}}
+
+
+def stress_bench(G, ops, dev, kw_test, rank, world, timed, pk):
+    """BASELINE configs[3]: 65,536 rays, N_samples=128 + N_importance=256 - the regime in which sample_pdf / merge and
+    compositing move the most bytes per ray (12,360 B/ray forward).  Inference with test kwargs over all 65,536 rays
+    (sharded over the ranks) and a training pass (train kwargs, loss, backward through the drop-in autograd path) over
+    4096-ray micro-batches; per-kernel GB/s = algorithmic bytes / CUDA-event time of each launch inside
+    the timed region, against the measured HBM copy peak.  In-pipeline figures: an input a kernel reads may still sit
+    in L2 from its producer (raw [32768,128,4] is 67 MB); the cold-cache ncu figures are under profiles/."""
+    R, S, N = 65536, 128, 256
+    lo, hi = G.dist.shard_bounds(R, rank, world)
+    kw = dict(kw_test, N_samples=S, N_importance=N)
+    rays2 = synthetic_frame_rays(0)
+    idx = torch.randint(0, rays2.shape[1], (R,), generator=torch.Generator().manual_seed(3))
+    rays = rays2[:, idx[lo:hi]].contiguous().to(dev)
+
+    def infer():
+        with torch.no_grad():
+            return G.render(H, W, FOCAL, chunk=CHUNK, rays=rays, **kw)
+
+    steps = 5
+    ms, launches, events, _ = timed(infer, steps, 3, kernel_events=True)
+
+    def kernel_table(events):
+        per = {}
+        for name, a, b, units in events:
+            if name.startswith("mlp") or name.startswith("tcnn"):
+                continue
+            dd = per.setdefault(name, [0.0, 0, 0])
+            dd[0] += a.elapsed_time(b); dd[1] += units; dd[2] += 1
+        return {k: {"GBps": v[1] / (v[0] * 1e-3) / 1e9, "frac_of_hbm_peak": v[1] / (v[0] * 1e-3) / 1e9 / pk["hbm_gbs"],
+                    "avg_launch_us": 1e3 * v[0] / v[2], "launches": v[2], "algorithmic_bytes_per_launch": v[1] / v[2]}
+                for k, v in per.items() if v[0] > 0}
+
+    out = {"metric": "rays/sec, 65,536-ray render at N_samples=128 + N_importance=256 (inference, test kwargs)",
+           "value": R * steps / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms / steps, "rays_total": R, "rays_per_gpu": hi - lo,
+           "scaling": "strong", "gpu_launches": launches, "hbm_peak_GBps": pk["hbm_gbs"],
+           "kernels_inference": kernel_table(events),
+           "note": "per-kernel GB/s = SURVEY 8d algorithmic bytes / CUDA-event time per launch, in-pipeline (inputs may be "
+                   "L2-resident from the producing kernel); cold-cache ncu dram figures: profiles/"}
+    # training pass over 4096-ray micro-batches (activations of more rays would not fit next to each other)
+    Rm = 4096
+    nets = [kw["network_fn"], kw["network_fine"]]
+    kwt = dict(kw, perturb=1.0, raw_noise_std=1.0)
+    g = torch.Generator().manual_seed(4)
+    tgt, tgd = torch.rand(Rm, 3, generator=g).to(dev), torch.rand(Rm, generator=g).to(dev)
+    rays_m = rays[:, :Rm].contiguous()
+
+    def train():
+        rgb, disp, acc, depth, ex = G.render(H, W, FOCAL, chunk=CHUNK, rays=rays_m, **kwt)
+        loss = G.img2mse(rgb, tgt) + G.img2mse(ex["rgb0"], tgt) + 0.1 * G.img2mse(disp, tgd)
+        for n in nets:
+            for p in n.parameters():
+                p.grad = None
+        loss.backward()
+        return loss
+
+    ms_t, launches_t, events_t, _ = timed(train, steps, 2, kernel_events=True)
+    out["train_microbatch"] = {"rays": Rm, "ms_per_step": ms_t / steps, "value": Rm * steps / (ms_t * 1e-3), "unit": "rays/s",
+                               "what": "forward + loss + backward (no optimizer step), drop-in autograd path, per GPU",
+                               "gpu_launches": launches_t, "kernels": kernel_table(events_t)}
+    return out
 
 
 def profile_traffic_bytes():
@@ -349,7 +448,7 @@ def profile_traffic_bytes():
 
 
 def tcnn_bench(G, ops, dev, kw_test, rank, world, timed):
-    """BASELINE configs[4]: 262,144 rays per GPU through the hash-grid model (NeRF_TCNN, coarse 64 + fine 64, test
+    """BASELINE configs[4]: 262,144 rays (sharded over the ranks) through the hash-grid model (NeRF_TCNN, coarse 64 + fine 64, test
     kwargs).  Reported beside the headline metric.  The model's kernel is bound by its 16 x 8 four-byte table reads per
     point (512 B/point from a 28 MB fp16 table that lives in L2), so the figure given is that gather rate."""
     R, chunk = 262144, 32768
@@ -360,9 +459,10 @@ def tcnn_bench(G, ops, dev, kw_test, rank, world, timed):
             n.encoder.params.normal_(0.0, 0.5)   # tiny-cuda-nn's +-1e-4 start would leave every feature an fp16 subnormal
     ident = G.run._identity
     kw = dict(kw_test, network_fn=nets[0], network_fine=nets[1], network_query_fn=G.NetworkQuery(ident, ident, 65536))
-    rays2 = synthetic_frame_rays(rank)
-    idx = torch.randint(0, rays2.shape[1], (R,), generator=torch.Generator().manual_seed(7 + rank))
-    rays = rays2[:, idx].contiguous().to(dev)
+    rays2 = synthetic_frame_rays(0)
+    idx = torch.randint(0, rays2.shape[1], (R,), generator=torch.Generator().manual_seed(7))
+    lo, hi = G.dist.shard_bounds(R, rank, world)
+    rays = rays2[:, idx[lo:hi]].contiguous().to(dev)
 
     def step():
         with torch.no_grad():
@@ -375,23 +475,59 @@ def tcnn_bench(G, ops, dev, kw_test, rank, world, timed):
     t = sum(a.elapsed_time(b) for name, a, b, _ in events if name == "tcnn")
     pts = sum(p for name, _, _, p in events if name == "tcnn")
     return {"metric": "rays/sec, 262,144-ray inference render through the hash-grid model (coarse64+fine64)",
-            "value": R * world * steps / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms / steps, "rays_per_gpu": R,
-            "scaling": "weak", "gpu_launches": launches, "passes_ms_per_step": both_ms,
+            "value": R * steps / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms / steps, "rays_total": R, "rays_per_gpu": hi - lo,
+            "scaling": "strong", "gpu_launches": launches, "passes_ms_per_step": both_ms,
             "kernel": {"name": "tcnn_forward_kernel", "bound": "L2 gather (28 MB fp16 table, 512 B/point of 4-byte reads)",
                        "points_per_s": pts / (t * 1e-3) if t else None, "gather_GBps": pts * 512 / (t * 1e-3) / 1e9 if t else None,
                        "share_of_step": t / ms if ms else None, "parity": "unpinned (oracle/tcnn_oracle.py restates tiny-cuda-nn)"}}
 
 
 # --------------------------------------------------------------------------------------------------------- #
+_REF = {}
+
+
+def reference_kind():
+    """"reference" when the unmodified reference files are staged under oracle/_ref/ (oracle/make_ref.py; they travel
+    to the GPU box with the snapshot), else "port" (oracle/nerf_oracle.py, pinned to the reference by the goldens)."""
+    from oracle import ref_loader
+    return "reference" if ref_loader.staged_available() else "port"
+
+
+def cpu_threads():
+    """All host cores, whatever the launcher exported: torchrun sets OMP_NUM_THREADS=1, which left the round-1
+    reference arm on one thread at N > 1."""
+    n = os.cpu_count() or 1
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
 def cpu_render(n_rays, threads=None):
-    """The oracle port of the reference render_rays on the host cores; returns seconds for one pass."""
-    from oracle import nerf_oracle as O
+    """The reference's own render() -> batchify_rays -> render_rays (staged copy, run.py:1672-1748, 2235-2381) on the
+    host cores with the reference's chunk (32,768) and netchunk (65,536), test kwargs; the oracle port if nothing is
+    staged.  Returns seconds for one pass over n_rays rays of the benchmark frame."""
+    import tempfile
+    from oracle import ref_loader
     if threads:
         torch.set_num_threads(threads)
     rays2 = synthetic_frame_rays(0)
     g = torch.Generator().manual_seed(1)
     idx = torch.randint(0, H * W, (n_rays,), generator=g)
     o, d = rays2[0, idx], rays2[1, idx]
+    if ref_loader.staged_available():
+        if "ns" not in _REF:
+            ns = ref_loader.load_staged("cpu")
+            torch.manual_seed(0)
+            import contextlib, io
+            with contextlib.redirect_stdout(io.StringIO()):       # create_nerf prints ("Found ckpts", "Not ndc!")
+                _, kw_test, *_ = ns["create_nerf"](ref_loader.default_args(tempfile.mkdtemp()))
+            kw_test.update(near=NEAR, far=FAR)
+            _REF["ns"], _REF["kw"] = ns, kw_test
+        ns, kw = _REF["ns"], _REF["kw"]
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            ns["render"](H, W, FOCAL, chunk=CHUNK, rays=torch.stack([o, d]), **kw)
+            return time.perf_counter() - t0
+    from oracle import nerf_oracle as O
     rays = O.pack_rays(o, d, NEAR, FAR)
     torch.manual_seed(0)
     pc, pf = O.init_params(0), O.init_params(None)
@@ -462,8 +598,9 @@ def cpu_train_step(n_rays=512):
                       f"(torch CPU fp32), no optimizer step, best of 2"}
 
 
-def cpu_baseline(bounded_s=20.0, n_rays=1024):
-    threads = torch.get_num_threads()
+def cpu_baseline(bounded_s=20.0, n_rays=4096):
+    threads = cpu_threads()
+    kind = reference_kind()
     cpu_render(256)                      # warm-up
     best, spent = None, 0.0
     for _ in range(3):
@@ -472,18 +609,26 @@ def cpu_baseline(bounded_s=20.0, n_rays=1024):
         best = dt if best is None else min(best, dt)
         if spent > bounded_s:
             break
-    return {"value": n_rays / best, "unit": "rays/s", "cores": threads, "kind": "port",
-            "sample": f"{n_rays} random pixels of the same frame, same kwargs, oracle/nerf_oracle.py (torch CPU fp32), "
-                      f"best of 3", "host_cpu_count": os.cpu_count()}
+    what = "the unmodified reference render() staged under oracle/_ref (torch CPU fp32)" if kind == "reference" \
+        else "oracle/nerf_oracle.py (torch CPU fp32)"
+    return {"value": n_rays / best, "unit": "rays/s", "cores": threads, "kind": kind,
+            "sample": f"{n_rays} random pixels of the same frame, same kwargs, chunk 32768 / netchunk 65536, {what}, best of 3",
+            "host_cpu_count": os.cpu_count()}
 
 
 def run_reference(args, rank, world):
-    """The reference's own CPU implementation of the path (its PyTorch code cannot travel to the GPU box, so the
-    oracle port — pinned to it by tests/golden — is what runs), all host threads, bounded sample per step."""
+    """The reference's own CPU implementation of the path on the box's host cores, all threads: the unmodified
+    reference code when oracle/_ref is staged (kind "reference"), else the oracle port.  Each step renders a bounded
+    sample (1,024 to 8,192 random pixels, sized so that the run takes about two minutes) of the same frame with the reference's own chunk / netchunk sizes."""
     if rank != 0:
         return
-    n_rays = 1024
-    threads = torch.get_num_threads()
+    threads = cpu_threads()
+    kind = reference_kind()
+    cpu_render(256)                                   # first touch (imports, thread pool)
+    rate = 1024 / cpu_render(1024)                    # rays/s of this host: size the per-step sample for ~120 s in all
+    n_rays = 8192
+    while n_rays > 1024 and (args.steps + args.warmup) * n_rays / rate > 120.0:
+        n_rays //= 2
     for _ in range(args.warmup):
         cpu_render(n_rays)
     t0 = time.perf_counter()
@@ -491,13 +636,16 @@ def run_reference(args, rank, world):
         cpu_render(n_rays)
     dt = time.perf_counter() - t0
     v = n_rays * args.steps / dt
-    sample = f"{n_rays} random pixels of the 1008x756 frame per step (bounded sample of the same workload)"
+    sample = (f"{n_rays} random pixels of the 1008x756 frame per step (bounded sample of the same workload), "
+              f"reference chunk 32768 / netchunk 65536, {threads} threads")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "full-frame inference render 1008x756, coarse 64 + fine 64 (bounded sample)",
-                       "rays_per_step": n_rays},
-            "cpu_baseline": {"value": v, "unit": "rays/s", "cores": threads, "kind": "port", "sample": sample},
+            "config": {"workload": "ONE full-frame inference render 1008x756 (762,048 rays), coarse 64 + fine 64 "
+                                   "(bounded sample per step)", "rays_per_step": n_rays,
+                       "code": "unmodified reference render()/render_rays()/NeRF (oracle/_ref, staged by oracle/make_ref.py)"
+                       if kind == "reference" else "oracle/nerf_oracle.py port"},
+            "cpu_baseline": {"value": v, "unit": "rays/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -536,6 +684,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-train", action="store_true", help="skip the 4096-ray training-step leg")
     ap.add_argument("--no-tcnn", action="store_true", help="skip the hash-grid model leg (BASELINE configs[4])")
+    ap.add_argument("--no-stress", action="store_true", help="skip the high-sample stress leg (BASELINE configs[3])")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))

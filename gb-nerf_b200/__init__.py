@@ -8,11 +8,13 @@ Layout
   run.py       drop-in for run.py's create_nerf / render / batchify_rays / render_rays / run_network / batchify
   loss.py      drop-in for DS_NeRF/loss.py (SigmaLoss)
   dist.py      ray sharding across one-process-per-GPU ranks, gradient all-reduce, image gather
+  train.py     TrainStep: one training iteration (render + loss + backward + all-reduce + Adam) as one CUDA graph
 
 The package directory is ``gb-nerf_b200`` (the project's name); import it as ``gbnerf_b200`` through the
 alias module at the repository root.  There is no CPU path: every operator raises without a CUDA device.
 """
-from . import _lib, ops, helpers, run, dist, loss, optim  # noqa: F401
+from . import _lib, ops, helpers, run, dist, loss, optim, train  # noqa: F401
+from .train import TrainStep  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
 from . import tcnn  # noqa: F401
 from .tcnn import NeRF_TCNN  # noqa: F401

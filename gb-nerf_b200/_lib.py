@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgbnerf.so")
+# GBNERF_LIB: another build of the same library (tools: libgbnerf_diag.so, csrc/build.py --diag); never a fallback
+LIB_PATH = os.environ.get("GBNERF_LIB") or os.path.join(_HERE, "libgbnerf.so")
 
 PRECISION = {"bf16": 0, "tf32": 1}
 PACK_BWD_BF16 = 2
@@ -51,6 +52,8 @@ SIGNATURES = {
     "gbn_tcnn_forward": (_i, [_p, _p, _p, _p, _i64, _p, _p, _i64, _i, _p, _p, _p]),
     "gbn_tcnn_backward": (_i, [_p, _p, _p, _p, _i64, _p, _p, _i64, _i, _p, _p, _f, _p, _p, _p, _p, _p]),
     "gbn_adam_step_repack": (_i, [_p, _p, _p, _p, C.c_double, C.c_double, C.c_double, C.c_double, _i64, _p, _p, _p]),
+    "gbn_adam_tick": (_i, [_p, _p, C.c_double, C.c_double, _p, _p]),
+    "gbn_adam_step_repack_dev": (_i, [_p, _p, _p, _p, _p, C.c_double, C.c_double, C.c_double, _p, _p, _p]),
     "gbn_loss_seed": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _f, _p, _p, _p, _p, _p]),
 }
 

@@ -1,6 +1,9 @@
 """Build libgbnerf.so in-tree with plain nvcc for sm_100a (no torch headers, no JIT cache).
 
-    python gb-nerf_b200/csrc/build.py [--force] [--verbose]
+    python gb-nerf_b200/csrc/build.py [--force] [--verbose] [--diag]
+
+--diag builds gb-nerf_b200/libgbnerf_diag.so instead: the same library with the diagnostic switches of the MLP
+kernels compiled in (-DGBN_TS_DIAG: GBNERF_TS_CHAOS, GBNERF_TS_GATE_DIRECT); select it with GBNERF_LIB=<path>.
 
 The shared library lands next to the package (gb-nerf_b200/libgbnerf.so); it is git-ignored but travels to
 the GPU box with the gpurun snapshot.
@@ -14,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libgbnerf.so")
 STAMP = os.path.join(PKG, ".libgbnerf.stamp")
-SOURCES = ["abi.cu", "render_ops.cu", "mlp_tc.cu", "mlp_aux.cu", "mlp_wgrad.cu", "render_staged.cu", "ray_setup.cu", "tcnn_model.cu", "normals.cu", "ts_probe.cu", "mlp_ts.cu", "mlp_tq.cu"]
+SOURCES = ["abi.cu", "render_ops.cu", "mlp_tc.cu", "mlp_aux.cu", "mlp_wgrad.cu", "render_staged.cu", "ray_setup.cu", "tcnn_model.cu", "normals.cu", "ts_probe.cu", "mlp_ts.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC,-O2,-Wall", "--expt-relaxed-constexpr"]
@@ -29,16 +32,18 @@ def _digest():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, diag=False):
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(HERE, s))]
     dig = _digest()
-    if not force and os.path.exists(OUT) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
-        return OUT
+    target = OUT.replace("libgbnerf.so", "libgbnerf_diag.so") if diag else OUT
+    stamp = STAMP + (".diag" if diag else "")
+    if not force and os.path.exists(target) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
+        return target
     objs = []
     procs = []
     for s in srcs:
-        o = os.path.join(HERE, s.replace(".cu", ".o"))
-        cmd = [NVCC, *FLAGS, "-c", os.path.join(HERE, s), "-o", o]
+        o = os.path.join(HERE, s.replace(".cu", ".diag.o" if diag else ".o"))
+        cmd = [NVCC, *FLAGS, *(["-DGBN_TS_DIAG"] if diag else []), "-c", os.path.join(HERE, s), "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -51,13 +56,13 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([NVCC, "-shared", "-o", OUT, *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+    subprocess.check_call([NVCC, "-shared", "-o", target, *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"])
     for o in objs:
         os.remove(o)
-    with open(STAMP, "w") as fh:
+    with open(stamp, "w") as fh:
         fh.write(dig)
-    return OUT
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, diag="--diag" in sys.argv))

@@ -139,17 +139,16 @@ int launch_view_bias(const uint8_t* packed, const MlpPlan& p, const float* viewd
 size_t ts_packed_bytes(int bwd);
 int ts_prepack(const void* const* params, void* packed, int bwd, cudaStream_t st);
 int ts_adam_repack(void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq, double lr,
-                   double beta1, double beta2, double eps, int64_t step, void* packed_fwd, void* packed_bwd, cudaStream_t st);
-size_t tq_packed_bytes(int bwd);
-int tq_prepack(const void* const* params, void* packed, int bwd, cudaStream_t st);
-// bf16 kernel family: 0 = shared-memory operands (mlp_tc.cu), 1 = TMEM operands in halves (mlp_ts.cu),
-// 2 = TMEM operands in quarters (mlp_tq.cu).  GBNERF_MLP=ss|ts|tq overrides the default (GBNERF_MLP_SS=1 == ss).
+                   double beta1, double beta2, double eps, int64_t step, void* packed_fwd, void* packed_bwd, cudaStream_t st,
+                   const float* dev_scalars = nullptr);
+int ts_adam_tick(double* state, const float* lr, double beta1, double beta2, float* scalars, cudaStream_t st);
+// bf16 kernel family: 0 = shared-memory operands (mlp_tc.cu), 1 = TMEM operands (mlp_ts.cu, default).
+// GBNERF_MLP=ss|ts overrides the default (GBNERF_MLP_SS=1 == ss).
 int mlp_variant() {
   static const int v = [] {
     const char* e = getenv("GBNERF_MLP");
     if (e && e[0] == 's') return 0;
     if (e && e[0] == 't' && e[1] == 's') return 1;
-    if (e && e[0] == 't' && e[1] == 'q') return 2;
     const char* s = getenv("GBNERF_MLP_SS");
     if (s && s[0] == '1') return 0;
     return GBN_DEFAULT_MLP_VARIANT;
@@ -170,8 +169,6 @@ extern "C" int gbn_mlp_prepack_weights(const void* const* params, void* packed, 
   GBN_REQUIRE(params && packed, "prepack: null pointer");
   GBN_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 255) == 0, "prepack: packed buffer must be 256-byte aligned");
   for (int i = 0; i < 2 * GBN_NUM_LINEAR; ++i) GBN_REQUIRE(params[i], "prepack: params[%d] is null", i);
-  if (precision != GBN_PRECISION_TF32 && mlp_variant() == 2)
-    return tq_prepack(params, packed, precision == GBN_PACK_BWD_BF16, (cudaStream_t)stream);
   if (precision != GBN_PRECISION_TF32 && mlp_variant() == 1)
     return ts_prepack(params, packed, precision == GBN_PACK_BWD_BF16, (cudaStream_t)stream);
   ParamPtrs pp;
@@ -190,8 +187,8 @@ extern "C" int gbn_mlp_prepack_weights(const void* const* params, void* packed, 
     if (!g_pack_init[dev]) {
       for (int pr = 0; pr < kNumPlans; ++pr) {
         const MlpPlan& q = mlp_plan(pr);
-        GBN_CUDA(cudaMemcpyToSymbolAsync(c_pack, q.pack.data(), q.pack.size() * sizeof(PackJob),
-                                         pr * kMaxJobs * sizeof(PackJob), cudaMemcpyHostToDevice, st));
+        GBN_CUDA(cudaMemcpyToSymbol(c_pack, q.pack.data(), q.pack.size() * sizeof(PackJob),
+                                         pr * kMaxJobs * sizeof(PackJob), cudaMemcpyHostToDevice));
       }
       g_pack_init[dev] = true;
     }
@@ -220,4 +217,23 @@ extern "C" int gbn_adam_step_repack(void* const* params, const void* const* grad
               "adam_step_repack: in-place re-pack exists for the default bf16 weight images only (pass NULL and re-pack)");
   return ts_adam_repack(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, packed_fwd, packed_bwd,
                         (cudaStream_t)stream);
+}
+
+extern "C" int gbn_adam_tick(double* step_state, const float* lr, double beta1, double beta2, float* scalars, void* stream) {
+  GBN_REQUIRE(step_state && lr && scalars, "adam_tick: null pointer");
+  GBN_REQUIRE(beta1 >= 0 && beta1 < 1 && beta2 >= 0 && beta2 < 1, "adam_tick: bad betas");
+  return ts_adam_tick(step_state, lr, beta1, beta2, scalars, (cudaStream_t)stream);
+}
+
+extern "C" int gbn_adam_step_repack_dev(void* const* params, const void* const* grads, void* const* exp_avg,
+                                        void* const* exp_avg_sq, const float* scalars, double beta1, double beta2, double eps,
+                                        void* packed_fwd, void* packed_bwd, void* stream) {
+  GBN_REQUIRE(params && grads && exp_avg && exp_avg_sq && scalars, "adam_step_repack_dev: null pointer");
+  for (int i = 0; i < 2 * GBN_NUM_LINEAR; ++i)
+    GBN_REQUIRE(params[i] && grads[i] && exp_avg[i] && exp_avg_sq[i], "adam_step_repack_dev: tensor %d has a null pointer", i);
+  GBN_REQUIRE(beta1 >= 0 && beta1 < 1 && beta2 >= 0 && beta2 < 1 && eps >= 0, "adam_step_repack_dev: bad hyper-parameters");
+  GBN_REQUIRE((packed_fwd == nullptr && packed_bwd == nullptr) || mlp_variant() == 1,
+              "adam_step_repack_dev: in-place re-pack exists for the default bf16 weight images only");
+  return ts_adam_repack(params, grads, exp_avg, exp_avg_sq, 0.0, beta1, beta2, eps, 1, packed_fwd, packed_bwd,
+                        (cudaStream_t)stream, scalars);
 }

@@ -512,11 +512,11 @@ static int ensure_device(cudaStream_t stream) {
   for (int pr = 0; pr < kNumPlans; ++pr) {
     const MlpPlan& p = plan(pr);
     GBN_REQUIRE((int)p.jobs.size() <= kMaxJobs, "job table overflow");
-    GBN_CUDA(cudaMemcpyToSymbolAsync(c_jobs, p.jobs.data(), p.jobs.size() * sizeof(MlpJob),
-                                     pr * kMaxJobs * sizeof(MlpJob), cudaMemcpyHostToDevice, stream));
-    GBN_CUDA(cudaMemcpyToSymbolAsync(c_unit_begin, p.unit_begin, sizeof(p.unit_begin),
-                                     pr * sizeof(p.unit_begin), cudaMemcpyHostToDevice, stream));
-    GBN_CUDA(cudaMemcpyToSymbolAsync(c_epi, p.epi, sizeof(p.epi), pr * sizeof(p.epi), cudaMemcpyHostToDevice, stream));
+    GBN_CUDA(cudaMemcpyToSymbol(c_jobs, p.jobs.data(), p.jobs.size() * sizeof(MlpJob),
+                                     pr * kMaxJobs * sizeof(MlpJob), cudaMemcpyHostToDevice));
+    GBN_CUDA(cudaMemcpyToSymbol(c_unit_begin, p.unit_begin, sizeof(p.unit_begin),
+                                     pr * sizeof(p.unit_begin), cudaMemcpyHostToDevice));
+    GBN_CUDA(cudaMemcpyToSymbol(c_epi, p.epi, sizeof(p.epi), pr * sizeof(p.epi), cudaMemcpyHostToDevice));
   }
   GBN_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<0>::alloc));
   GBN_CUDA(cudaFuncSetAttribute(nerf_mlp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<1>::alloc));
@@ -529,12 +529,6 @@ int launch_view_bias(const uint8_t* packed, const MlpPlan& p, const float* viewd
                      const float* emb, int64_t n, float* out, cudaStream_t stream);  // mlp_aux.cu
 bool mlp_use_ts();                                                                    // mlp_aux.cu
 int mlp_variant();                                                                    // mlp_aux.cu
-size_t tq_packed_bytes(int bwd);                                                      // mlp_tq.cu
-int tq_forward(const void* packed, const float* ro, const float* rd, const float* vd, int64_t stride, const float* z,
-               const float* pts, const float* emb, int64_t R, int S, float* raw, void* workspace, void* stash,
-               cudaStream_t stream);
-int tq_backward_data(const void* packed_bwd, const float* g_raw, int64_t P, const void* stash_h, void* stash_g, void* workspace,
-                     cudaStream_t stream);
 size_t ts_packed_bytes(int bwd);                                                      // mlp_ts.cu
 int ts_forward(const void* packed, const float* ro, const float* rd, const float* vd, int64_t stride, const float* z,
                const float* pts, const float* emb, int64_t R, int S, float* raw, void* workspace, void* stash,
@@ -554,8 +548,6 @@ static int run_mlp(const void* packed, int precision, const float* ro, const flo
               "mlp: raw / workspace must be 16-byte aligned");
   GBN_REQUIRE(stash == nullptr || precision == GBN_PRECISION_BF16, "mlp: the training stash exists for bf16 only");
   GBN_REQUIRE((reinterpret_cast<uintptr_t>(stash) & 127) == 0, "mlp: stash must be 128-byte aligned");
-  if (precision == GBN_PRECISION_BF16 && mlp_variant() == 2)
-    return tq_forward(packed, ro, rd, vd, stride, z, pts, emb, R, S, raw, workspace, stash, stream);
   if (precision == GBN_PRECISION_BF16 && mlp_variant() == 1)
     return ts_forward(packed, ro, rd, vd, stride, z, pts, emb, R, S, raw, workspace, stash, stream);
   int rc = ensure_device(stream);
@@ -588,7 +580,6 @@ using namespace gbn;
 
 extern "C" size_t gbn_mlp_packed_bytes(int precision) {
   if (precision < 0 || precision >= kNumPlans) return 0;
-  if (precision != GBN_PRECISION_TF32 && mlp_variant() == 2) return tq_packed_bytes(precision == GBN_PACK_BWD_BF16);
   if (precision != GBN_PRECISION_TF32 && mlp_variant() == 1) return ts_packed_bytes(precision == GBN_PACK_BWD_BF16);
   return mlp_plan(precision).total_bytes;
 }
@@ -646,7 +637,6 @@ extern "C" int gbn_mlp_backward_data(const void* packed_bwd, const float* g_raw,
                   ((reinterpret_cast<uintptr_t>(stash_h) | reinterpret_cast<uintptr_t>(stash_g)) & 127) == 0,
               "mlp_backward_data: misaligned buffer");
   cudaStream_t st = (cudaStream_t)stream;
-  if (mlp_variant() == 2) return tq_backward_data(packed_bwd, g_raw, P, stash_h, stash_g, workspace, st);
   if (mlp_variant() == 1) return ts_backward_data(packed_bwd, g_raw, P, stash_h, stash_g, workspace, st);
   int rc = ensure_device(st);
   if (rc != GBN_OK) return rc;

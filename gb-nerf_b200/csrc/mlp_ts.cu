@@ -42,6 +42,11 @@ __constant__ TsJob c_tsjobs[2][kTsMaxJobs];
 __constant__ TsStep c_tssteps[2][kTsMaxSteps];
 __constant__ TsPackJob c_tspack[2][kTsMaxJobs];
 
+#ifdef GBN_TS_DIAG
+constexpr bool kDiag = true;
+#else
+constexpr bool kDiag = false;
+#endif
 constexpr int kTsThreads = 512;
 constexpr int kTsStageBytes = 32768;
 
@@ -95,6 +100,9 @@ struct TsArgs {
   int order_per_tile;
   int empty1_per_tile;
   int no_split;            // GBNERF_TS_SPLIT=0: K-high jobs wait for both instalments of input half 1 up front
+  int gate_direct;         // diagnostic (GBNERF_TS_GATE_DIRECT=1): dgrad epilogue reads its ReLU gates from global memory
+  unsigned chaos;          // diagnostic (GBNERF_TS_CHAOS=seed): pseudo-random nanosleeps at every hand-over point, to shake
+                           // timing-dependent holes of the barrier protocol out on real hardware (tools/dgrad_hunt.py)
 };
 
 // Post-mortem of a watchdog expiry, in host-mapped memory so that it survives a dead context
@@ -168,6 +176,20 @@ __device__ __forceinline__ void ts_wait_progress(uint32_t addr, uint32_t need, u
       }
     }
   }
+}
+
+// Chaos mode: a warp-uniform pseudo-random delay of 0 .. ~4 us (most calls: none) keyed on the seed, the CTA, the warp
+// and a per-site counter.  Results must not depend on it.
+__device__ __forceinline__ void ts_chaos(unsigned seed, unsigned site) {
+#ifndef GBN_TS_DIAG
+  (void)seed; (void)site;
+  return;      // diagnostics are compiled into libgbnerf_diag.so only (csrc/build.py --diag): the product kernels carry none
+#else
+  if (seed == 0u) return;
+  unsigned h = seed ^ (blockIdx.x * 0x9e3779b9u) ^ ((threadIdx.x >> 5) * 0x85ebca6bu) ^ (site * 0xc2b2ae35u);
+  h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
+  if ((h & 7u) == 0u) __nanosleep((h >> 8) & 0xfffu);
+#endif
 }
 
 __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -255,6 +277,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
     for (int t = 0; t < my_tiles; ++t)
       for (int j = 0; j < a.njobs; ++j) {
         const uint32_t s = cnt % kTsStages, par = (cnt / kTsStages) & 1;
+        ts_chaos(a.chaos, cnt);
         ts_wait(base + L::w_empty + 8 * s, par ^ 1, abort_addr, a.err, 0x10000000 | j);
         const uint32_t bytes = (uint32_t)jobs[j].w_bytes16 * 16;
         const uint8_t* src = a.packed + jobs[j].w_off;
@@ -281,11 +304,15 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
       for (int j = 0; j < a.njobs; ++j) {
         const TsJob jb = nxt;
         nxt = jobs[j + 1 < a.njobs ? j + 1 : 0];   // constant-memory fetch of the next job overlaps this one
+        // (Letting each issuer also wait for the fills of the OTHER issuer's jobs, so that it sees every phase of every
+        // stage, does not work: a warp that reaches such a wait two fills late sees the parity it expects to flip and
+        // blocks until the fill after that, which may be one only it can release.  Tried in round 2: launch failures.)
         if ((jb.d_col >= kTsAcc1) != second) { ++cnt; continue; }
         unsigned long long* tr = (a.trace && blockIdx.x == 0 && t == a.trace_tile && lane == 0) ? a.trace : nullptr;
         if (tr) tr[4 * j] = clock64();
         bool split = false;
         uint32_t split_par = 0, split_bar = 0;
+        ts_chaos(a.chaos, 2u * cnt);
         if (jb.flags & kAnyWait) {
           if (jb.flags & TJ_WAIT_ENC) ts_wait(base + L::enc_full, t & 1, abort_addr, a.err, 0x20000000 | j);
           if (jb.flags & TJ_WAIT_DIR) ts_wait(base + L::dir_full, t & 1, abort_addr, a.err, 0x20800000 | j);
@@ -320,6 +347,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
           ts_wait(base + L::order, seq & 1, abort_addr, a.err, 0x24000000 | j);
         }
         const uint32_t s = cnt % kTsStages, par = (cnt / kTsStages) & 1;
+        ts_chaos(a.chaos, 2u * cnt + 1u);
         if (tr) tr[4 * j + 1] = clock64();
         if ((jb.flags & TJ_PREV_OTHER) && cnt >= (uint32_t)kTsStages)
           ts_wait_progress(base + L::prog + (second ? 0u : 4u), cnt - kTsStages + 1, abort_addr, a.err, 0x26000000 | j);
@@ -343,6 +371,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
             umma_bf16_ts(d, a_t + 40, bd1 + 2, idesc, 1u);
           }
           __syncwarp();
+          ts_chaos(a.chaos, 0x40000000u + cnt);
           ts_wait(split_bar, split_par, abort_addr, a.err, 0x21e00000 | j);
           tc_fence_after_sync();
         }
@@ -397,12 +426,13 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
     // row-strided 16-byte global loads
     if constexpr (BWD) {
       uint32_t mc = 0;
-      for (int t = 0; t < my_tiles; ++t) {
+      for (int t = 0; t < (kDiag && a.gate_direct ? 0 : my_tiles); ++t) {
         const int64_t tile = blockIdx.x + (int64_t)t * gridDim.x;
         for (int si = 0; si < a.nsteps; ++si) {
           const TsStep st = c_tssteps[PROG][si];
           if (st.mode != EPI_MASK) continue;
           const uint32_t b = mc & 1, par = (mc >> 1) & 1;
+          ts_chaos(a.chaos, mc);
           ts_wait(base + L::m_empty + 8 * b, par ^ 1, abort_addr, a.err, 0x60000000 | si);
           if (elect_one()) {
             mbar_expect_tx(base + L::m_full + 8 * b, 2 * kBlkBytes);
@@ -465,6 +495,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
 #pragma unroll
         for (int i = 0; i < 32; ++i) w[i] = pack_bf16(e[2 * i], e[2 * i + 1]);
       }
+      ts_chaos(a.chaos, (unsigned)t);
       if (t > 0) ts_wait(base + L::enc_empty, (t - 1) & 1, abort_addr, a.err, 0x30000000 | t);
       uint8_t* gblk = nullptr;
       if constexpr (BWD) gblk = a.stash_g + (size_t)tile * kStashTileBytes + (size_t)kGRaw * kBlkBytes + row_off;
@@ -531,13 +562,12 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
       const int64_t tile = blockIdx.x + (int64_t)t * gridDim.x;
       const int64_t p = tile * kTileRows + row;
       float sigma_acc = 0.f;
-      uint8_t* const tile_h = a.stash_h != nullptr ? a.stash_h + (size_t)tile * kStashTileBytes + row_off : nullptr;
-      uint8_t* const tile_g = BWD ? a.stash_g + (size_t)tile * kStashTileBytes + row_off : nullptr;
       unsigned long long* tr = (a.trace && blockIdx.x == 0 && t == a.trace_tile && (threadIdx.x & 127) == 0)
                                    ? a.trace + 960 + wg * 128 : nullptr;
       for (int si = 0; si < a.nsteps; ++si) {
         const TsStep st = c_tssteps[PROG][si];
         if (tr) tr[si * 4] = clock64();
+        ts_chaos(a.chaos, (unsigned)(t * 64 + si));
         ts_wait(base + L::acc_full + 8 * st.acc, (accpar >> st.acc) & 1, abort_addr, a.err, 0x40000000 | (si << 8) | wg);
         accpar ^= 1u << st.acc;
         if (tr) tr[si * 4 + 1] = clock64();
@@ -576,7 +606,12 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
         // both 32-channel groups in flight at once: two tcgen05.ld, one wait, then the arithmetic, two tcgen05.st
         uint4 hm[2][4];
         if constexpr (BWD) {
-          if (st.mode == EPI_MASK) {
+          if (kDiag && st.mode == EPI_MASK && a.gate_direct) {
+            const uint4* hg = reinterpret_cast<const uint4*>(a.stash_h + (size_t)tile * kStashTileBytes +
+                                                             (size_t)(st.mask_blk + wg) * kBlkBytes + row_off);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) hm[c >> 2][c & 3] = __ldg(hg + (c ^ (row & 7)));
+          } else if (st.mode == EPI_MASK) {
             const uint32_t b = mc & 1;
             ts_wait(base + L::m_full + 8 * b, (mc >> 1) & 1, abort_addr, a.err, 0x41000000 | (si << 8) | wg);
             const uint32_t hb = base + L::mstage + (b * 2 + wg) * kBlkBytes + row_off;
@@ -644,6 +679,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
           wg_bar(wg);
           if (storer) bulk_s2g(gout, my_ostage, kBlkBytes);
         }
+        ts_chaos(a.chaos, 0x20000000u + (unsigned)(t * 64 + si));
         if (!st.no_act) {
           tmem_st_wait();
           tc_fence_before_sync();
@@ -772,12 +808,11 @@ static int ts_ensure_device(cudaStream_t stream) {
   for (int pr = 0; pr < 2; ++pr) {
     const TsPlan& p = ts_plan(pr);
     GBN_REQUIRE((int)p.jobs.size() <= kTsMaxJobs && (int)p.steps.size() <= kTsMaxSteps, "TS table overflow");
-    GBN_CUDA(cudaMemcpyToSymbolAsync(c_tsjobs, p.jobs.data(), p.jobs.size() * sizeof(TsJob), pr * kTsMaxJobs * sizeof(TsJob),
-                                     cudaMemcpyHostToDevice, stream));
-    GBN_CUDA(cudaMemcpyToSymbolAsync(c_tssteps, p.steps.data(), p.steps.size() * sizeof(TsStep),
-                                     pr * kTsMaxSteps * sizeof(TsStep), cudaMemcpyHostToDevice, stream));
-    GBN_CUDA(cudaMemcpyToSymbolAsync(c_tspack, p.pack.data(), p.pack.size() * sizeof(TsPackJob),
-                                     pr * kTsMaxJobs * sizeof(TsPackJob), cudaMemcpyHostToDevice, stream));
+    GBN_CUDA(cudaMemcpyToSymbol(c_tsjobs, p.jobs.data(), p.jobs.size() * sizeof(TsJob), pr * kTsMaxJobs * sizeof(TsJob), cudaMemcpyHostToDevice));
+    GBN_CUDA(cudaMemcpyToSymbol(c_tssteps, p.steps.data(), p.steps.size() * sizeof(TsStep),
+                                     pr * kTsMaxSteps * sizeof(TsStep), cudaMemcpyHostToDevice));
+    GBN_CUDA(cudaMemcpyToSymbol(c_tspack, p.pack.data(), p.pack.size() * sizeof(TsPackJob),
+                                     pr * kTsMaxJobs * sizeof(TsPackJob), cudaMemcpyHostToDevice));
   }
   if (g_ts_wd_host_ptr == nullptr) {   // watchdog post-mortem record (zero-copy host memory, one per process)
     void* hp = nullptr;
@@ -791,12 +826,19 @@ static int ts_ensure_device(cudaStream_t stream) {
   if (g_ts_wd_host_ptr != nullptr) {
     unsigned int* dp = nullptr;
     GBN_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dp), g_ts_wd_host_ptr, 0));
-    GBN_CUDA(cudaMemcpyToSymbolAsync(g_ts_wd_host, &dp, sizeof(dp), 0, cudaMemcpyHostToDevice, stream));
+    GBN_CUDA(cudaMemcpyToSymbol(g_ts_wd_host, &dp, sizeof(dp), 0, cudaMemcpyHostToDevice));
   }
   GBN_CUDA(cudaFuncSetAttribute(nerf_mlp_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TsSmemT<false>::alloc));
   GBN_CUDA(cudaFuncSetAttribute(nerf_mlp_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TsSmemT<true>::alloc));
   g_ts_init[dev] = true;
   return GBN_OK;
+}
+
+// GBNERF_TS_CHAOS=<seed>: every launch gets a different delay pattern (seed advanced per launch); 0 / unset = off
+static unsigned ts_chaos_seed() {
+  static const unsigned base = [] { const char* e = getenv("GBNERF_TS_CHAOS"); return e ? (unsigned)strtoul(e, nullptr, 0) : 0u; }();
+  static unsigned n = 0;
+  return base ? base + 0x9e3779b9u * (++n) : 0u;
 }
 
 size_t ts_packed_bytes(int bwd) { return ts_plan(bwd).total_bytes; }
@@ -832,6 +874,8 @@ struct TsAdamArgs {
   uint32_t njobs[2];
   uint32_t off_bias[2], off_wdir[2], off_bdir[2];
   float step_size, w1, b2, w2, eps, bc2_sqrt;
+  const float* dev_scalars;   // non-NULL: {step_size, bc2_sqrt} are read from device memory (adam_tick_kernel), so that a
+                              // captured CUDA graph can be replayed step after step
 };
 
 __device__ __forceinline__ void ts_scatter_weight(const TsAdamArgs& a, int layer, int n, int k, float val) {
@@ -870,8 +914,20 @@ __device__ __forceinline__ void ts_scatter_bias(const TsAdamArgs& a, int layer, 
   }
 }
 
+// One thread: step count += 1 and the two step-dependent scalars of torch.optim.Adam, in double as torch takes them on
+// the host (bias_correction1/2 = 1 - beta^step; step_size = lr / bias_correction1).  state[0] = step (double),
+// scalars = {step_size, sqrt(bias_correction2)} (float).
+__global__ void adam_tick_kernel(double* state, const float* lr, double beta1, double beta2, float* scalars) {
+  const double step = state[0] + 1.0;
+  state[0] = step;
+  scalars[0] = (float)((double)lr[0] / (1.0 - pow(beta1, step)));
+  scalars[1] = (float)sqrt(1.0 - pow(beta2, step));
+}
+
 __global__ void __launch_bounds__(256) adam_repack_kernel(const __grid_constant__ TsAdamArgs a) {
   const uint32_t total = a.start[2 * GBN_NUM_LINEAR];
+  const float step_size = a.dev_scalars ? __ldg(a.dev_scalars) : a.step_size;
+  const float bc2_sqrt = a.dev_scalars ? __ldg(a.dev_scalars + 1) : a.bc2_sqrt;
   for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     int lo = 0, hi = 2 * GBN_NUM_LINEAR;   // tensor ti with start[ti] <= e < start[ti+1]
     while (hi - lo > 1) {
@@ -885,8 +941,8 @@ __global__ void __launch_bounds__(256) adam_repack_kernel(const __grid_constant_
     m = m + a.w1 * (g - m);                       // exp_avg.lerp_(grad, 1 - beta1)
     v = v * a.b2;                                 // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value = 1 - beta2)
     v = v + a.w2 * g * g;
-    const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
-    p = p + (-a.step_size) * (m / denom);         // param.addcdiv_(exp_avg, denom, value = -lr / bias_correction1)
+    const float denom = sqrtf(v) / bc2_sqrt + a.eps;
+    p = p + (-step_size) * (m / denom);         // param.addcdiv_(exp_avg, denom, value = -lr / bias_correction1)
     a.m[ti][i] = m; a.v[ti][i] = v; a.p[ti][i] = p;
     const int layer = ti >> 1;
     if (ti & 1) ts_scatter_bias(a, layer, (int)i, p);
@@ -898,8 +954,14 @@ __global__ void __launch_bounds__(256) adam_repack_kernel(const __grid_constant_
   }
 }
 
+int ts_adam_tick(double* state, const float* lr, double beta1, double beta2, float* scalars, cudaStream_t st) {
+  adam_tick_kernel<<<1, 1, 0, st>>>(state, lr, beta1, beta2, scalars);
+  return check_launch("adam_tick_kernel");
+}
+
 int ts_adam_repack(void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq, double lr,
-                   double beta1, double beta2, double eps, int64_t step, void* packed_fwd, void* packed_bwd, cudaStream_t st) {
+                   double beta1, double beta2, double eps, int64_t step, void* packed_fwd, void* packed_bwd, cudaStream_t st,
+                   const float* dev_scalars) {
   int rc = ts_ensure_device(st);
   if (rc != GBN_OK) return rc;
   static const int kIn[GBN_NUM_LINEAR] = {63, 256, 256, 256, 256, 319, 256, 256, 256, 256, 283, 128};
@@ -931,6 +993,7 @@ int ts_adam_repack(void* const* params, const void* const* grads, void* const* e
   a.step_size = (float)(lr / bc1);
   a.w1 = (float)(1.0 - beta1); a.b2 = (float)beta2; a.w2 = (float)(1.0 - beta2);
   a.eps = (float)eps; a.bc2_sqrt = (float)sqrt(bc2);
+  a.dev_scalars = dev_scalars;
   adam_repack_kernel<<<(off + 255) / 256, 256, 0, st>>>(a);
   return check_launch("adam_repack_kernel");
 }
@@ -956,6 +1019,7 @@ int ts_forward(const void* packed, const float* ro, const float* rd, const float
   a.order_per_tile = p.order_per_tile;
   a.empty1_per_tile = p.empty1_per_tile;
   { static const bool ns = [] { const char* e = getenv("GBNERF_TS_SPLIT"); return e && e[0] == '0'; }(); a.no_split = ns; }
+  a.chaos = ts_chaos_seed();
   mlp_get_trace(&a.trace, &a.trace_tile);
   const int64_t ntiles = (a.P + kTileRows - 1) / kTileRows;
   const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
@@ -981,6 +1045,8 @@ int ts_backward_data(const void* packed_bwd, const float* g_raw, int64_t P, cons
   a.order_per_tile = p.order_per_tile;
   a.empty1_per_tile = p.empty1_per_tile;
   { static const bool ns = [] { const char* e = getenv("GBNERF_TS_SPLIT"); return e && e[0] == '0'; }(); a.no_split = ns; }
+  { static const bool gd = [] { const char* e = getenv("GBNERF_TS_GATE_DIRECT"); return e && e[0] == '1'; }(); a.gate_direct = gd; }
+  a.chaos = ts_chaos_seed();
   const int64_t ntiles = (P + kTileRows - 1) / kTileRows;
   const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
   nerf_mlp_ts_kernel<true><<<grid, kTsThreads, TsSmemT<true>::alloc, stream>>>(a);

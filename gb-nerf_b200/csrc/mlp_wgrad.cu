@@ -337,7 +337,7 @@ extern "C" int gbn_mlp_backward_weights(const void* stash_h, const void* stash_g
     if (!g_wg_init[dev]) {
       WgItem items[kWgItems];
       make_items(items, mlp_use_ts());
-      GBN_CUDA(cudaMemcpyToSymbolAsync(c_wg, items, sizeof(items), 0, cudaMemcpyHostToDevice, st));
+      GBN_CUDA(cudaMemcpyToSymbol(c_wg, items, sizeof(items), 0, cudaMemcpyHostToDevice));
       GBN_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WgSmem::alloc));
       g_wg_init[dev] = true;
     }

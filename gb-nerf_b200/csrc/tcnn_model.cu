@@ -656,7 +656,7 @@ int tcnn_ensure_device(cudaStream_t st) {
     off += n;
   }
   GBN_REQUIRE(off == kGridEntries, "hash-grid level table sums to %u entries, expected %u", off, kGridEntries);
-  GBN_CUDA(cudaMemcpyToSymbolAsync(c_levels, lv, sizeof(lv), 0, cudaMemcpyHostToDevice, st));
+  GBN_CUDA(cudaMemcpyToSymbol(c_levels, lv, sizeof(lv), 0, cudaMemcpyHostToDevice));
   GBN_CUDA(cudaStreamSynchronize(st));   // lv is a stack array
   GBN_CUDA(cudaFuncSetAttribute(tcnn_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)((kWeightHalves + kTcWarps * 32 * kTileLd) * 2)));

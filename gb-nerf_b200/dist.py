@@ -61,11 +61,13 @@ class GradBucket:
         self.flat.zero_()
 
     def rebind(self):
-        """Re-attach the views if something replaced ``p.grad`` (e.g. ``zero_grad(set_to_none=True)``)."""
+        """Re-attach the views if something replaced ``p.grad`` (e.g. ``zero_grad(set_to_none=True)``): a replaced
+        gradient is copied into the bucket, a missing one (parameter unused this step) counts as zero."""
         off = 0
         for p in self.params:
             view = self.flat[off:off + p.numel()].view_as(p)
             if p.grad is None:
+                view.zero_()
                 p.grad = view
             elif p.grad.data_ptr() != view.data_ptr():
                 view.copy_(p.grad)
@@ -73,7 +75,11 @@ class GradBucket:
             off += p.numel()
 
     def all_reduce(self, average=False, async_op=False):
-        """SUM over ranks (the per-rank losses are already scaled by 1/R_global)."""
+        """SUM over ranks (the per-rank losses are already scaled by 1/R_global).
+
+        Safe after ``optimizer.zero_grad()`` (which sets grads to None, so that autograd allocates fresh ones outside
+        the bucket): gradients that no longer alias the bucket are copied in and re-attached first."""
+        self.rebind()
         rank, ws = world()
         if ws == 1:
             return None
@@ -88,7 +94,9 @@ class GradBucket:
 def gather_rows(local, total_rows, dst=0):
     """Concatenate per-rank row blocks (sharded by ``shard_bounds``) on rank ``dst``; returns None elsewhere.
 
-    ``dst=None`` gathers on every rank.  Blocks may differ by one row, so they travel padded to the largest.
+    One ``gather`` to ``dst``: only that rank allocates and receives the whole [total_rows, ...] result, every other
+    rank sends its block once (24 B/ray for the image outputs).  ``dst=None`` gathers on every rank
+    (``all_gather``).  Blocks may differ by one row, so they travel padded to the largest.
     """
     rank, ws = world()
     if ws == 1:
@@ -99,11 +107,18 @@ def gather_rows(local, total_rows, dst=0):
     if local.shape[0] < maxn:
         pad = torch.cat([local, local.new_zeros((maxn - local.shape[0],) + tuple(local.shape[1:]))], 0)
     pad = pad.contiguous()
-    bufs = [torch.empty_like(pad) for _ in range(ws)]
-    dist.all_gather(bufs, pad)
+    even = all(hi - lo == maxn for lo, hi in sizes)
     if dst is not None and rank != dst:
+        dist.gather(pad, None, dst=dst)
         return None
-    return torch.cat([b[:hi - lo] for b, (lo, hi) in zip(bufs, sizes)], 0)
+    buf = pad.new_empty((ws, maxn) + tuple(pad.shape[1:]))
+    if dst is None:
+        dist.all_gather(list(buf.unbind(0)), pad)
+    else:
+        dist.gather(pad, list(buf.unbind(0)), dst=dst)
+    if even:
+        return buf.view((ws * maxn,) + tuple(pad.shape[1:]))
+    return torch.cat([buf[r, :hi - lo] for r, (lo, hi) in enumerate(sizes)], 0)
 
 
 def render_sharded(render_fn, rays_flat, gather_keys=("rgb_map", "disp_map", "acc_map", "depth_map"), dst=0, **kw):

@@ -171,9 +171,11 @@ class _Composite(torch.autograd.Function):
         rgb = torch.empty(R, 3, device=dev); disp = torch.empty(R, device=dev); acc = torch.empty(R, device=dev)
         depth = torch.empty(R, device=dev); weights = torch.empty(R, S, device=dev)
         alpha = torch.empty(R, S, device=dev) if need_alpha else None
-        _lib.call("gbn_composite_forward", _ptr(raw), _ptr(z), _ptr(rays_d), pitch, _ptr(noise), R, S,
-                  int(bool(white_bkgd)), _ptr(rgb), _ptr(disp), _ptr(acc), _ptr(depth), _ptr(weights), _ptr(alpha),
-                  _stream())
+        # algorithmic bytes: 24 S + 36 per ray, + 4 S each for noise in / alpha out
+        with _timed_launch(f"composite_fwd_S{S}", R * (24 * S + 36 + 4 * S * ((noise is not None) + bool(need_alpha)))):
+            _lib.call("gbn_composite_forward", _ptr(raw), _ptr(z), _ptr(rays_d), pitch, _ptr(noise), R, S,
+                      int(bool(white_bkgd)), _ptr(rgb), _ptr(disp), _ptr(acc), _ptr(depth), _ptr(weights), _ptr(alpha),
+                      _stream())
         ctx.save_for_backward(raw, z, rays_d, noise if noise is not None else torch.empty(0, device=dev))
         ctx.cfg = (pitch, bool(white_bkgd), bool(detach_weights), noise is not None)
         if alpha is None:
@@ -189,9 +191,12 @@ class _Composite(torch.autograd.Function):
         g_raw = torch.empty_like(raw)
         c = lambda g: g.contiguous().float() if g is not None else None
         g_rgb, g_disp, g_acc, g_weights, g_depth = map(c, (g_rgb, g_disp, g_acc, g_weights, g_depth))
-        _lib.call("gbn_composite_backward", _ptr(raw), _ptr(z), _ptr(rays_d), pitch,
-                  _ptr(noise if has_noise else None), R, S, int(white), int(detach_w), _ptr(g_rgb), _ptr(g_disp),
-                  _ptr(g_acc), _ptr(g_depth), _ptr(g_weights), _ptr(g_raw), _stream())
+        # algorithmic bytes: read raw, z (20 S) [+ noise 4 S] [+ g_weights 4 S] + grads, write g_raw 16 S.  (SURVEY §8d
+        # counts 40 S + 60 with the weights re-read; this kernel recomputes them instead, so 36 S + 60 is what it must move)
+        with _timed_launch(f"composite_bwd_S{S}", R * (36 * S + 60 + 4 * S * (has_noise + (g_weights is not None)))):
+            _lib.call("gbn_composite_backward", _ptr(raw), _ptr(z), _ptr(rays_d), pitch,
+                      _ptr(noise if has_noise else None), R, S, int(white), int(detach_w), _ptr(g_rgb), _ptr(g_disp),
+                      _ptr(g_acc), _ptr(g_depth), _ptr(g_weights), _ptr(g_raw), _stream())
         return g_raw, None, None, None, None, None, None
 
 
@@ -249,8 +254,11 @@ def sample_pdf_merge(z_vals, weights, n_importance, u=None, want_samples=False):
     dev = z_vals.device
     merged = torch.empty(R, S + N, device=dev); std = torch.empty(R, device=dev)
     samples = torch.empty(R, N, device=dev) if want_samples else None
-    _lib.call("gbn_sample_pdf_merge", _ptr(z_vals), _ptr(weights), _ptr(u), R, S, N, _ptr(samples), _ptr(merged),
-              _ptr(std), _stream())
+    # algorithmic bytes (fused with the merge): read z 4 S + weights 4 S (+ u 4 N), write z 4 (S + N) + z_std 4
+    with _timed_launch(f"sample_merge_S{S}_N{N}{'_det' if u is None else ''}",
+                       R * (8 * S + 4 * (S + N) + 4 + (4 * N if u is not None else 0) + (4 * N if want_samples else 0))):
+        _lib.call("gbn_sample_pdf_merge", _ptr(z_vals), _ptr(weights), _ptr(u), R, S, N, _ptr(samples), _ptr(merged),
+                  _ptr(std), _stream())
     return merged, std, samples
 
 

@@ -22,6 +22,19 @@ class FusedAdam(torch.optim.Adam):
             raise NotImplementedError("the reference uses plain Adam (run.py:2065): no weight decay, no amsgrad")
         super().__init__(params, lr=lr, betas=betas, eps=eps, **kw)
         self._plans = None
+        self._lazy_steps = 0      # steps taken by train.TrainStep's graph (device-side counter) not yet in state['step']
+
+    def _flush_lazy(self):
+        """TrainStep advances Adam on the device; fold its step count into the per-tensor ``step`` entries."""
+        n, self._lazy_steps = self._lazy_steps, 0
+        if n:
+            for st in self.state.values():
+                if "step" in st:
+                    st["step"] += n
+
+    def state_dict(self):
+        self._flush_lazy()
+        return super().state_dict()
 
     # -- which NeRF modules are stepped natively ------------------------------------------------------------
     def _build_plans(self):
@@ -69,6 +82,7 @@ class FusedAdam(torch.optim.Adam):
 
     @torch.no_grad()
     def step(self, closure=None):
+        self._flush_lazy()
         loss = None
         if closure is not None:
             with torch.enable_grad():

@@ -152,7 +152,7 @@ int gbn_watchdog_report(unsigned int* out, int words);
 int gbn_debug_ts_plan(int bwd, void* jobs, int max_jobs, void* steps, int max_steps, int* meta);
 
 /* Which bf16 kernel family this process uses (env GBNERF_MLP): 0 = operands in shared memory ("ss"), 1 = activations
- * in tensor memory ("ts", default), 2 = quarter-pipelined experiment ("tq").  The packed weight images differ. */
+ * in tensor memory ("ts", default).  The packed weight images differ. */
 int gbn_mlp_variant(void);
 
 /* ---- optimizer step fused with the weight re-pack: run.py:1529 `optimizer.step()` on the Adam of run.py:2065 --------
@@ -165,6 +165,16 @@ int gbn_mlp_variant(void);
 int gbn_adam_step_repack(void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
                          double lr, double beta1, double beta2, double eps, int64_t step, void* packed_fwd,
                          void* packed_bwd, void* stream);
+
+/* The same step for a captured CUDA graph (replayed once per training step): nothing step-dependent is a kernel
+ * argument.  gbn_adam_tick (one thread) adds 1 to step_state[0] (device double, the 1-based step count) and writes
+ * scalars[0] = lr[0] / (1 - beta1^step), scalars[1] = sqrt(1 - beta2^step) (device floats; lr is a device float the
+ * host refreshes before a replay - run.py:1540-1544 decays it every step).  gbn_adam_step_repack_dev is
+ * gbn_adam_step_repack reading those two scalars from device memory. */
+int gbn_adam_tick(double* step_state, const float* lr, double beta1, double beta2, float* scalars, void* stream);
+int gbn_adam_step_repack_dev(void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
+                             const float* scalars, double beta1, double beta2, double eps, void* packed_fwd,
+                             void* packed_bwd, void* stream);
 
 /* ---- depth -> normal map: depth2normal_geo, run.py:2458-2474 (called at run.py:1440-1443) ---------------------------
  * points [B,3,H,W] (xyz per pixel, depth2xyz_torch's output moved to channel-first as the reference does) ->

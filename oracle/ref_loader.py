@@ -70,6 +70,42 @@ def load(device="cpu"):
     return ns
 
 
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def staged_available() -> bool:
+    return os.path.isfile(os.path.join(STAGED_ROOT, "run_hotpath.py"))
+
+
+def load_staged(device="cpu"):
+    """The same namespace as ``load()``, from the copy ``oracle/make_ref.py`` staged under ``oracle/_ref/`` (the
+    unmodified reference files; present on the GPU box, where ``/root/reference`` is not).  Used by ``bench.py``'s
+    ``--impl reference`` / ``cpu_baseline`` legs (kind "reference")."""
+    import numpy as np
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+
+    if not staged_available():
+        raise FileNotFoundError(f"no staged reference under {STAGED_ROOT} (python oracle/make_ref.py)")
+    for name in ("matplotlib", "matplotlib.pyplot"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    if STAGED_ROOT not in sys.path:
+        sys.path.insert(0, STAGED_ROOT)
+    helpers = importlib.import_module("DS_NeRF.run_nerf_helpers")
+    loss_mod = importlib.import_module("DS_NeRF.loss")
+    ns = {k: getattr(helpers, k) for k in dir(helpers) if not k.startswith("__")}
+    dev = torch.device(device)
+    ns.update(torch=torch, np=np, nn=nn, F=F, os=os, SigmaLoss=loss_mod.SigmaLoss, device=dev, DEBUG=False,
+              device_ids=[dev.index or 0] if dev.type == "cuda" else [])
+    with open(os.path.join(STAGED_ROOT, "run_hotpath.py")) as fh:
+        exec(compile(fh.read(), "run_hotpath.py", "exec"), ns)
+    ns["helpers"] = helpers
+    return ns
+
+
 def default_args(tmpdir, **over):
     """aconfig_1 hot-path values + --no_tcnn."""
     a = types.SimpleNamespace(

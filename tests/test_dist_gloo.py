@@ -41,6 +41,20 @@ def _worker(rank, ws, port, q):
         bucket.rebind()
         assert all(p.grad is not None for p in lin.parameters())
 
+        # the reference loop calls optimizer.zero_grad() (grads -> None): autograd then allocates fresh gradients
+        # OUTSIDE the bucket; all_reduce() must pick them up instead of reducing a stale buffer
+        lin.zero_grad(set_to_none=True)
+        lin(x * 3).sum().backward()
+        assert any(p.grad.data_ptr() < bucket.flat.data_ptr() or
+                   p.grad.data_ptr() >= bucket.flat.data_ptr() + bucket.flat.numel() * 4 for p in lin.parameters())
+        local2 = torch.cat([p.grad.flatten().clone() for p in lin.parameters()])
+        bucket.all_reduce()
+        gathered = [torch.zeros_like(local2) for _ in range(ws)]
+        dist.all_gather(gathered, local2)
+        assert torch.allclose(bucket.flat, sum(gathered))
+        assert all(torch.equal(p.grad.flatten(), bucket.flat[o:o + p.numel()])
+                   for p, o in zip(bucket.params, [0, 35, 42, 63]))
+
         # image gather through render_sharded with a stand-in renderer
         def fake_render(r, **kw):
             return {"rgb_map": r[:, 0:3] * 2, "disp_map": r[:, 3], "acc_map": r[:, 4], "depth_map": r[:, 5]}

@@ -1,0 +1,159 @@
+"""Hunt for the rare nondeterminism of the dgrad program: ONE stash-writing forward, then the dgrad
+launch alone repeated LAUNCHES times (optionally from a cold L2), every G stash compared bit for bit with the first.
+For each launch that differs it reports WHERE (tile, block, rows, channels) and WHAT the wrong block looks like
+(gate-like 0 <-> value flips, or changed values; a least-squares fit of the change against the K-chunks of the
+product says which operand chunk was stale).
+
+usage: dgrad_hunt.py LAUNCHES [R S] [cold|warm|full]   env switches: see DESIGN 6 (GBNERF_TS_*)
+`full` = the sequence of the pytest (tests/test_gpu_mlp_backward.py::test_training_kernels_repeat_...): every repeat
+runs flush, a fresh zeroed stash, the stash-writing forward, flush, dgrad AND wgrad.
+"""
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import gbnerf_b200 as G  # noqa: E402
+from gbnerf_b200 import _lib, ops  # noqa: E402
+from oracle import nerf_oracle as O  # noqa: E402  (diagnostic tool: the oracle only supplies inputs)
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
+R = int(sys.argv[2]) if len(sys.argv) > 3 else 1024
+S = int(sys.argv[3]) if len(sys.argv) > 3 else 128
+MODE = sys.argv[4] if len(sys.argv) > 4 else "cold"
+COLD, FULL = MODE != "warm", MODE == "full"
+P = R * S
+T = (P + 127) // 128
+NB = 40
+dev = torch.device("cuda:0")
+torch.manual_seed(11)
+net = G.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True, precision="bf16").to(dev)
+net.load_state_dict(O.init_params(11))
+rays = O.synthetic_rays(R, seed=3).to(dev)
+z = O.stratified_z(rays[:, 6:7].cpu(), rays[:, 7:8].cpu(), S, True,
+                   torch.rand(R, S, generator=torch.Generator().manual_seed(2))).to(dev)
+g_raw = torch.randn(P, 4, generator=torch.Generator().manual_seed(4)).to(dev)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+stash_h = ops._stash(P, dev).zero_()
+raw, ws = ops.mlp_forward_raw(net.packed_weights(), "bf16", rays[:, 8:11], R, S, rays_o=rays[:, 0:3], rays_d=rays[:, 3:6],
+                              z=z, stash=stash_h)
+assert ops.mlp_error_code(ws) == 0
+packed_bwd = net.packed_weights_bwd()
+wsb = torch.zeros(512, device=dev, dtype=torch.uint8)
+stream = torch.cuda.current_stream().cuda_stream
+
+
+def dgrad(out):
+    _lib.call("gbn_mlp_backward_data", packed_bwd.data_ptr(), g_raw.data_ptr(), P, stash_h.data_ptr(), out.data_ptr(),
+              wsb.data_ptr(), stream)
+
+
+def unswizzle(blk):
+    """uint8 [16384] block image -> float [128 rows, 64 channels]"""
+    x = blk.view(torch.bfloat16).view(128, 8, 8)
+    r = torch.arange(128, device=blk.device)[:, None]
+    c = torch.arange(8, device=blk.device)[None, :]
+    return torch.gather(x, 1, (c ^ (r & 7))[:, :, None].expand(128, 8, 8)).reshape(128, 64).float()
+
+
+def tile_rows(stash, tile, blk0, nblk):
+    v = stash.view(T, NB, 16384)
+    return torch.cat([unswizzle(v[tile, blk0 + i]) for i in range(nblk)], 1)
+
+
+ref = ops._stash(P, dev).zero_()
+dgrad(ref)
+torch.cuda.synchronize()
+print(f"# dgrad_hunt: {N} launches, R={R} S={S} ({T} tiles, {T / 148:.1f} per CTA), {'cold' if COLD else 'warm'} L2, "
+      f"env {{{', '.join(f'{k}={v}' for k, v in sorted(os.environ.items()) if k.startswith('GBNERF'))}}}", flush=True)
+print("first launch watchdog word", hex(ops.mlp_error_code(wsb)), flush=True)
+refv = ref.view(T, NB, 16384)[:, :39]
+out = ops._stash(P, dev).zero_()
+outv = out.view(T, NB, 16384)[:, :39]
+Wf = net.feature_linear.weight.detach().bfloat16().float()      # [256 feature, 256 h7]
+wa = net.alpha_linear.weight.detach().bfloat16().float()[0]     # [256]
+
+
+def forensics(tile, blocks):
+    """blocks: differing block ids of this tile (sorted)"""
+    top = [b for b in blocks if b >= 34 and b <= 37]
+    early = [b for b in blocks if b < 6]
+    msg = f"   tile {tile} = CTA {tile % 148} local tile {tile // 148}: blocks {blocks}"
+    if early:
+        msg += f"  (!! g_hv/g_feature blocks differ: {early})"
+    print(msg)
+    for b in (top or blocks[-1:]):
+        good, bad = unswizzle(refv[tile, b]), unswizzle(outv[tile, b])
+        d = good != bad
+        rws, chs = d.any(1).nonzero().flatten(), d.any(0).nonzero().flatten()
+        z2v = int(((good == 0) & (bad != 0)).sum()); v2z = int(((good != 0) & (bad == 0)).sum())
+        vv = int(((good != 0) & (bad != 0) & d).sum())
+        print(f"   block {b}: {int(d.sum())} of 8192 elements differ; rows {rws.min().item()}..{rws.max().item()} "
+              f"({rws.numel()} rows), channels {chs.min().item()}..{chs.max().item()} ({chs.numel()}); "
+              f"0->value {z2v}, value->0 {v2z}, value->value {vv}; max|good| {good.abs().max():.3e} max|bad| {bad.abs().max():.3e}")
+        by_warp = [int(d[32 * w:32 * w + 32].sum()) for w in range(4)]
+        by_chunk = [int(d[:, 8 * c:8 * c + 8].sum()) for c in range(8)]
+        print(f"   differing elements by 32-row group {by_warp}, by 8-channel chunk {by_chunk}")
+        if 34 <= b <= 37:
+            # g_h7[:, n] = gate_h7 * (g_feature W_f[:, n] + g_sigma w_alpha[n]): which 16-wide K chunk changed?
+            n0 = 64 * (b - 34)
+            gf = tile_rows(ref, tile, 2, 4)                          # [128, 256] g_feature (bit-stable blocks)
+            gs = g_raw[tile * 128:tile * 128 + 128, 3].bfloat16().float()
+            gate = (tile_rows(stash_h, tile, 28, 4)[:, n0:n0 + 64] != 0).float()
+            terms = [gf[:, 16 * i:16 * i + 16] @ Wf[16 * i:16 * i + 16, n0:n0 + 64] for i in range(16)]
+            terms.append(gs[:, None] * wa[None, n0:n0 + 64])
+            full = sum(terms)
+            print(f"   check: |good - gate*full| max {(good - gate * full).abs().max():.3e} (bf16 rounding expected ~1e-2 rel)")
+            m = d & (gate != 0)
+            if int(m.sum()) > 20:
+                A = torch.stack([t[m] for t in terms], 1)           # [n, 17]
+                y = (bad - good)[m][:, None]
+                coef = torch.linalg.lstsq(A, y).solution.flatten()
+                print("   lstsq coefficients of (bad-good) on the 16 K-chunks + alpha term (-1 = chunk missing/stale):")
+                print("   " + " ".join(f"{c:+.2f}" for c in coef.tolist()))
+            gate_bad = (bad != 0).float()
+            print(f"   gate mismatch (bad zero pattern vs h7 gate): {int((gate_bad != gate).sum())} elements; "
+                  f"good vs gate {int(((good != 0).float() != gate).sum())}")
+            for other in range(0, 38, 2):
+                if other == 28 + 2 * ((b - 34) // 2):
+                    continue
+                og = (unswizzle(stash_h.view(T, NB, 16384)[tile, other + ((b - 34) & 1)]) != 0).float()
+                mism = int((gate_bad != og).sum())
+                if mism < 200:
+                    print(f"   !! bad block's zero pattern matches H block {other + ((b - 34) & 1)} ({mism} mismatches)")
+
+
+shapes = [tuple(t.shape) for t in net.param_list()]
+h_ref = stash_h.clone() if FULL else None
+bad_launches = 0
+t0 = time.time()
+for it in range(N):
+    if FULL:
+        flush.zero_()
+        stash_h = ops._stash(P, dev).zero_()
+        raw2, ws = ops.mlp_forward_raw(net.packed_weights(), "bf16", rays[:, 8:11], R, S, rays_o=rays[:, 0:3],
+                                       rays_d=rays[:, 3:6], z=z, stash=stash_h)
+        flush.zero_()
+        grads, wsb, out = ops.mlp_backward_raw(packed_bwd, g_raw, stash_h, rays[:, 8:11], R, S, shapes)
+        outv = out.view(T, NB, 16384)[:, :39]
+        if not torch.equal(raw2, raw) or not torch.equal(stash_h, h_ref):
+            print(f"launch {it}: FORWARD differs (raw {torch.equal(raw2, raw)}, H stash {torch.equal(stash_h, h_ref)})", flush=True)
+    else:
+        if COLD:
+            flush.zero_()
+        dgrad(out)
+    same = torch.equal(outv, refv)
+    e = ops.mlp_error_code(wsb)
+    if not same or e:
+        bad_launches += 1
+        blk = (outv != refv).any(-1).nonzero().tolist()
+        tiles = sorted(set(t for t, _ in blk))
+        print(f"launch {it}: {len(blk)} blocks differ in tiles {tiles[:8]}; watchdog {hex(e)}", flush=True)
+        if bad_launches <= 6:
+            for t in tiles[:3]:
+                forensics(t, sorted(b for tt, b in blk if tt == t))
+        sys.stdout.flush()
+print(f"RESULT {bad_launches} of {N} launches differed ({time.time() - t0:.1f} s)", flush=True)
