@@ -518,8 +518,16 @@ def cpu_render(n_rays, threads=None):
             ns = ref_loader.load_staged("cpu")
             torch.manual_seed(0)
             import contextlib, io
-            with contextlib.redirect_stdout(io.StringIO()):       # create_nerf prints ("Found ckpts", "Not ndc!")
-                _, kw_test, *_ = ns["create_nerf"](ref_loader.default_args(tempfile.mkdtemp()))
+            # The reference wraps its models in nn.DataParallel(device_ids=device_ids) (run.py:2020,2056); with an empty
+            # device list that is a pass-through only when torch sees no accelerator, so CUDA is hidden from that one
+            # constructor call - the reference code itself is untouched and everything runs on the host cores.
+            real = torch.cuda.is_available
+            torch.cuda.is_available = lambda: False
+            try:
+                with contextlib.redirect_stdout(io.StringIO()):   # create_nerf prints ("Found ckpts", "Not ndc!")
+                    _, kw_test, *_ = ns["create_nerf"](ref_loader.default_args(tempfile.mkdtemp()))
+            finally:
+                torch.cuda.is_available = real
             kw_test.update(near=NEAR, far=FAR)
             _REF["ns"], _REF["kw"] = ns, kw_test
         ns, kw = _REF["ns"], _REF["kw"]

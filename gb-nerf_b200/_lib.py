@@ -29,6 +29,7 @@ SIGNATURES = {
     "gbn_sample_pdf": (_i, [_p, _p, _p, _i64, _i, _i, _p, _p]),
     "gbn_searchsorted_right": (_i, [_p, _p, _i64, _i, _i, _p, _p]),
     "gbn_sample_pdf_merge": (_i, [_p, _p, _p, _i64, _i, _i, _p, _p, _p, _p]),
+    "gbn_sample_pdf_merge_ex": (_i, [_p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p, _p]),
     "gbn_mlp_packed_bytes": (_sz, [_i]),
     "gbn_mlp_prepack_weights": (_i, [C.POINTER(_p), _p, _i, _p]),
     "gbn_mlp_workspace_bytes": (_sz, [_i64]),

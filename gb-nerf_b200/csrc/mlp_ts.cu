@@ -101,6 +101,11 @@ struct TsArgs {
   int empty1_per_tile;
   int no_split;            // GBNERF_TS_SPLIT=0: K-high jobs wait for both instalments of input half 1 up front
   int gate_direct;         // diagnostic (GBNERF_TS_GATE_DIRECT=1): dgrad epilogue reads its ReLU gates from global memory
+  unsigned long long* dbg; // diagnostic: gate-check event log (dgrad; the buffer of gbn_mlp_set_trace), see the epilogue
+  unsigned chaos_roles;    // diagnostic: which roles get chaos delays (bit 0 weight producer, 1 issuers, 2 gate producer,
+                           // 3 input warps, 4 epilogue before acc_full, 5 epilogue before the hand-over arrival)
+  unsigned fix;            // diagnostic (GBNERF_TS_FIX): candidate fixes, bit 0: fence.proxy.async before the m_empty
+                           // arrival, bit 1: consume the gate registers before that arrival
   unsigned chaos;          // diagnostic (GBNERF_TS_CHAOS=seed): pseudo-random nanosleeps at every hand-over point, to shake
                            // timing-dependent holes of the barrier protocol out on real hardware (tools/dgrad_hunt.py)
 };
@@ -180,12 +185,12 @@ __device__ __forceinline__ void ts_wait_progress(uint32_t addr, uint32_t need, u
 
 // Chaos mode: a warp-uniform pseudo-random delay of 0 .. ~4 us (most calls: none) keyed on the seed, the CTA, the warp
 // and a per-site counter.  Results must not depend on it.
-__device__ __forceinline__ void ts_chaos(unsigned seed, unsigned site) {
+__device__ __forceinline__ void ts_chaos(unsigned seed, unsigned site, bool role_on = true) {
 #ifndef GBN_TS_DIAG
-  (void)seed; (void)site;
+  (void)seed; (void)site; (void)role_on;
   return;      // diagnostics are compiled into libgbnerf_diag.so only (csrc/build.py --diag): the product kernels carry none
 #else
-  if (seed == 0u) return;
+  if (seed == 0u || !role_on) return;
   unsigned h = seed ^ (blockIdx.x * 0x9e3779b9u) ^ ((threadIdx.x >> 5) * 0x85ebca6bu) ^ (site * 0xc2b2ae35u);
   h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
   if ((h & 7u) == 0u) __nanosleep((h >> 8) & 0xfffu);
@@ -277,7 +282,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
     for (int t = 0; t < my_tiles; ++t)
       for (int j = 0; j < a.njobs; ++j) {
         const uint32_t s = cnt % kTsStages, par = (cnt / kTsStages) & 1;
-        ts_chaos(a.chaos, cnt);
+        ts_chaos(a.chaos, cnt, a.chaos_roles & 1u);
         ts_wait(base + L::w_empty + 8 * s, par ^ 1, abort_addr, a.err, 0x10000000 | j);
         const uint32_t bytes = (uint32_t)jobs[j].w_bytes16 * 16;
         const uint8_t* src = a.packed + jobs[j].w_off;
@@ -312,7 +317,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
         if (tr) tr[4 * j] = clock64();
         bool split = false;
         uint32_t split_par = 0, split_bar = 0;
-        ts_chaos(a.chaos, 2u * cnt);
+        ts_chaos(a.chaos, 2u * cnt, a.chaos_roles & 2u);
         if (jb.flags & kAnyWait) {
           if (jb.flags & TJ_WAIT_ENC) ts_wait(base + L::enc_full, t & 1, abort_addr, a.err, 0x20000000 | j);
           if (jb.flags & TJ_WAIT_DIR) ts_wait(base + L::dir_full, t & 1, abort_addr, a.err, 0x20800000 | j);
@@ -347,7 +352,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
           ts_wait(base + L::order, seq & 1, abort_addr, a.err, 0x24000000 | j);
         }
         const uint32_t s = cnt % kTsStages, par = (cnt / kTsStages) & 1;
-        ts_chaos(a.chaos, 2u * cnt + 1u);
+        ts_chaos(a.chaos, 2u * cnt + 1u, a.chaos_roles & 2u);
         if (tr) tr[4 * j + 1] = clock64();
         if ((jb.flags & TJ_PREV_OTHER) && cnt >= (uint32_t)kTsStages)
           ts_wait_progress(base + L::prog + (second ? 0u : 4u), cnt - kTsStages + 1, abort_addr, a.err, 0x26000000 | j);
@@ -371,7 +376,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
             umma_bf16_ts(d, a_t + 40, bd1 + 2, idesc, 1u);
           }
           __syncwarp();
-          ts_chaos(a.chaos, 0x40000000u + cnt);
+          ts_chaos(a.chaos, 0x40000000u + cnt, a.chaos_roles & 2u);
           ts_wait(split_bar, split_par, abort_addr, a.err, 0x21e00000 | j);
           tc_fence_after_sync();
         }
@@ -432,8 +437,13 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
           const TsStep st = c_tssteps[PROG][si];
           if (st.mode != EPI_MASK) continue;
           const uint32_t b = mc & 1, par = (mc >> 1) & 1;
-          ts_chaos(a.chaos, mc);
+          ts_chaos(a.chaos, mc, a.chaos_roles & 4u);
           ts_wait(base + L::m_empty + 8 * b, par ^ 1, abort_addr, a.err, 0x60000000 | si);
+          if (kDiag && (a.fix & 8u)) fence_proxy_async_smem();
+#ifdef GBN_TS_DIAG
+          if (a.dbg != nullptr && (a.fix & 16u) && blockIdx.x < 16 && mc < 128 && lane == 0)
+            a.dbg[32768 + blockIdx.x * 128 + mc] = clock64();          // clock at which fill `mc` is issued
+#endif
           if (elect_one()) {
             mbar_expect_tx(base + L::m_full + 8 * b, 2 * kBlkBytes);
             tma_bulk_g2s(base + L::mstage + b * 2 * kBlkBytes,
@@ -495,7 +505,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
 #pragma unroll
         for (int i = 0; i < 32; ++i) w[i] = pack_bf16(e[2 * i], e[2 * i + 1]);
       }
-      ts_chaos(a.chaos, (unsigned)t);
+      ts_chaos(a.chaos, (unsigned)t, a.chaos_roles & 8u);
       if (t > 0) ts_wait(base + L::enc_empty, (t - 1) & 1, abort_addr, a.err, 0x30000000 | t);
       uint8_t* gblk = nullptr;
       if constexpr (BWD) gblk = a.stash_g + (size_t)tile * kStashTileBytes + (size_t)kGRaw * kBlkBytes + row_off;
@@ -567,7 +577,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
       for (int si = 0; si < a.nsteps; ++si) {
         const TsStep st = c_tssteps[PROG][si];
         if (tr) tr[si * 4] = clock64();
-        ts_chaos(a.chaos, (unsigned)(t * 64 + si));
+        ts_chaos(a.chaos, (unsigned)(t * 64 + si), a.chaos_roles & 16u);
         ts_wait(base + L::acc_full + 8 * st.acc, (accpar >> st.acc) & 1, abort_addr, a.err, 0x40000000 | (si << 8) | wg);
         accpar ^= 1u << st.acc;
         if (tr) tr[si * 4 + 1] = clock64();
@@ -617,7 +627,77 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
             const uint32_t hb = base + L::mstage + (b * 2 + wg) * kBlkBytes + row_off;
 #pragma unroll
             for (int c = 0; c < 8; ++c) hm[c >> 2][c & 3] = ld_smem16(hb + ((uint32_t)(c ^ (row & 7)) << 4));
+#ifdef GBN_TS_DIAG
+            if (a.fix & 2u) {
+#pragma unroll
+              for (int c = 0; c < 8; ++c) asm volatile("" ::"r"(hm[c >> 2][c & 3].x), "r"(hm[c >> 2][c & 3].w) : "memory");
+            }
+            if (a.fix & 4u) __nanosleep(200);
+            if (a.dbg != nullptr && (a.fix & 16u) && blockIdx.x < 16 && mc < 128 && lane == 0)
+              a.dbg[65536 + (blockIdx.x * 128 + mc) * 8 + (warp - 8)] = clock64();   // clock of this warp's m_empty arrival
+#endif
+            // The staging buffer was written by the async proxy (bulk copy) and has just been read through the generic
+            // proxy; the arrival below hands it back to the gate producer, whose next bulk copy overwrites it.  An
+            // mbarrier hand-over alone does not order generic-proxy READS before later async-proxy WRITES: without this
+            // proxy fence the next fill (two EPI_MASK steps ahead) was observed landing in the last chunks a warp read -
+            // the "one 64-channel block of g_h7" nondeterminism of round 1 (reproduced at 0.3-23 % of launches
+            // with tools/chaos_hunt*.sh, 0 of 10,500 with the fence; a plain delay before the arrival does not close it).
+            if (!kDiag || !(a.fix & 32u)) fence_proxy_async_smem();
             mbar_arrive(base + L::m_empty + 8 * b);
+#ifdef GBN_TS_DIAG
+            if (a.dbg != nullptr && !(a.fix & 16u)) {
+              // gate check: the same 128 bytes straight from the H stash; on a mismatch log where, when, and whether the
+              // wrong chunk equals the gates of the NEXT fill of this staging buffer (two EPI_MASK steps ahead) or of the
+              // PREVIOUS one.  Record: [tile, si | warp << 8 | lane << 16, mc, chunk mask | next << 8 | prev << 16, clock]
+              const uint4* hg = reinterpret_cast<const uint4*>(a.stash_h + (size_t)tile * kStashTileBytes +
+                                                               (size_t)(st.mask_blk + wg) * kBlkBytes + row_off);
+              unsigned bad = 0;
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const uint4 g = __ldg(hg + (c ^ (row & 7))), h = hm[c >> 2][c & 3];
+                if (g.x != h.x || g.y != h.y || g.z != h.z || g.w != h.w) bad |= 1u << c;
+              }
+              if (bad) {
+                int seen = 0, nsi = si, blk_next = -1, blk_prev = -1;
+                int64_t tile_next = tile, tile_prev = tile;
+                for (int k = 0; k < 2 * a.nsteps && seen < 2; ++k) {      // second EPI_MASK step after this one
+                  if (++nsi == a.nsteps) { nsi = 0; tile_next += gridDim.x; }
+                  if (c_tssteps[PROG][nsi].mode == EPI_MASK) { ++seen; blk_next = c_tssteps[PROG][nsi].mask_blk; }
+                }
+                seen = 0; nsi = si;
+                for (int k = 0; k < 2 * a.nsteps && seen < 2; ++k) {      // second EPI_MASK step before this one
+                  if (--nsi < 0) { nsi = a.nsteps - 1; tile_prev -= gridDim.x; }
+                  if (c_tssteps[PROG][nsi].mode == EPI_MASK) { ++seen; blk_prev = c_tssteps[PROG][nsi].mask_blk; }
+                }
+                unsigned eq_next = 0, eq_prev = 0;
+                const int64_t ntiles_all = (a.P + kTileRows - 1) / kTileRows;
+                for (int c = 0; c < 8; ++c) {
+                  if (!((bad >> c) & 1u)) continue;
+                  const uint4 h = hm[c >> 2][c & 3];
+                  if (tile_next < ntiles_all) {
+                    const uint4 g = __ldg(reinterpret_cast<const uint4*>(a.stash_h + (size_t)tile_next * kStashTileBytes +
+                                                                       (size_t)(blk_next + wg) * kBlkBytes + row_off) + (c ^ (row & 7)));
+                    if (g.x == h.x && g.y == h.y && g.z == h.z && g.w == h.w) eq_next |= 1u << c;
+                  }
+                  if (tile_prev >= 0) {
+                    const uint4 g = __ldg(reinterpret_cast<const uint4*>(a.stash_h + (size_t)tile_prev * kStashTileBytes +
+                                                                       (size_t)(blk_prev + wg) * kBlkBytes + row_off) + (c ^ (row & 7)));
+                    if (g.x == h.x && g.y == h.y && g.z == h.z && g.w == h.w) eq_prev |= 1u << c;
+                  }
+                }
+                const unsigned long long slot = atomicAdd(a.dbg, 1ull);
+                if (slot < 2000) {
+                  unsigned long long* r = a.dbg + 8 + slot * 8;
+                  r[0] = (unsigned long long)tile; r[1] = (unsigned)si | ((unsigned)warp << 8) | ((unsigned)lane << 16);
+                  r[2] = mc; r[3] = bad | (eq_next << 8) | (eq_prev << 16); r[4] = clock64();
+                  unsigned long long w0, w1;
+                  asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(w0) : "r"(base + L::m_full + 8 * b));
+                  asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(w1) : "r"(base + L::m_empty + 8 * b));
+                  r[5] = w0; r[6] = w1; r[7] = blockIdx.x;
+                }
+              }
+            }
+#endif
             ++mc;
           }
         }
@@ -679,7 +759,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
           wg_bar(wg);
           if (storer) bulk_s2g(gout, my_ostage, kBlkBytes);
         }
-        ts_chaos(a.chaos, 0x20000000u + (unsigned)(t * 64 + si));
+        ts_chaos(a.chaos, 0x20000000u + (unsigned)(t * 64 + si), a.chaos_roles & 32u);
         if (!st.no_act) {
           tmem_st_wait();
           tc_fence_before_sync();
@@ -1020,6 +1100,7 @@ int ts_forward(const void* packed, const float* ro, const float* rd, const float
   a.empty1_per_tile = p.empty1_per_tile;
   { static const bool ns = [] { const char* e = getenv("GBNERF_TS_SPLIT"); return e && e[0] == '0'; }(); a.no_split = ns; }
   a.chaos = ts_chaos_seed();
+  a.chaos_roles = 0xffu;
   mlp_get_trace(&a.trace, &a.trace_tile);
   const int64_t ntiles = (a.P + kTileRows - 1) / kTileRows;
   const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
@@ -1047,6 +1128,9 @@ int ts_backward_data(const void* packed_bwd, const float* g_raw, int64_t P, cons
   { static const bool ns = [] { const char* e = getenv("GBNERF_TS_SPLIT"); return e && e[0] == '0'; }(); a.no_split = ns; }
   { static const bool gd = [] { const char* e = getenv("GBNERF_TS_GATE_DIRECT"); return e && e[0] == '1'; }(); a.gate_direct = gd; }
   a.chaos = ts_chaos_seed();
+  { static const unsigned r = [] { const char* e = getenv("GBNERF_TS_CHAOS_ROLES"); return e ? (unsigned)strtoul(e, nullptr, 0) : 0xffu; }(); a.chaos_roles = r; }
+  { static const unsigned f = [] { const char* e = getenv("GBNERF_TS_FIX"); return e ? (unsigned)strtoul(e, nullptr, 0) : 0u; }(); a.fix = f; }
+  { int tt = 0; mlp_get_trace(&a.dbg, &tt); }
   const int64_t ntiles = (P + kTileRows - 1) / kTileRows;
   const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
   nerf_mlp_ts_kernel<true><<<grid, kTsThreads, TsSmemT<true>::alloc, stream>>>(a);

@@ -186,6 +186,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgArgs a)
           s1 += __uint_as_float(v & 0xffff0000u);
         }
       }
+      // generic-proxy reads of a bulk-copied stage, then the stage goes back to the bulk-copy producer: proxy fence
+      // first (same rule as the gate staging of mlp_ts.cu; an mbarrier hand-over does not order them by itself)
+      fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(base + L::empty + 8 * s);
     }

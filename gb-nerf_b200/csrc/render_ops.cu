@@ -412,10 +412,11 @@ __device__ __forceinline__ void warp_bitonic_sort(float* a, int n, int lane) {
 // and ranked by binary search instead.
 __global__ void __launch_bounds__(kThreads) sample_merge_kernel(const float* __restrict__ z_vals,
                                                                 const float* __restrict__ weights,
-                                                                const float* __restrict__ u, int64_t R, int S, int N,
+                                                                const float* __restrict__ u, const float* __restrict__ cdf_in,
+                                                                int64_t R, int S, int N,
                                                                 int Npad, float* __restrict__ z_samples,
                                                                 float* __restrict__ z_merged,
-                                                                float* __restrict__ z_std) {
+                                                                float* __restrict__ z_std, int* __restrict__ inds_out) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int per_warp = 5 * S + Npad + N + 1;
@@ -432,7 +433,8 @@ __global__ void __launch_bounds__(kThreads) sample_merge_kernel(const float* __r
     if (u == nullptr) for (int j = lane; j <= S; j += 32) hist[j] = 0;
     __syncwarp();
     for (int j = lane; j < B; j += 32) bn[j] = __fmul_rn(.5f, __fadd_rn(zv[j + 1], zv[j]));
-    warp_build_cdf(weights + ray * S + 1, S - 2, cdf, lane);
+    if (cdf_in != nullptr) { for (int j = lane; j < B; j += 32) cdf[j] = __ldg(cdf_in + ray * B + j); }
+    else warp_build_cdf(weights + ray * S + 1, S - 2, cdf, lane);
     __syncwarp();
     float sum = 0.f;
     for (int n = lane; n < Npad; n += 32) {
@@ -443,6 +445,7 @@ __global__ void __launch_bounds__(kThreads) sample_merge_kernel(const float* __r
         v = invert_one(cdf, bn, B, uu, &lo);
         sum += v;
         if (z_samples) st_stream(z_samples + ray * N + n, v);
+        if (inds_out) inds_out[ray * N + n] = upper_bound_s(cdf, B, uu);
         if (u == nullptr) {
           const int c = lo + 1 + (zv[lo + 1] <= v ? 1 : 0);
           mrg[n + c] = v;
@@ -483,10 +486,6 @@ __global__ void __launch_bounds__(kThreads) sample_merge_kernel(const float* __r
   }
 }
 
-// ---- the same kernel for the shapes the render path uses (S = 32 KS, N = 32 KN): everything a lane owns lives in
-// registers (element lane + 32 k), all loops unroll, searches are fixed-depth and branch-free, the random-u sort is a
-// register bitonic network over shuffles.  Same arithmetic, element for element, as sample_merge_kernel above (the
-// generic kernel took 1013 warp instructions per 64+64 ray, 74 % issue-bound; see profiles/).
 template <int STEPS, bool UPPER>   // #{j < n : a[j] <= v} (UPPER) or #{j < n : a[j] < v}, n < 2^STEPS... n <= 2^STEPS - 1 + 1
 __device__ __forceinline__ int count_below(const float* a, int n, float v) {
   int lo = 0;
@@ -500,19 +499,33 @@ __device__ __forceinline__ int count_below(const float* a, int n, float v) {
   return lo;
 }
 
-template <int KN>
-__device__ __forceinline__ void warp_bitonic_sort_regs(float (&v)[KN], int lane) {
-  constexpr int N = 32 * KN;
+
+// ---- sample + merge with CONSECUTIVE ownership (the render path's shapes) ---------------------------------------------
+// S = 4 LANES coarse depths and N = KN LANES new samples per ray, LANES = 8, 16 (four / two rays per warp) or 32.  A lane owns
+// four consecutive depths / weights / cdf entries (one 16-byte load each) and KN consecutive samples, so
+//   * the cdf is an in-lane prefix + ONE LANES-wide shuffle scan of (w + 1e-5), scaled by one reciprocal of the total
+//     (the generic kernels divide every bin by the total and scan 32-strided chunks);
+//   * bins, the rank histogram of the deterministic merge and the merged row are vector accesses;
+//   * with 64 coarse samples the two half-warps share every shuffle / scan instruction (cf. composite_fwd_pair64_kernel);
+//   * the interpolation uses one fast reciprocal per sample (the reference's IEEE division costs ~10 instructions; the
+//     value tolerance of the path is 2e-5 relative, the bin INDEX is exact either way: it comes from the search alone).
+// Searches are the same fixed-depth upper-bound walks as in sample_merge_fast_kernel; `inds_out` returns their result
+// (= torch.searchsorted(cdf, u, right=True), helpers:333) and `cdf_in` replaces the cdf built from the weights, which
+// together let the test assert bit-exact indices on this kernel given the same cdf and uniforms.
+// 125-190 warp instructions per ray against 465 for sample_merge_fast_kernel<2,2> (profiles/).
+template <int LANES, int KN>
+__device__ __forceinline__ void seg_bitonic_sort(float (&v)[KN], int l) {
+  constexpr int N = LANES * KN;
 #pragma unroll
   for (int kk = 2; kk <= N; kk <<= 1) {
 #pragma unroll
     for (int j = kk >> 1; j > 0; j >>= 1) {
-      if (j >= 32) {                       // partner lives in the same lane
+      if (j < KN) {                          // partner element lives in the same lane
 #pragma unroll
         for (int k = 0; k < KN; ++k) {
-          const int k2 = k ^ (j >> 5);
+          const int k2 = k ^ j;
           if (k2 > k) {
-            const bool up = ((32 * k) & kk) == 0;   // kk > j >= 32: decided by k alone
+            const bool up = ((l * KN + k) & kk) == 0;
             const float x = v[k], y = v[k2];
             const bool sw = (x > y) == up;
             v[k] = sw ? y : x;
@@ -522,9 +535,9 @@ __device__ __forceinline__ void warp_bitonic_sort_regs(float (&v)[KN], int lane)
       } else {
 #pragma unroll
         for (int k = 0; k < KN; ++k) {
-          const float y = __shfl_xor_sync(kFullMask, v[k], j);
-          const bool lower = (lane & j) == 0;
-          const bool up = (((lane + 32 * k) & kk) == 0);
+          const float y = __shfl_xor_sync(kFullMask, v[k], j / KN);
+          const bool lower = (l & (j / KN)) == 0;
+          const bool up = ((l * KN + k) & kk) == 0;
           v[k] = (lower == up) ? fminf(v[k], y) : fmaxf(v[k], y);
         }
       }
@@ -532,128 +545,181 @@ __device__ __forceinline__ void warp_bitonic_sort_regs(float (&v)[KN], int lane)
   }
 }
 
-template <int KS, int KN, bool DET>
-__global__ void __launch_bounds__(kThreads) sample_merge_fast_kernel(const float* __restrict__ z_vals,
+template <int LANES, int KN, bool DET>
+__global__ void __launch_bounds__(kThreads) sample_merge_cons_kernel(const float* __restrict__ z_vals,
                                                                      const float* __restrict__ weights,
-                                                                     const float* __restrict__ u, int64_t R,
-                                                                     float* __restrict__ z_samples, float* __restrict__ z_merged,
-                                                                     float* __restrict__ z_std) {
-  constexpr int S = 32 * KS, N = 32 * KN, B = S - 1, M = S - 2;
-  constexpr int LOGS = KS == 1 ? 5 : (KS == 2 ? 6 : (KS <= 4 ? 7 : 8));          // B < 2^LOGS
-  constexpr int LOGN1 = KN == 1 ? 6 : (KN == 2 ? 7 : (KN <= 4 ? 8 : 9));         // N < 2^LOGN1
-  constexpr int kPerWarp = 5 * S + 2 * N + 32;
-  extern __shared__ float smem[];
+                                                                     const float* __restrict__ u,
+                                                                     const float* __restrict__ cdf_in, int64_t R,
+                                                                     float* __restrict__ z_samples,
+                                                                     float* __restrict__ z_merged, float* __restrict__ z_std,
+                                                                     int* __restrict__ inds_out) {
+  constexpr int S = 4 * LANES, N = KN * LANES, B = S - 1, RPW = 32 / LANES;
+  constexpr int LOGB = S == 32 ? 5 : (S == 64 ? 6 : 7);                        // B = 2^LOGB - 1
+  constexpr int LOGS1 = LOGB + 1;                                              // counts 0 .. S
+  constexpr int LOGN1 = N <= 32 ? 6 : (N <= 64 ? 7 : (N <= 128 ? 8 : 9));      // counts 0 .. N
+  constexpr int kPerRay = 5 * S + 2 * N + 4;                                   // cdf | bins | z | samples | merged | hist
+  extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  float* zv = smem + (size_t)wib * kPerWarp;
-  float* cdf = zv + S;
-  float* bn = cdf + S;
-  float* smp = bn + S;
-  float* mrg = smp + N;
-  int* hist = reinterpret_cast<int*>(mrg + S + N);   // S + 32 counters
+  const int sub = lane / LANES, l = lane % LANES;
+  float* const base = smem + ((size_t)wib * RPW + sub) * kPerRay;
+  float* const cdf = base;
+  float* const bn = cdf + S;
+  float* const zv = bn + S;
+  float* const smp = zv + S;
+  float* const mrg = smp + N;
+  int* const hist = reinterpret_cast<int*>(mrg + S + N);                       // S + 4 counters
+  const int64_t ngroups = (R + RPW - 1) / RPW;
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
-  for (int64_t ray = (int64_t)blockIdx.x * kWarpsPerBlock + wib; ray < R; ray += nwarps) {
-    float zr[KS], pv[KS];
-    float tot = 0.f;
+  for (int64_t grp = (int64_t)blockIdx.x * kWarpsPerBlock + wib; grp < ngroups; grp += nwarps) {
+    const int64_t ray = grp * RPW + sub;
+    const bool valid = ray < R;
+    const int64_t rr = valid ? ray : R - 1;                                    // the odd last half-warp re-does the last ray
+    const float4 zq = *reinterpret_cast<const float4*>(z_vals + rr * S + l * 4);
+    const float zz[4] = {zq.x, zq.y, zq.z, zq.w};
+    *reinterpret_cast<float4*>(zv + l * 4) = zq;
+    float c[4];
+    if (cdf_in != nullptr) {                                                   // externally supplied cdf [R, S - 1] (test hook)
 #pragma unroll
-    for (int k = 0; k < KS; ++k) {
-      const int j = lane + 32 * k;
-      zr[k] = ld_stream(z_vals + ray * S + j);
-      zv[j] = zr[k];
-      pv[k] = j < M ? __fadd_rn(ld_stream(weights + ray * S + 1 + j), 1e-5f) : 0.f;
-      tot += pv[k];
-      if (DET) hist[j] = 0;
+      for (int k = 0; k < 4; ++k) c[k] = (l * 4 + k < B) ? __ldg(cdf_in + rr * B + l * 4 + k) : 1.f;
+    } else {
+      const float4 wq = *reinterpret_cast<const float4*>(weights + rr * S + l * 4);
+      const float ww[4] = {wq.x, wq.y, wq.z, wq.w};
+      float run = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {                                            // q_i = w_i + 1e-5 for 1 <= i <= S - 2 (helpers:308)
+        const int i = l * 4 + k;
+        run += (i >= 1 && i <= S - 2) ? __fadd_rn(ww[k], 1e-5f) : 0.f;
+        c[k] = run;
+      }
+      float incl = run;
+#pragma unroll
+      for (int o = 1; o < LANES; o <<= 1) {
+        const float t = __shfl_up_sync(kFullMask, incl, o, LANES);
+        if (l >= o) incl += t;
+      }
+      const float rtot = __frcp_rn(__shfl_sync(kFullMask, incl, LANES - 1, LANES));
+      const float excl = incl - run;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) c[k] = (excl + c[k]) * rtot;                 // cdf[i] = sum_{1 <= m <= i} q_m / sum q
     }
-    if (DET) hist[S + lane] = 0;
-    tot = warp_sum(tot);
-    float carry = 0.f;
-    if (lane == 0) cdf[0] = 0.f;
-#pragma unroll
-    for (int k = 0; k < KS; ++k) {
-      const int j = lane + 32 * k;
-      const float p = j < M ? __fdiv_rn(pv[k], tot) : 0.f;
-      const float incl = warp_scan_add(p, lane);
-      if (j < M) cdf[j + 1] = carry + incl;
-      carry += __shfl_sync(kFullMask, incl, 31);
-      float nxt = __shfl_down_sync(kFullMask, zr[k], 1);
-      const float wrap = __shfl_sync(kFullMask, zr[k + 1 < KS ? k + 1 : k], 0);
-      if (lane == 31) nxt = wrap;
-      if (j < B) bn[j] = __fmul_rn(.5f, __fadd_rn(nxt, zr[k]));
+    *reinterpret_cast<float4*>(cdf + l * 4) = make_float4(c[0], c[1], c[2], c[3]);
+    const float znext = __shfl_down_sync(kFullMask, zz[0], 1, LANES);
+    *reinterpret_cast<float4*>(bn + l * 4) = make_float4(.5f * (zz[1] + zz[0]), .5f * (zz[2] + zz[1]), .5f * (zz[3] + zz[2]),
+                                                         .5f * (znext + zz[3]));
+    if (DET) {
+      *reinterpret_cast<int4*>(hist + l * 4) = make_int4(0, 0, 0, 0);
+      if (l == 0) *reinterpret_cast<int4*>(hist + S) = make_int4(0, 0, 0, 0);
     }
     __syncwarp();
-    float sv[KN];
+    // ---- KN consecutive samples per lane --------------------------------------------------------------------------
+    float uu[KN], sv[KN];
+    if (DET) {
+#pragma unroll
+      for (int k = 0; k < KN; ++k) uu[k] = linspace01(l * KN + k, N);
+    } else if (KN == 2) {
+      const float2 q = *reinterpret_cast<const float2*>(u + rr * N + l * KN);
+      uu[0] = q.x; uu[1] = q.y;
+    } else {
+#pragma unroll
+      for (int k = 0; k < KN; k += 4) {
+        const float4 q = *reinterpret_cast<const float4*>(u + rr * N + l * KN + k);
+        uu[k] = q.x; uu[k + 1 < KN ? k + 1 : k] = q.y; uu[k + 2 < KN ? k + 2 : k] = q.z; uu[k + 3 < KN ? k + 3 : k] = q.w;
+      }
+    }
     float sum = 0.f;
+    int los[KN];
 #pragma unroll
     for (int k = 0; k < KN; ++k) {
-      const int n = lane + 32 * k;
-      const float uu = DET ? linspace01(n, N) : ld_stream(u + ray * N + n);
-      const int ind = count_below<LOGS, true>(cdf, B, uu);
+      const int ind = count_below<LOGB, true>(cdf, B, uu[k]);
       const int lo = ind - 1 < 0 ? 0 : ind - 1;
       const int hi = ind > B - 1 ? B - 1 : ind;
       const float c0 = cdf[lo], c1 = cdf[hi];
-      float den = __fsub_rn(c1, c0);
+      float den = c1 - c0;
       if (den < 1e-5f) den = 1.f;
-      const float t = __fdiv_rn(__fsub_rn(uu, c0), den);
+      const float t = __fdividef(uu[k] - c0, den);
       const float b0 = bn[lo], b1 = bn[hi];
-      const float v = __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
-      sv[k] = v;
-      sum += v;
-      if (z_samples) st_stream(z_samples + ray * N + n, v);
-      if (DET) {
-        const int c = lo + 1 + (zv[lo + 1] <= v ? 1 : 0);
-        mrg[n + c] = v;
-        atomicAdd(&hist[c], 1);
-      }
+      sv[k] = fmaf(t, b1 - b0, b0);
+      sum += sv[k];
+      los[k] = lo;
+      if (inds_out != nullptr && valid) inds_out[ray * N + l * KN + k] = ind;
     }
-    if (z_std) {
-      const float mean = warp_sum(sum) / (float)N;
+    if (z_samples != nullptr && valid) {
+#pragma unroll
+      for (int k = 0; k < KN; ++k) st_stream(z_samples + ray * N + l * KN + k, sv[k]);
+    }
+    if (z_std != nullptr) {                                                    // std(unbiased=False), run.py:2370
+#pragma unroll
+      for (int o = LANES / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(kFullMask, sum, o);
+      const float mean = sum * (1.f / (float)N);
       float var = 0.f;
 #pragma unroll
-      for (int k = 0; k < KN; ++k) { const float dv = sv[k] - mean; var += dv * dv; }
-      var = warp_sum(var);
-      if (lane == 0) z_std[ray] = sqrtf(var / (float)N);
+      for (int k = 0; k < KN; ++k) { const float dv = sv[k] - mean; var = fmaf(dv, dv, var); }
+#pragma unroll
+      for (int o = LANES / 2; o > 0; o >>= 1) var += __shfl_xor_sync(kFullMask, var, o);
+      if (l == 0 && valid) z_std[ray] = sqrtf(var * (1.f / (float)N));
     }
+    // ---- merge with the coarse depths -------------------------------------------------------------------------------
     if (DET) {
-      __syncwarp();
-      int icarry = 0;
+      // a sample from bin lo lies between z[lo] and z[lo + 2]: rank among the coarse depths = lo + 1 + (z[lo + 1] <= s);
+      // the samples are ascending (u is), so sample n lands at n + rank; coarse depth i at i + #{samples ranked <= i}
 #pragma unroll
-      for (int k = 0; k < KS; ++k) {
-        const int i = lane + 32 * k;
-        int v = hist[i];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int t = __shfl_up_sync(kFullMask, v, o);
-          if (lane >= o) v += t;
-        }
-        mrg[i + icarry + v] = zr[k];
-        icarry += __shfl_sync(kFullMask, v, 31);
+      for (int k = 0; k < KN; ++k) {
+        const int cnt = los[k] + 1 + (zv[los[k] + 1] <= sv[k] ? 1 : 0);
+        mrg[l * KN + k + cnt] = sv[k];
+        atomicAdd(&hist[cnt], 1);
       }
-    } else {
-      warp_bitonic_sort_regs<KN>(sv, lane);
+      __syncwarp();
+      const int4 hq = *reinterpret_cast<const int4*>(hist + l * 4);
+      const int h1 = hq.x, h2 = h1 + hq.y, h3 = h2 + hq.z, h4 = h3 + hq.w;
+      int incl = h4;
 #pragma unroll
-      for (int k = 0; k < KN; ++k) smp[lane + 32 * k] = sv[k];
+      for (int o = 1; o < LANES; o <<= 1) {
+        const int t = __shfl_up_sync(kFullMask, incl, o, LANES);
+        if (l >= o) incl += t;
+      }
+      const int excl = incl - h4;
+      mrg[l * 4 + 0 + excl + h1] = zz[0];
+      mrg[l * 4 + 1 + excl + h2] = zz[1];
+      mrg[l * 4 + 2 + excl + h3] = zz[2];
+      mrg[l * 4 + 3 + excl + h4] = zz[3];
+    } else {
+      seg_bitonic_sort<LANES, KN>(sv, l);
+#pragma unroll
+      for (int k = 0; k < KN; ++k) smp[l * KN + k] = sv[k];
       __syncwarp();
 #pragma unroll
-      for (int k = 0; k < KS; ++k) mrg[lane + 32 * k + count_below<LOGN1, false>(smp, N, zr[k])] = zr[k];
+      for (int k = 0; k < 4; ++k) mrg[l * 4 + k + count_below<LOGN1, false>(smp, N, zz[k])] = zz[k];
 #pragma unroll
-      for (int k = 0; k < KN; ++k) mrg[lane + 32 * k + count_below<LOGS + 1, true>(zv, S, sv[k])] = sv[k];
+      for (int k = 0; k < KN; ++k) mrg[l * KN + k + count_below<LOGS1, true>(zv, S, sv[k])] = sv[k];
     }
     __syncwarp();
-#pragma unroll
-    for (int k = 0; k < KS + KN; ++k) st_stream(z_merged + ray * (S + N) + lane + 32 * k, mrg[lane + 32 * k]);
+    // merged rows of the warp's RPW consecutive rays are contiguous in memory: 16-byte stores
+    {
+      const float* wm = smem + (size_t)wib * RPW * kPerRay;
+      const int64_t first = grp * RPW;
+      const int nvalid = (int)((R - first) < RPW ? (R - first) : RPW);
+      float4* out = reinterpret_cast<float4*>(z_merged + first * (S + N));
+      constexpr int per_ray4 = (S + N) / 4;
+      for (int idx = lane; idx < nvalid * per_ray4; idx += 32) {
+        const int r = idx / per_ray4, o = idx - r * per_ray4;
+        st_stream4(out + idx, *reinterpret_cast<const float4*>(wm + (size_t)r * kPerRay + 3 * S + N + 4 * o));
+      }
+    }
     __syncwarp();
   }
 }
 
-template <int KS, int KN>
-static int launch_sample_merge_fast(const float* z_vals, const float* weights, const float* u, int64_t R, float* z_samples,
-                                    float* z_merged, float* z_std, cudaStream_t stream) {
-  constexpr size_t smem = (size_t)kWarpsPerBlock * (5 * 32 * KS + 2 * 32 * KN + 32) * sizeof(float);
-  static_assert(smem <= 48 * 1024, "sample_merge_fast: shared memory above the default limit");
+template <int LANES, int KN>
+static int launch_sample_merge_cons(const float* z_vals, const float* weights, const float* u, const float* cdf_in, int64_t R,
+                                    float* z_samples, float* z_merged, float* z_std, int* inds_out, cudaStream_t stream) {
+  constexpr int S = 4 * LANES, N = KN * LANES, RPW = 32 / LANES;
+  constexpr size_t smem = (size_t)kWarpsPerBlock * RPW * (5 * S + 2 * N + 4) * sizeof(float);
+  static_assert(smem <= 48 * 1024, "sample_merge_cons: shared memory above the default limit");
   const int per_sm = (int)((200 * 1024) / smem);
-  const int grid = persistent_grid(R, per_sm > 8 ? 8 : per_sm);
-  if (u) sample_merge_fast_kernel<KS, KN, false><<<grid, kThreads, smem, stream>>>(z_vals, weights, u, R, z_samples, z_merged, z_std);
-  else sample_merge_fast_kernel<KS, KN, true><<<grid, kThreads, smem, stream>>>(z_vals, weights, u, R, z_samples, z_merged, z_std);
-  return check_launch("sample_merge_fast_kernel");
+  const int grid = persistent_grid((R + RPW - 1) / RPW, per_sm > 8 ? 8 : per_sm);
+  if (u) sample_merge_cons_kernel<LANES, KN, false><<<grid, kThreads, smem, stream>>>(z_vals, weights, u, cdf_in, R, z_samples, z_merged, z_std, inds_out);
+  else sample_merge_cons_kernel<LANES, KN, true><<<grid, kThreads, smem, stream>>>(z_vals, weights, u, cdf_in, R, z_samples, z_merged, z_std, inds_out);
+  return check_launch("sample_merge_cons_kernel");
 }
 
 // =========================================================================================================
@@ -818,18 +884,24 @@ extern "C" int gbn_sample_pdf(const float* bins, const float* weights, const flo
   return check_launch("sample_pdf_kernel");
 }
 
-extern "C" int gbn_sample_pdf_merge(const float* z_vals, const float* weights, const float* u, int64_t R, int S,
-                                    int N, float* z_samples, float* z_merged, float* z_std, void* stream) {
+extern "C" int gbn_sample_pdf_merge_ex(const float* z_vals, const float* weights, const float* u, const float* cdf_in,
+                                       int64_t R, int S, int N, float* z_samples, float* z_merged, float* z_std,
+                                       int* inds_out, void* stream) {
   if (R == 0) return GBN_OK;
-  GBN_REQUIRE(z_vals && weights && z_merged, "sample_pdf_merge: null pointer");
+  GBN_REQUIRE(z_vals && (weights || cdf_in) && z_merged, "sample_pdf_merge: null pointer");
   GBN_REQUIRE(R >= 0 && S >= 3 && N >= 1, "sample_pdf_merge: need S>=3, N>=1 (S=%d N=%d)", S, N);
   {
     static const bool generic_only = [] { const char* e = getenv("GBNERF_SAMPLE_GENERIC"); return e && e[0] == '1'; }();
     cudaStream_t st = (cudaStream_t)stream;
-#define GBN_SM_FAST(KS, KN) \
-  if (!generic_only && S == 32 * KS && N == 32 * KN) return launch_sample_merge_fast<KS, KN>(z_vals, weights, u, R, z_samples, z_merged, z_std, st)
-    GBN_SM_FAST(2, 2); GBN_SM_FAST(2, 4); GBN_SM_FAST(4, 2); GBN_SM_FAST(4, 4); GBN_SM_FAST(4, 8); GBN_SM_FAST(2, 1); GBN_SM_FAST(1, 1);
-#undef GBN_SM_FAST
+    const uintptr_t al = reinterpret_cast<uintptr_t>(z_vals) | reinterpret_cast<uintptr_t>(weights) | reinterpret_cast<uintptr_t>(u) |
+                         reinterpret_cast<uintptr_t>(z_merged);
+    // the render path's shapes: S = 4 LANES, N = KN LANES (rows are then multiples of 16 bytes: vector accesses)
+#define GBN_SM_CONS(LANES, KN) \
+  if (!generic_only && (al & 15) == 0 && S == 4 * LANES && N == KN * LANES) \
+    return launch_sample_merge_cons<LANES, KN>(z_vals, weights, u, cdf_in, R, z_samples, z_merged, z_std, inds_out, st)
+    GBN_SM_CONS(16, 4); GBN_SM_CONS(16, 8); GBN_SM_CONS(16, 2); GBN_SM_CONS(32, 2); GBN_SM_CONS(32, 4); GBN_SM_CONS(32, 8);
+    GBN_SM_CONS(8, 4);
+#undef GBN_SM_CONS
   }
   int npad = 1;
   while (npad < N) npad <<= 1;
@@ -842,8 +914,13 @@ extern "C" int gbn_sample_pdf_merge(const float* z_vals, const float* weights, c
   }
   const int per_sm = smem > 0 ? (int)((220 * 1024) / smem) : 4;
   sample_merge_kernel<<<persistent_grid(R, per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm)), kThreads, smem,
-                        (cudaStream_t)stream>>>(z_vals, weights, u, R, S, N, npad, z_samples, z_merged, z_std);
+                        (cudaStream_t)stream>>>(z_vals, weights, u, cdf_in, R, S, N, npad, z_samples, z_merged, z_std, inds_out);
   return check_launch("sample_merge_kernel");
+}
+
+extern "C" int gbn_sample_pdf_merge(const float* z_vals, const float* weights, const float* u, int64_t R, int S,
+                                    int N, float* z_samples, float* z_merged, float* z_std, void* stream) {
+  return gbn_sample_pdf_merge_ex(z_vals, weights, u, nullptr, R, S, N, z_samples, z_merged, z_std, nullptr, stream);
 }
 
 extern "C" int gbn_loss_seed(const float* rgb, const float* rgb0, const float* disp, const float* target_rgb,

@@ -480,6 +480,344 @@ __global__ void __launch_bounds__(kStThreads, K <= 2 ? 4 : 3) composite_bwd_stag
   }
 }
 
+// ---- long rays: S = 128 M (M = 2 .. 8), e.g. the fine pass of BASELINE configs[3] (128 + 256 = 384 samples) --------------
+// A lane that owned S / 32 consecutive samples would need ~110 registers at S = 384.  Here the ring slot still holds the
+// WHOLE ray (cp.async, D rays deep per warp), but the warp walks it in M segments of 128 samples with the K = 4
+// register footprint: inside a segment a lane owns 4 consecutive samples, one shuffle product scan covers the segment,
+// and the transmittance at the segment's start is a carried scalar.  The backward walks the segments forward once
+// (transmittance carries, the lane's exclusive in-segment products, depth and acc totals) and then in reverse with a
+// carried suffix sum: per 128 samples the same one product scan + one reverse sum scan as composite_bwd_staged_kernel.
+constexpr int kSegWarps = 4;
+constexpr int kSegThreads = kSegWarps * 32;
+
+template <int M, int D, bool NOISE>
+__global__ void __launch_bounds__(kSegThreads) composite_fwd_seg_kernel(
+    const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ noise,
+    const float* __restrict__ d, int64_t stride, int64_t R, int white,
+    float* __restrict__ rgb, float* __restrict__ disp, float* __restrict__ acc, float* __restrict__ depth,
+    float* __restrict__ weights, float* __restrict__ alpha_out) {
+  constexpr int S = 128 * M;
+  constexpr uint32_t ray_bytes = (uint32_t)S * (NOISE ? 24u : 20u);       // raw | z | noise of one ray
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* const ring = smem + (size_t)warp * D * ray_bytes;
+  const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
+  const int64_t nwarps = (int64_t)gridDim.x * kSegWarps;
+  const int64_t w0 = (int64_t)blockIdx.x * kSegWarps + warp;
+  const int64_t my_rays = w0 < R ? (R - w0 + nwarps - 1) / nwarps : 0;
+
+  auto issue = [&](int64_t i) {
+    const int64_t ray = w0 + i * nwarps;
+    const uint32_t dst = ring_u32 + (uint32_t)(i % D) * ray_bytes;
+    const float4* rsrc = reinterpret_cast<const float4*>(raw) + ray * S;
+#pragma unroll
+    for (int k = 0; k < 4 * M; ++k) cp_async16(dst + (k * 32 + lane) * 16, rsrc + k * 32 + lane);
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+      cp_async16(dst + S * 16 + (k * 32 + lane) * 16, reinterpret_cast<const float4*>(z + ray * S) + k * 32 + lane);
+      if (NOISE) cp_async16(dst + S * 20 + (k * 32 + lane) * 16, reinterpret_cast<const float4*>(noise + ray * S) + k * 32 + lane);
+    }
+  };
+#pragma unroll
+  for (int j = 0; j < D - 1; ++j) {
+    if (j < my_rays) issue(j);
+    cp_async_commit();
+  }
+  float dn_lane = 0.f;
+  for (int64_t i = 0; i < my_rays; ++i) {
+    const int64_t ray = w0 + i * nwarps;
+    if (i + D - 1 < my_rays) issue(i + D - 1);
+    cp_async_commit();
+    if ((i & 31) == 0) {
+      const int64_t ii = i + lane;
+      if (ii < my_rays) {
+        const int64_t r = w0 + ii * nwarps;
+        const float dx = __ldg(d + r * stride), dy = __ldg(d + r * stride + 1), dz = __ldg(d + r * stride + 2);
+        dn_lane = sqrtf(dx * dx + dy * dy + dz * dz);
+      }
+    }
+    const float dnorm = __shfl_sync(kFullMask, dn_lane, (int)(i & 31));
+    cp_async_wait<D - 1>();
+    __syncwarp();
+    const uint8_t* st = ring + (size_t)(i % D) * ray_bytes;
+    const float4* sraw = reinterpret_cast<const float4*>(st);
+    const float* sz = reinterpret_cast<const float*>(st + S * 16);
+    const float* sn = reinterpret_cast<const float*>(st + S * 20);
+    float carry = 1.f;                                   // transmittance at the start of the segment
+    float sr = 0.f, sg = 0.f, sb = 0.f, sd = 0.f, sa = 0.f;
+    float* wrow = weights + ray * S;
+    float* arow = alpha_out ? alpha_out + ray * S : nullptr;
+#pragma unroll
+    for (int seg = 0; seg < M; ++seg) {
+      const int base = seg * 128 + lane * 4;
+      float4 rw[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) rw[k] = sraw[base + k];
+      const float4 zq = reinterpret_cast<const float4*>(sz)[base >> 2];
+      float4 nq = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (NOISE) nq = reinterpret_cast<const float4*>(sn)[base >> 2];
+      const float zz[4] = {zq.x, zq.y, zq.z, zq.w}, nz[4] = {nq.x, nq.y, nq.z, nq.w};
+      float znext = __shfl_down_sync(kFullMask, zz[0], 1);
+      if (lane == 31 && seg + 1 < M) znext = sz[base + 4];          // first depth of the next segment
+      float a[4], tl[4];
+      float prod = 1.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float zn = k < 3 ? zz[k < 3 ? k + 1 : k] : znext;
+        const float dl = (seg == M - 1 && lane == 31 && k == 3) ? 1e10f : (zn - zz[k]);
+        const float sigma = fmaxf(rw[k].w + nz[k], 0.f);
+        a[k] = 1.f - __expf(-sigma * (dl * dnorm));
+        tl[k] = prod;
+        prod *= (1.f - a[k]) + 1e-10f;
+      }
+      const float incl = warp_scan_mul(prod, lane);
+      float excl = __shfl_up_sync(kFullMask, incl, 1);
+      if (lane == 0) excl = 1.f;
+      excl *= carry;
+      float w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        w[k] = a[k] * (excl * tl[k]);
+        sr = fmaf(w[k], fast_sigmoid(rw[k].x), sr);
+        sg = fmaf(w[k], fast_sigmoid(rw[k].y), sg);
+        sb = fmaf(w[k], fast_sigmoid(rw[k].z), sb);
+        sd = fmaf(w[k], zz[k], sd);
+        sa += w[k];
+      }
+      st_stream4(reinterpret_cast<float4*>(wrow + base), make_float4(w[0], w[1], w[2], w[3]));
+      if (arow) st_stream4(reinterpret_cast<float4*>(arow + base), make_float4(a[0], a[1], a[2], a[3]));
+      carry *= __shfl_sync(kFullMask, incl, 31);
+    }
+    __syncwarp();   // slot may be refilled by the next iteration's issue
+    const float tot = warp_sum5(sa, sr, sg, sb, sd, lane);
+    const float tacc = __shfl_sync(kFullMask, tot, 0);
+    if ((lane & 3) == 0 && lane <= 16) {
+      const float bg = white ? (1.f - tacc) : 0.f;
+      if (lane == 0) acc[ray] = tot;
+      else if (lane == 4) rgb[ray * 3 + 0] = tot + bg;
+      else if (lane == 8) rgb[ray * 3 + 1] = tot + bg;
+      else if (lane == 12) rgb[ray * 3 + 2] = tot + bg;
+      else {
+        const float q = __fdividef(tot, tacc);   // NaN when acc == 0, as torch.max propagates the NaN of 0/0
+        disp[ray] = __fdividef(1.f, (q != q) ? q : fmaxf(1e-10f, q));
+        depth[ray] = tot;
+      }
+    }
+  }
+}
+
+template <int M, int D, bool NOISE, bool GW>
+__global__ void __launch_bounds__(kSegThreads) composite_bwd_seg_kernel(
+    const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ noise,
+    const float* __restrict__ d, int64_t stride, int64_t R, int white, int detach_w,
+    const float* __restrict__ g_rgb, const float* __restrict__ g_disp, const float* __restrict__ g_acc,
+    const float* __restrict__ g_depth, const float* __restrict__ g_w, float* __restrict__ g_raw) {
+  constexpr int S = 128 * M;
+  constexpr uint32_t ray_bytes = (uint32_t)S * (20u + (NOISE ? 4u : 0u) + (GW ? 4u : 0u));   // raw | z | noise | g_w
+  constexpr uint32_t off_z = S * 16, off_n = S * 20, off_g = S * (NOISE ? 24 : 20);
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* const ring = smem + (size_t)warp * D * ray_bytes;
+  const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
+  const int64_t nwarps = (int64_t)gridDim.x * kSegWarps;
+  const int64_t w0 = (int64_t)blockIdx.x * kSegWarps + warp;
+  const int64_t my_rays = w0 < R ? (R - w0 + nwarps - 1) / nwarps : 0;
+
+  auto issue = [&](int64_t i) {
+    const int64_t ray = w0 + i * nwarps;
+    const uint32_t dst = ring_u32 + (uint32_t)(i % D) * ray_bytes;
+    const float4* rsrc = reinterpret_cast<const float4*>(raw) + ray * S;
+#pragma unroll
+    for (int k = 0; k < 4 * M; ++k) cp_async16(dst + (k * 32 + lane) * 16, rsrc + k * 32 + lane);
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+      cp_async16(dst + off_z + (k * 32 + lane) * 16, reinterpret_cast<const float4*>(z + ray * S) + k * 32 + lane);
+      if (NOISE) cp_async16(dst + off_n + (k * 32 + lane) * 16, reinterpret_cast<const float4*>(noise + ray * S) + k * 32 + lane);
+      if (GW) cp_async16(dst + off_g + (k * 32 + lane) * 16, reinterpret_cast<const float4*>(g_w + ray * S) + k * 32 + lane);
+    }
+  };
+#pragma unroll
+  for (int j = 0; j < D - 1; ++j) {
+    if (j < my_rays) issue(j);
+    cp_async_commit();
+  }
+  float dn_l = 0.f, gr_l = 0.f, gg_l = 0.f, gb_l = 0.f, gdisp_l = 0.f, gacc_l = 0.f, gdep_l = 0.f;
+  for (int64_t i = 0; i < my_rays; ++i) {
+    const int64_t ray = w0 + i * nwarps;
+    if (i + D - 1 < my_rays) issue(i + D - 1);
+    cp_async_commit();
+    if ((i & 31) == 0) {
+      const int64_t ii = i + lane;
+      if (ii < my_rays) {
+        const int64_t r = w0 + ii * nwarps;
+        const float dx = __ldg(d + r * stride), dy = __ldg(d + r * stride + 1), dz = __ldg(d + r * stride + 2);
+        dn_l = sqrtf(dx * dx + dy * dy + dz * dz);
+        gr_l = g_rgb ? __ldg(g_rgb + r * 3) : 0.f; gg_l = g_rgb ? __ldg(g_rgb + r * 3 + 1) : 0.f; gb_l = g_rgb ? __ldg(g_rgb + r * 3 + 2) : 0.f;
+        gdisp_l = g_disp ? __ldg(g_disp + r) : 0.f; gacc_l = g_acc ? __ldg(g_acc + r) : 0.f; gdep_l = g_depth ? __ldg(g_depth + r) : 0.f;
+      }
+    }
+    const int src = (int)(i & 31);
+    const float dnorm = __shfl_sync(kFullMask, dn_l, src);
+    const float gr = __shfl_sync(kFullMask, gr_l, src), gg = __shfl_sync(kFullMask, gg_l, src), gb = __shfl_sync(kFullMask, gb_l, src);
+    const float gdisp = __shfl_sync(kFullMask, gdisp_l, src);
+    float gacc = __shfl_sync(kFullMask, gacc_l, src), gdep = __shfl_sync(kFullMask, gdep_l, src);
+    cp_async_wait<D - 1>();
+    __syncwarp();
+    const uint8_t* st = ring + (size_t)(i % D) * ray_bytes;
+    const float4* sraw = reinterpret_cast<const float4*>(st);
+    const float* sz = reinterpret_cast<const float*>(st + off_z);
+    const float* sn = reinterpret_cast<const float*>(st + off_n);
+    const float* sgw = reinterpret_cast<const float*>(st + off_g);
+
+    // what one segment needs recomputed in both passes: alpha, e, delta, the lane's in-lane exclusive products
+    auto segment = [&](int seg, float (&a)[4], float (&e)[4], float (&dlt)[4], float (&tl)[4], float (&zz)[4], float (&pre)[4]) -> float {
+      const int base = seg * 128 + lane * 4;
+      const float4 zq = reinterpret_cast<const float4*>(sz)[base >> 2];
+      float4 nq = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (NOISE) nq = reinterpret_cast<const float4*>(sn)[base >> 2];
+      zz[0] = zq.x; zz[1] = zq.y; zz[2] = zq.z; zz[3] = zq.w;
+      const float nz[4] = {nq.x, nq.y, nq.z, nq.w};
+      float znext = __shfl_down_sync(kFullMask, zz[0], 1);
+      if (lane == 31 && seg + 1 < M) znext = sz[base + 4];
+      float prod = 1.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float zn = k < 3 ? zz[k < 3 ? k + 1 : k] : znext;
+        const float dl = (seg == M - 1 && lane == 31 && k == 3) ? 1e10f : (zn - zz[k]);
+        dlt[k] = dl * dnorm;
+        pre[k] = sraw[base + k].w + nz[k];
+        e[k] = __expf(-fmaxf(pre[k], 0.f) * dlt[k]);
+        a[k] = 1.f - e[k];
+        tl[k] = prod;
+        prod *= (1.f - a[k]) + 1e-10f;
+      }
+      return prod;
+    };
+
+    // ---- pass 1, forward over the segments: exclusive transmittance of every lane's first sample, depth and acc totals
+    float t0[M];                                         // transmittance in front of this lane's 4 samples of segment seg
+    float carry = 1.f, sd = 0.f, sa = 0.f;
+#pragma unroll
+    for (int seg = 0; seg < M; ++seg) {
+      float a[4], e[4], dlt[4], tl[4], zz[4], pre[4];
+      const float prod = segment(seg, a, e, dlt, tl, zz, pre);
+      const float incl = warp_scan_mul(prod, lane);
+      float excl = __shfl_up_sync(kFullMask, incl, 1);
+      if (lane == 0) excl = 1.f;
+      t0[seg] = excl * carry;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float w = a[k] * (t0[seg] * tl[k]);
+        sd = fmaf(w, zz[k], sd);
+        sa += w;
+      }
+      carry *= __shfl_sync(kFullMask, incl, 31);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sd += __shfl_xor_sync(kFullMask, sd, o); sa += __shfl_xor_sync(kFullMask, sa, o); }
+    if (gdisp != 0.f) {   // disp = 1 / max(1e-10, depth / acc): above the clamp disp = acc / depth
+      const float q = sd / sa;
+      if (!(q <= 1e-10f)) {   // also taken for NaN, which then propagates as in autograd
+        gdep += -gdisp * sa / (sd * sd);
+        gacc += gdisp / sd;
+      }
+    }
+    if (white) gacc -= gr + gg + gb;
+    // ---- pass 2, segments in reverse: G_k, suffix sums of G_k w_k, gradients -------------------------------------------
+    float later_segs = 0.f;                              // sum of G w over all later segments
+#pragma unroll
+    for (int seg = M - 1; seg >= 0; --seg) {
+      const int base = seg * 128 + lane * 4;
+      float a[4], e[4], dlt[4], tl[4], zz[4], pre[4];
+      segment(seg, a, e, dlt, tl, zz, pre);
+      float4 gq = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (GW) gq = reinterpret_cast<const float4*>(sgw)[base >> 2];
+      const float gw[4] = {gq.x, gq.y, gq.z, gq.w};
+      float G[4], suf[4], T[4], w[4];
+      float run = 0.f;
+#pragma unroll
+      for (int k = 3; k >= 0; --k) {
+        const float4 rw = sraw[base + k];
+        T[k] = t0[seg] * tl[k];
+        w[k] = a[k] * T[k];
+        G[k] = gdep * zz[k] + gacc + gw[k];
+        if (!detach_w) G[k] += gr * fast_sigmoid(rw.x) + gg * fast_sigmoid(rw.y) + gb * fast_sigmoid(rw.z);
+        suf[k] = run;
+        run = fmaf(G[k], w[k], run);
+      }
+      const float rincl = warp_rscan_add(run, lane);
+      float later = __shfl_down_sync(kFullMask, rincl, 1);
+      if (lane == 31) later = 0.f;
+      later += later_segs;
+      float4* out = reinterpret_cast<float4*>(g_raw) + ray * S + base;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 rw = sraw[base + k];
+        const float f = (1.f - a[k]) + 1e-10f;
+        const float dalpha = G[k] * T[k] - __fdividef(suf[k] + later, f);
+        const float cr = fast_sigmoid(rw.x), cg = fast_sigmoid(rw.y), cb = fast_sigmoid(rw.z);
+        float4 o;
+        o.x = w[k] * gr * cr * (1.f - cr);
+        o.y = w[k] * gg * cg * (1.f - cg);
+        o.z = w[k] * gb * cb * (1.f - cb);
+        o.w = (pre[k] > 0.f) ? dalpha * dlt[k] * e[k] : 0.f;
+        st_stream4(out + k, o);
+      }
+      later_segs += __shfl_sync(kFullMask, rincl, 0);
+    }
+    __syncwarp();   // slot may be refilled by the next iteration's issue
+  }
+}
+
+// S = 128 M for M in 2..8 (forward: M >= 3, shorter rays take composite_fwd_staged_kernel); returns 1 when launched
+template <int M>
+static int launch_fwd_seg(const float* raw, const float* z, const float* rays_d, int64_t ray_stride, const float* noise, int64_t R,
+                          int white, float* rgb, float* disp, float* acc, float* depth, float* weights, float* alpha,
+                          cudaStream_t stream) {
+  constexpr int D = 2;
+  const size_t smem = (size_t)kSegWarps * D * 128 * M * (noise ? 24 : 20);
+  const int per_sm = (int)((200 * 1024) / smem) < 1 ? 1 : (int)((200 * 1024) / smem);
+  const int64_t blocks = (R + kSegWarps - 1) / kSegWarps, cap = (int64_t)kNumSMs * (per_sm > 6 ? 6 : per_sm);
+  const int grid = (int)(blocks < cap ? blocks : cap);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(composite_fwd_seg_kernel<M, D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kSegWarps * D * 128 * M * 24));
+    cudaFuncSetAttribute(composite_fwd_seg_kernel<M, D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kSegWarps * D * 128 * M * 20));
+    attr = true;
+  }
+  if (noise) composite_fwd_seg_kernel<M, D, true><<<grid, kSegThreads, smem, stream>>>(raw, z, noise, rays_d, ray_stride, R, white, rgb, disp, acc, depth, weights, alpha);
+  else composite_fwd_seg_kernel<M, D, false><<<grid, kSegThreads, smem, stream>>>(raw, z, noise, rays_d, ray_stride, R, white, rgb, disp, acc, depth, weights, alpha);
+  return check_launch("composite_fwd_seg_kernel");
+}
+
+template <int M, bool NOISE, bool GW>
+static int launch_bwd_seg2(const float* raw, const float* z, const float* rays_d, int64_t ray_stride, const float* noise, int64_t R,
+                           int white, int detach_w, const float* g_rgb, const float* g_disp, const float* g_acc,
+                           const float* g_depth, const float* g_w, float* g_raw, cudaStream_t stream) {
+  constexpr int D = 2;
+  constexpr size_t smem = (size_t)kSegWarps * D * 128 * M * (20 + (NOISE ? 4 : 0) + (GW ? 4 : 0));
+  constexpr int per_sm = (int)((200 * 1024) / smem) < 1 ? 1 : (int)((200 * 1024) / smem);
+  const int64_t blocks = (R + kSegWarps - 1) / kSegWarps, cap = (int64_t)kNumSMs * (per_sm > 6 ? 6 : per_sm);
+  const int grid = (int)(blocks < cap ? blocks : cap);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(composite_bwd_seg_kernel<M, D, NOISE, GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = true;
+  }
+  composite_bwd_seg_kernel<M, D, NOISE, GW><<<grid, kSegThreads, smem, stream>>>(raw, z, noise, rays_d, ray_stride, R, white, detach_w,
+                                                                               g_rgb, g_disp, g_acc, g_depth, g_w, g_raw);
+  return check_launch("composite_bwd_seg_kernel");
+}
+template <int M>
+static int launch_bwd_seg(const float* raw, const float* z, const float* rays_d, int64_t ray_stride, const float* noise, int64_t R,
+                          int white, int detach_w, const float* g_rgb, const float* g_disp, const float* g_acc,
+                          const float* g_depth, const float* g_w, float* g_raw, cudaStream_t stream) {
+#define GBN_SEG_ARGS raw, z, rays_d, ray_stride, noise, R, white, detach_w, g_rgb, g_disp, g_acc, g_depth, g_w, g_raw, stream
+  if (noise) return g_w ? launch_bwd_seg2<M, true, true>(GBN_SEG_ARGS) : launch_bwd_seg2<M, true, false>(GBN_SEG_ARGS);
+  return g_w ? launch_bwd_seg2<M, false, true>(GBN_SEG_ARGS) : launch_bwd_seg2<M, false, false>(GBN_SEG_ARGS);
+#undef GBN_SEG_ARGS
+}
+
 // returns 1 when it launched (shape S = 64 or 128, 16-byte aligned operands), 0 when the caller must use the generic kernel
 int launch_composite_bwd_staged(const float* raw, const float* z, const float* rays_d, int64_t ray_stride, const float* noise,
                                 int64_t R, int S, int white, int detach_w, const float* g_rgb, const float* g_disp,
@@ -489,7 +827,17 @@ int launch_composite_bwd_staged(const float* raw, const float* z, const float* r
   static const bool off = [] { const char* e = getenv("GBNERF_COMP_BWD_GENERIC"); return e && e[0] == '1'; }();
   const uintptr_t al = reinterpret_cast<uintptr_t>(raw) | reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(noise) |
                        reinterpret_cast<uintptr_t>(g_w) | reinterpret_cast<uintptr_t>(g_raw);
-  if (off || R < 1 || (S != 64 && S != 128) || (al & 15) != 0) return 0;
+  if (off || R < 1 || (al & 15) != 0) return 0;
+  if (S >= 256 && S <= 1024 && S % 128 == 0) {   // long rays: segment walk (composite_bwd_seg_kernel)
+#define GBN_SEG_CALL(MM) *rc = launch_bwd_seg<MM>(raw, z, rays_d, ray_stride, noise, R, white, detach_w, g_rgb, g_disp, g_acc, g_depth, g_w, g_raw, stream)
+    switch (S / 128) {
+      case 2: GBN_SEG_CALL(2); break; case 3: GBN_SEG_CALL(3); break; case 4: GBN_SEG_CALL(4); break; case 5: GBN_SEG_CALL(5); break;
+      case 6: GBN_SEG_CALL(6); break; case 7: GBN_SEG_CALL(7); break; default: GBN_SEG_CALL(8); break;
+    }
+#undef GBN_SEG_CALL
+    return 1;
+  }
+  if (S != 64 && S != 128) return 0;
   const int64_t blocks = (R + kStWarps - 1) / kStWarps, cap = (int64_t)kNumSMs * 4;
   const int grid = (int)(blocks < cap ? blocks : cap);
 #define GBN_BW_LAUNCH(KK, NN, GG)                                                                                       \
@@ -525,7 +873,17 @@ int64_t launch_composite_fwd_staged(const float* raw, const float* z, const floa
   const int K = (S + 31) / 32;
   const uintptr_t al = reinterpret_cast<uintptr_t>(raw) | reinterpret_cast<uintptr_t>(weights) | reinterpret_cast<uintptr_t>(alpha);
   const bool full = S == 32 * K && ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(noise)) & 15) == 0;
-  if (R < 1 || S < 2 || K > 8 || K == 5 || K == 7 || (al & 15) != 0) return 0;
+  if (R < 1 || S < 2 || (al & 15) != 0) return 0;
+  if (S >= 384 && S <= 1024 && S % 128 == 0 && full) {   // long rays: segment walk (composite_fwd_seg_kernel)
+#define GBN_SEG_CALL(MM) *rc = launch_fwd_seg<MM>(raw, z, rays_d, ray_stride, noise, R, white, rgb, disp, acc, depth, weights, alpha, stream)
+    switch (S / 128) {
+      case 3: GBN_SEG_CALL(3); break; case 4: GBN_SEG_CALL(4); break; case 5: GBN_SEG_CALL(5); break;
+      case 6: GBN_SEG_CALL(6); break; case 7: GBN_SEG_CALL(7); break; default: GBN_SEG_CALL(8); break;
+    }
+#undef GBN_SEG_CALL
+    return R;
+  }
+  if (K > 8 || K == 5 || K == 7) return 0;
   static const bool no_pairs = [] { const char* e = getenv("GBNERF_COMP_NOPAIR"); return e && e[0] == '1'; }();
   if (S == 64 && full && !no_pairs) {   // two rays per warp (composite_fwd_pair64_kernel)
     constexpr int D = 2;

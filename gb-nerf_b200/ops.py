@@ -243,22 +243,33 @@ def sample_pdf(bins, weights, n_samples, u=None):
     return out
 
 
-def sample_pdf_merge(z_vals, weights, n_importance, u=None, want_samples=False):
-    """Fused run.py:2343-2348 + :2370.  Returns (z_merged [R,S+N], z_std [R], z_samples [R,N] or None)."""
-    z_vals, weights = _dense(z_vals.detach(), "z_vals", 2), _dense(weights.detach(), "weights", 2)
+def sample_pdf_merge(z_vals, weights, n_importance, u=None, want_samples=False, cdf=None, want_inds=False):
+    """Fused run.py:2343-2348 + :2370.  Returns (z_merged [R,S+N], z_std [R], z_samples [R,N] or None); with
+    ``want_inds`` a fourth item, the int32 bin indices ``searchsorted(cdf, u, right=True)`` of helpers:333.
+    ``cdf`` [R,S-1] replaces the cdf built from ``weights`` (test hook: same cdf + same u -> bit-exact indices)."""
+    z_vals = _dense(z_vals.detach(), "z_vals", 2)
+    weights = _dense(weights.detach(), "weights", 2, allow_none=cdf is not None)
     u = _dense(u, "u", 2, allow_none=True)
+    cdf = _dense(cdf, "cdf", 2, allow_none=True)
     R, S = z_vals.shape
-    if tuple(weights.shape) != (R, S):
+    if weights is not None and tuple(weights.shape) != (R, S):
         raise ValueError("weights must match z_vals")
+    if cdf is not None and tuple(cdf.shape) != (R, S - 1):
+        raise ValueError("cdf must be [R, S-1]")
     N = int(n_importance)
+    if u is not None and tuple(u.shape) != (R, N):
+        raise ValueError("u must be [R, N_importance]")
     dev = z_vals.device
     merged = torch.empty(R, S + N, device=dev); std = torch.empty(R, device=dev)
     samples = torch.empty(R, N, device=dev) if want_samples else None
+    inds = torch.empty(R, N, device=dev, dtype=torch.int32) if want_inds else None
     # algorithmic bytes (SURVEY §8d, fused with the merge): read z 4 S + weights 4 S (+ u 4 N), write z 4 (S + N) + z_std 4
     with _timed_launch(f"sample_merge_S{S}_N{N}{'_det' if u is None else ''}",
                        R * (8 * S + 4 * (S + N) + 4 + (4 * N if u is not None else 0) + (4 * N if want_samples else 0))):
-        _lib.call("gbn_sample_pdf_merge", _ptr(z_vals), _ptr(weights), _ptr(u), R, S, N, _ptr(samples), _ptr(merged),
-                  _ptr(std), _stream())
+        _lib.call("gbn_sample_pdf_merge_ex", _ptr(z_vals), _ptr(weights), _ptr(u), _ptr(cdf), R, S, N, _ptr(samples),
+                  _ptr(merged), _ptr(std), _ptr(inds), _stream())
+    if want_inds:
+        return merged, std, samples, inds
     return merged, std, samples
 
 

@@ -217,7 +217,8 @@ class TrainStep:
         torch.cuda.synchronize(self.dev)
         self.graph = torch.cuda.CUDAGraph()
         n0 = _lib.kernel_launches()
-        with torch.cuda.graph(self.graph):
+        # thread_local: NCCL's watchdog thread polls events of its own while the step is being captured
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self._launches()
         self.launches_per_step = _lib.kernel_launches() - n0    # kernels of libgbnerf.so inside one replay
 

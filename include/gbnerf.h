@@ -108,6 +108,13 @@ int gbn_searchsorted_right(const float* cdf, const float* u, int64_t R, int B, i
 int gbn_sample_pdf_merge(const float* z_vals, const float* weights, const float* u, int64_t R, int S, int N,
                          float* z_samples, float* z_merged, float* z_std, void* stream);
 
+/* The same call with the two hooks SURVEY 8(b) asks for, so that the north-star tolerance "bin indices bit-exact given
+ * the same CDF and uniforms" can be asserted on the production kernel itself: cdf_in (NULL, or [R, S-1] fp32: used
+ * instead of the cdf built from `weights`, which may then be NULL) and inds_out (NULL, or [R, N] int32 receiving
+ * searchsorted(cdf, u, right=True) of run_nerf_helpers.py:333 for every sample, in the order of `u`). */
+int gbn_sample_pdf_merge_ex(const float* z_vals, const float* weights, const float* u, const float* cdf_in, int64_t R,
+                            int S, int N, float* z_samples, float* z_merged, float* z_std, int* inds_out, void* stream);
+
 /* ---- the 8x256 NeRF MLP: NeRF.forward (run_nerf_helpers.py:106-129) --------------------------------------
  * Weights are re-laid-out once per optimiser step into the kernel's shared-memory image
  * (UMMA K-major, 128-byte swizzle, K padded to 64) — `params` is a HOST array of 24 DEVICE pointers in the

@@ -174,13 +174,14 @@ def test_autograd_end_to_end(G):
             assert relerr < 0.15, (name, relerr)
 
 
-@pytest.mark.xfail(strict=False, reason="OPEN (DESIGN 3.2): about 1 cold-cache dgrad launch in 40 differs in ONE tile's G stash "
-                   "(from the first 64-channel block of g_h7 down); forward output and stash are bit-stable")
 def test_training_kernels_repeat_bit_exactly_from_a_cold_cache(G):
     """The stash-writing forward and the dgrad program are deterministic: the same launch repeated with the weight
     image evicted from L2 (slow first weight fills, the condition under which an issuer once passed a ring stage on
     the other issuer's phase) must reproduce its outputs bit for bit, with clean watchdog words.
-    tools/cold_repeat.py is the same loop with a report of WHERE a repeat differs."""
+    Round 1 left this test xfail: about 1 launch in 40 on one box differed in one 64-channel block of g_h7.  Cause
+    (round 2, tools/dgrad_hunt.py + the chaos mode of the diagnostic library): the dgrad epilogue handed its gate
+    staging buffer back to the bulk-copy producer without a generic->async proxy fence; fixed in csrc/mlp_ts.cu, so the
+    test is strict again.  tools/dgrad_hunt.py is the same loop with a report of WHERE and HOW a repeat differs."""
     ops = G.ops
     torch.manual_seed(11)
     R, S = 1024, 128                                  # 1024 tiles: ~7 per CTA, 0.66 GB per stash

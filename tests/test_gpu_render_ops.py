@@ -212,6 +212,41 @@ def test_sample_pdf_merge(G, det, S, N):
     rel_close(std, torch.std(smp, dim=-1, unbiased=False), rtol=1e-4, atol=1e-6)
 
 
+@pytest.mark.parametrize("det", [True, False])
+@pytest.mark.parametrize("S,N", [(64, 64), (64, 128), (64, 32), (128, 64), (128, 128), (128, 256), (32, 32), (96, 64), (17, 5)])
+def test_sample_pdf_merge_indices_bit_exact_on_the_production_kernel(G, det, S, N):
+    """North star: "sample_pdf bin indices bit-exact given the same CDF and uniforms" - asserted on the kernel the render
+    path launches (sample_merge_cons_kernel for the first seven shapes, the generic kernel for the last two), which gets
+    the reference's own cdf through the `cdf` hook and returns its search result through `inds`: must equal
+    torch.searchsorted(cdf, u, right=True) (helpers:333) element for element, ties and exact hits included."""
+    g = torch.Generator().manual_seed(S * 11 + N)
+    R = 257                                                  # odd: the last half-warp group is half empty at S = 64
+    z = torch.sort(torch.rand(R, S, generator=g) * 6.8 + 1.2, -1)[0]
+    w = torch.rand(R, S, generator=g)
+    if S > 8:
+        w[0] = 0.
+        w[1] = 0.; w[1, S // 2] = 3.
+        w[2, 1:S // 2] = 0.                                  # runs of (almost) equal cdf values
+    cdf = O.build_cdf(w[:, 1:-1]).contiguous()
+    if det:
+        u, uu = None, torch.linspace(0., 1., N, device="cuda").cpu().expand(R, N).contiguous()
+    else:
+        u = torch.rand(R, N, generator=g)
+        u[:, 0] = cdf[:, (S - 1) // 2]                       # exact hits on a cdf value
+        u[:, N - 1] = cdf[:, 0]
+        if N > 2:
+            u[3, 1], u[3, 2] = 0., 1.
+        uu = u
+    merged, std, smp, inds = G.ops.sample_pdf_merge(dev(z), None, N, dev(u), want_samples=True, cdf=dev(cdf), want_inds=True)
+    want = torch.searchsorted(cdf, uu, right=True)
+    assert inds.dtype == torch.int32 and torch.equal(inds.cpu().long(), want)
+    assert torch.equal(want, O.upper_bound(cdf, uu))
+    # and the samples drawn from those bins match the oracle's inversion of the same cdf
+    z_mid = .5 * (z[:, 1:] + z[:, :-1])
+    rel_close(smp, O.invert_cdf(z_mid, cdf, uu)[0], rtol=2e-5, atol=1e-6)
+    assert torch.equal(merged.cpu(), torch.sort(torch.cat([z, smp.cpu()], -1), -1)[0])
+
+
 # ---- loss seed ---------------------------------------------------------------------------------------------- #
 def test_loss_seed(G):
     g = torch.Generator().manual_seed(11)

@@ -91,9 +91,10 @@ def test_eager_train_step_equals_autograd_path(G):
         for (name, pa), (_, pb) in zip(na.named_parameters(), nb.named_parameters()):
             assert (pa - pb).abs().max().item() < 2e-5, name          # one Adam step moves every weight by ~lr = 3e-3
         # the kernel patched the bf16 images in place: identical to a fresh re-pack of the new weights
-        img = nb.packed_weights().clone()
-        nb._packed_key = None
-        assert torch.equal(nb.packed_weights(), img)
+        # (re-packing over a copy: bytes the packer never writes - alignment gaps - keep their old content)
+        fwd, bwd = nb.packed_weights(), nb.packed_weights_bwd()
+        assert torch.equal(fwd, G.ops.prepack_weights(nb.param_list(), "bf16", out=fwd.clone()))
+        assert torch.equal(bwd, G.ops.prepack_weights(nb.param_list(), "bf16_bwd", out=bwd.clone()))
     assert opt_b.state_dict()["state"][0]["step"] == 1
 
 

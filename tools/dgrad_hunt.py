@@ -128,6 +128,64 @@ def forensics(tile, blocks):
 
 shapes = [tuple(t.shape) for t in net.param_list()]
 h_ref = stash_h.clone() if FULL else None
+# gate check of the diagnostic library (csrc/build.py --diag, GBNERF_LIB=...): the dgrad epilogue compares every gate chunk
+# it read from the staging buffer with the H stash itself and logs mismatches
+dbg = None
+if os.environ.get("HUNT_GATECHECK") == "1":
+    dbg = torch.zeros(65536 + 16 * 128 * 8, dtype=torch.int64, device=dev)
+    _lib.call("gbn_mlp_set_trace", dbg.data_ptr(), 0)
+
+
+def check_order():
+    """GBNERF_TS_FIX bit 4 (16): clocks of every gate fill's issue and of every epilogue warp's m_empty arrival, CTAs 0-15:
+    fill mc must be issued after all eight warps arrived for step mc - 2."""
+    issue = dbg[32768:32768 + 16 * 128].view(16, 128).cpu()
+    arrive = dbg[65536:].view(16, 128, 8).cpu()
+    viol, worst = 0, 0
+    for cta in range(16):
+        for mc in range(2, 119):
+            if issue[cta, mc] == 0 or (arrive[cta, mc - 2] == 0).any():
+                continue
+            late = int(arrive[cta, mc - 2].max() - issue[cta, mc])
+            if late > 0:
+                viol += 1
+                worst = max(worst, late)
+                if viol <= 5:
+                    print(f"   ORDER VIOLATION cta {cta} fill {mc} issued {late} cycles BEFORE the last arrival of step {mc - 2}: "
+                          f"arrivals - issue = {(arrive[cta, mc - 2] - issue[cta, mc]).tolist()}")
+    return viol, worst
+
+
+def dump_gatecheck():
+    if dbg is None:
+        return
+    if int(os.environ.get("GBNERF_TS_FIX", "0"), 0) & 16:
+        print("order check (last launch): violations, worst cycles =", check_order())
+        return
+    n = int(dbg[0].item())
+    print(f"gate check: {n} mismatching thread-reads logged")
+    rec = dbg[8:8 + 8 * min(n, 2000)].view(-1, 8).cpu().tolist()
+    by = {}
+    for tile, w1, mc, w3, clk, mfull, mempty, cta in rec:
+        si, warp, lane = w1 & 0xff, (w1 >> 8) & 0xff, (w1 >> 16) & 0xff
+        bad, eqn, eqp = w3 & 0xff, (w3 >> 8) & 0xff, (w3 >> 16) & 0xff
+        k = (si, warp)
+        d = by.setdefault(k, dict(n=0, bad=[0] * 8, next=0, prev=0, neither=0, clk=[], tiles=set(), lanes=set()))
+        d["n"] += 1
+        d["tiles"].add(tile); d["lanes"].add(lane); d["clk"].append(clk)
+        for c in range(8):
+            if (bad >> c) & 1:
+                d["bad"][c] += 1
+                if (eqn >> c) & 1: d["next"] += 1
+                elif (eqp >> c) & 1: d["prev"] += 1
+                else: d["neither"] += 1
+    for (si, warp), d in sorted(by.items()):
+        print(f"   step {si} warp {warp}: {d['n']} thread-reads in {len(d['tiles'])} tiles, lanes {min(d['lanes'])}..{max(d['lanes'])}, "
+              f"bad chunks by read order {d['bad']}, wrong chunk == next fill {d['next']}, == previous fill {d['prev']}, neither {d['neither']}")
+    for r in rec[:6]:
+        print("   raw:", [hex(x & 0xffffffffffffffff) for x in r])
+
+
 bad_launches = 0
 t0 = time.time()
 for it in range(N):
@@ -156,4 +214,5 @@ for it in range(N):
             for t in tiles[:3]:
                 forensics(t, sorted(b for tt, b in blk if tt == t))
         sys.stdout.flush()
+dump_gatecheck()
 print(f"RESULT {bad_launches} of {N} launches differed ({time.time() - t0:.1f} s)", flush=True)
