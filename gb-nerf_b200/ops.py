@@ -248,7 +248,7 @@ def sample_pdf_merge(z_vals, weights, n_importance, u=None, want_samples=False, 
     ``want_inds`` a fourth item, the int32 bin indices ``searchsorted(cdf, u, right=True)`` of helpers:333.
     ``cdf`` [R,S-1] replaces the cdf built from ``weights`` (test hook: same cdf + same u -> bit-exact indices)."""
     z_vals = _dense(z_vals.detach(), "z_vals", 2)
-    weights = _dense(weights.detach(), "weights", 2, allow_none=cdf is not None)
+    weights = _dense(weights.detach() if weights is not None else None, "weights", 2, allow_none=cdf is not None)
     u = _dense(u, "u", 2, allow_none=True)
     cdf = _dense(cdf, "cdf", 2, allow_none=True)
     R, S = z_vals.shape
@@ -328,15 +328,15 @@ def mlp_forward_raw(packed, precision, viewdirs, R, S, rays_o=None, rays_d=None,
     return raw, ws
 
 
-def mlp_forward_embedded_raw(packed, precision, emb):
+def mlp_forward_embedded_raw(packed, precision, emb, stash=None):
     emb = _dense(emb, "embedded", 2)
     if emb.shape[1] != 90:
         raise ValueError(f"embedded input must be [P, 90], got {tuple(emb.shape)}")
     P = emb.shape[0]
     raw = torch.empty(P, 4, device=emb.device, dtype=torch.float32)
     ws = _workspace(P, emb.device)
-    _lib.call("gbn_mlp_forward_embedded", _ptr(packed), PRECISION[precision], _ptr(emb), P, _ptr(raw), _ptr(ws), None,
-              _stream())
+    _lib.call("gbn_mlp_forward_embedded", _ptr(packed), PRECISION[precision], _ptr(emb), P, _ptr(raw), _ptr(ws),
+              _ptr(stash), _stream())
     return raw, ws
 
 
@@ -376,30 +376,16 @@ def torch_posenc(x, n_freqs):
     return torch.cat(parts, -1)
 
 
-def _torch_mlp(params, emb):
-    """Differentiable restatement (cuBLAS GEMMs on the device) used ONLY for parameter gradients of the two
-    variants the tcgen05 backward does not cover: tf32 modules and the pre-embedded NeRF.forward(x) form."""
-    W = lambda i: params[2 * i]
-    b = lambda i: params[2 * i + 1]
-    x_pts, x_dir = emb[:, :63], emb[:, 63:]
-    h = x_pts
-    for i in range(8):
-        h = torch.relu(torch.addmm(b(i), h, W(i).t()))
-        if i == 4:
-            h = torch.cat([x_pts, h], -1)
-    sigma = torch.addmm(b(9), h, W(9).t())
-    feat = torch.addmm(b(8), h, W(8).t())
-    hv = torch.relu(torch.addmm(b(10), torch.cat([feat, x_dir], -1), W(10).t()))
-    return torch.cat([torch.addmm(b(11), hv, W(11).t()), sigma], -1)
-
-
 class _Mlp(torch.autograd.Function):
     """raw = NeRF(embed(o + d z), embed(viewdir)).
 
-    Forward: the fused tcgen05 kernel; when parameter gradients are needed (bf16 modules) it also writes the
-    activation stash.  Backward: the tcgen05 dgrad kernel (same skeleton, transposed weights) then the tcgen05
-    wgrad kernel + two small CUDA-core kernels.  Inputs carry no gradient, exactly as in the reference where
-    z_samples is detached and rays are data (run.py:2346).
+    Forward: the fused tcgen05 kernel; when parameter gradients are needed it also writes the activation stash.
+    Backward: the tcgen05 dgrad kernel (same skeleton, transposed weights) then the tcgen05 wgrad kernel - for all three
+    input forms (rays + depths, explicit points, pre-embedded rows).  There is no other backward: tf32 modules are
+    inference-only and raise when a gradient is asked of them (the reference trains in fp32 through autograd of
+    run_nerf_helpers.py:106-129; here training is the bf16 path).  Inputs carry no gradient, exactly as in the
+    reference's loop where z_samples is detached and rays are data (run.py:2346); asking for one raises instead of
+    silently returning zeros.
     """
 
     @staticmethod
@@ -409,7 +395,14 @@ class _Mlp(torch.autograd.Function):
         # inside forward(): the caller's grad mode comes in as an argument, or every inference call would write the
         # training stash
         need_grad = grad_mode and any(ctx.needs_input_grad[7:])
-        ctx.native = need_grad and module.precision == "bf16" and mode in ("rays", "pts")
+        if grad_mode and any(ctx.needs_input_grad[3:7]):
+            raise NotImplementedError(
+                "gbnerf_b200: gradients with respect to rays / points / depths / embedded inputs are not implemented "
+                "(the reference's training loop needs none, run.py:2346); detach the inputs")
+        # parameter gradients exist for bf16 modules on the default kernels only; a tf32 module is inference-only: its
+        # forward runs as usual (callers often render without torch.no_grad()), asking it for a gradient raises
+        ctx.unsupported = need_grad and (module.precision != "bf16" or _lib.load().gbn_mlp_variant() != 1)
+        ctx.native = need_grad and not ctx.unsupported
         stash = None
         if mode == "rays":
             rays_o, rays_d, viewdirs, z = a0, a1, a2, a3
@@ -425,45 +418,36 @@ class _Mlp(torch.autograd.Function):
                 stash = _stash(R * S, pts.device)
             raw, ws = mlp_forward_raw(packed, module.precision, viewdirs, R, S, pts=pts.contiguous(), stash=stash)
         else:
-            raw, ws = mlp_forward_embedded_raw(packed, module.precision, a0)
+            R, S = a0.shape[0], 1
+            if ctx.native:
+                stash = _stash(R, a0.device)
+            raw, ws = mlp_forward_embedded_raw(packed, module.precision, a0, stash=stash)
+            viewdirs = a0[:, :3]            # placeholder: the wgrad of the default kernels takes directions from the stash
         module.last_workspace = ws
         ctx.mode, ctx.module = mode, module
         if ctx.native:
             ctx.stash, ctx.RS = stash, (R, S)
             ctx.save_for_backward(viewdirs)
             ctx.shapes = [tuple(p.shape) for p in params]
-        elif need_grad:
-            ctx.save_for_backward(*[t for t in (a0, a1, a2, a3) if t is not None], *params)
-            ctx.n_in = sum(t is not None for t in (a0, a1, a2, a3))
         return raw
 
     @staticmethod
     def backward(ctx, g_raw):
-        if ctx.native:
-            (viewdirs,) = ctx.saved_tensors
-            R, S = ctx.RS
-            grads, ws, _ = mlp_backward_raw(ctx.module.packed_weights_bwd(), g_raw.contiguous(), ctx.stash, viewdirs, R, S,
-                                            ctx.shapes)
-            ctx.module.last_workspace_bwd = ws
-            ctx.stash = None
-            return (None, None, None, None, None, None, None, *grads)
-        saved = ctx.saved_tensors
-        ins, params = saved[:ctx.n_in], saved[ctx.n_in:]
-        with torch.enable_grad():
-            ps = [p.detach().requires_grad_(True) for p in params]
-            if ctx.mode == "rays":
-                o, d, vd, z = ins
-                pts = o[:, None, :] + d[:, None, :] * z[:, :, None]
-                emb = torch.cat([torch_posenc(pts.reshape(-1, 3), 10),
-                                 torch_posenc(vd[:, None, :].expand(pts.shape).reshape(-1, 3), 4)], -1)
-            elif ctx.mode == "pts":
-                pts, vd = ins
-                emb = torch.cat([torch_posenc(pts.reshape(-1, 3), 10),
-                                 torch_posenc(vd[:, None, :].expand(pts.shape).reshape(-1, 3), 4)], -1)
-            else:
-                (emb,) = ins
-            out = _torch_mlp(ps, emb)
-            grads = torch.autograd.grad(out, ps, g_raw.reshape(out.shape))
+        if ctx.unsupported:
+            raise NotImplementedError(
+                "gbnerf_b200: parameter gradients exist for bf16 modules on the default kernels only - a tf32 module is "
+                "inference-only (construct the NeRF with precision='bf16' to train)")
+        if not ctx.native:
+            return (None,) * 7 + (None,) * 24
+        if ctx.stash is None:
+            raise RuntimeError("gbnerf_b200: backward through the same MLP call twice is not supported (the activation "
+                               "stash is released after the first pass; re-run the forward)")
+        (viewdirs,) = ctx.saved_tensors
+        R, S = ctx.RS
+        grads, ws, _ = mlp_backward_raw(ctx.module.packed_weights_bwd(), g_raw.contiguous(), ctx.stash, viewdirs, R, S,
+                                        ctx.shapes)
+        ctx.module.last_workspace_bwd = ws
+        ctx.stash = None
         return (None, None, None, None, None, None, None, *grads)
 
 

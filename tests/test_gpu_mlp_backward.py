@@ -171,7 +171,11 @@ def test_autograd_end_to_end(G):
             want = pr[name].grad
             got = q.grad.cpu()
             relerr = ((got - want).norm() / (want.norm() + 1e-12)).item()
-            assert relerr < 0.15, (name, relerr)
+            # bf16 activations / gradients through up to nine layers, ReLU gates of near-zero pre-activations flipping:
+            # measured <= 8 % on the full gradients and < 1 % on their norms (tools/grad_parity_probe.py); a corrupted
+            # tile (the round-1 gate race) is far outside both
+            assert relerr < 0.12, (name, relerr)
+            assert abs(got.norm().item() - want.norm().item()) <= 0.02 * want.norm().item() + 1e-9, (name, got.norm().item(), want.norm().item())
 
 
 def test_training_kernels_repeat_bit_exactly_from_a_cold_cache(G):

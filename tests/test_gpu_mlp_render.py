@@ -13,6 +13,7 @@ from oracle import nerf_oracle as O
 pytestmark = pytest.mark.gpu
 
 TOL = {"bf16": 2e-2, "tf32": 1e-3}
+GNORM_TOL, GRAD_TOL = 0.02, 0.12     # native bf16 backward vs the reference's fp32 gradients (measured by tools/grad_parity_probe.py: norms within 0.7 %, full gradients within 7.8 %)
 
 
 @pytest.fixture(scope="module")
@@ -152,12 +153,14 @@ def test_render_test_kwargs_golden(G, golden, params, precision):
     assert rgb.shape == (48, 3) and ex["weights"].shape == (48, 128) and ex["raw"].shape == (48, 128, 4)
 
 
-@pytest.mark.parametrize("precision", ["tf32"])
-def test_render_train_kwargs_golden(G, golden, params, precision):
-    """Train kwargs with the reference's RNG stream replayed (t_rand -> noise0 -> u -> noise1), forward, loss and
-    parameter gradients."""
+def test_render_train_kwargs_golden(G, golden, params):
+    """Train kwargs with the reference's RNG stream replayed (t_rand -> noise0 -> u -> noise1): forward, loss and the
+    parameter gradients of the NATIVE backward (tcgen05 dgrad + wgrad, bf16) against the unmodified reference's fp32
+    autograd (tests/golden/render_train.npz): every parameter's gradient norm and the full gradients the golden carries.
+    Bounds: what bf16 storage of activations / gradients gives on this batch with head-room (tools/grad_parity_probe.py
+    prints the measured figures; a corrupted tile - the round-1 race - moves them by far more)."""
     g = golden("render_train.npz")
-    nets, nq = build_path(G, params, precision)
+    nets, nq = build_path(G, params, "bf16")
     rays = g["rays"].cuda()
     rnd = {k: g[k].cuda() for k in ("t_rand", "noise0", "u", "noise1")}
     ret = G.render_rays(rays, nets[0], nq, 64, retraw=True, lindisp=True, perturb=1.0, N_importance=64,
@@ -165,14 +168,56 @@ def test_render_train_kwargs_golden(G, golden, params, precision):
     loss = G.img2mse(ret["rgb_map"], g["target_rgb"].cuda()) + G.img2mse(ret["rgb0"], g["target_rgb"].cuda()) \
         + 0.1 * G.img2mse(ret["disp_map"], g["target_disp"].cuda())
     loss.backward()
-    assert (ret["rgb0"].cpu() - g["rgb0"]).abs().max().item() < TOL[precision]
-    assert (ret["rgb_map"].cpu() - g["rgb_map"]).abs().max().item() < 2.5 * TOL[precision]
+    assert G.ops.mlp_error_code(nets[1].last_workspace_bwd) == 0 and G.ops.mlp_error_code(nets[0].last_workspace_bwd) == 0
+    assert (ret["rgb0"].cpu() - g["rgb0"]).abs().max().item() < TOL["bf16"]
+    assert (ret["rgb_map"].cpu() - g["rgb_map"]).abs().max().item() < 2.5 * TOL["bf16"]
     assert abs(loss.item() - g["loss"].item()) < 5e-3 * max(1.0, abs(g["loss"].item()))
     for tag, net in (("c", nets[0]), ("f", nets[1])):
         for name, p in net.named_parameters():
             want = g[f"gnorm_{tag}_{name}"].item()
             got = p.grad.norm().item()
-            assert abs(got - want) <= 0.05 * want + 1e-6, (tag, name, got, want)
+            assert abs(got - want) <= GNORM_TOL * want + 1e-6, (tag, name, got, want)
+            if f"grad_{tag}_{name}" in g.keys():
+                w = g[f"grad_{tag}_{name}"]
+                rel = ((p.grad.cpu() - w).norm() / w.norm()).item()
+                assert rel < GRAD_TOL, (tag, name, rel)
+
+
+def test_tf32_modules_are_inference_only(G, params):
+    """No cuBLAS / eager fallback behind the native backward: a tf32 module renders, asking it for gradients raises."""
+    nets, nq = build_path(G, params, "tf32")
+    rays = O.synthetic_rays(16, seed=1).cuda()
+    ret = G.render_rays(rays, nets[0], nq, 64, lindisp=True, perturb=0., N_importance=64, network_fine=nets[1],
+                        white_bkgd=True, raw_noise_std=0.)
+    with pytest.raises(NotImplementedError, match="inference-only"):
+        ret["rgb_map"].sum().backward()
+    with pytest.raises(NotImplementedError, match="not implemented"):
+        nets_b, nq_b = build_path(G, params, "bf16")
+        z = torch.rand(16, 8, device="cuda").sort(-1)[0].requires_grad_(True)
+        nets_b[0].forward_rays(rays[:, 0:3], rays[:, 3:6], rays[:, 8:11], z)
+
+
+def test_embedded_form_uses_the_native_backward(G, params):
+    """NeRF.forward(x) on pre-embedded rows (the reference module's own signature): gradients come from the same tcgen05
+    dgrad + wgrad kernels and agree with fp32 autograd of the oracle network within bf16 tolerance; a second backward
+    through the same call is refused with a clear message."""
+    net = make_net(G, params[0], "bf16")
+    g = torch.Generator().manual_seed(3)
+    pts = torch.rand(300, 3, generator=g) * 4 - 2
+    dirs = torch.nn.functional.normalize(torch.randn(300, 3, generator=g), dim=-1)
+    emb = torch.cat([O.posenc(pts, 10), O.posenc(dirs, 4)], -1)
+    out = net(emb.cuda())
+    go = torch.randn(300, 4, generator=g)
+    out.backward(go.cuda(), retain_graph=True)
+    prm = {k: v.clone().requires_grad_(True) for k, v in params[0].items()}
+    want = O.mlp_forward(prm, emb)
+    want.backward(go)
+    assert (out.detach().cpu() - want.detach()).abs().max().item() < TOL["bf16"]
+    for name, p in net.named_parameters():
+        rel = ((p.grad.cpu() - prm[name].grad).norm() / (prm[name].grad.norm() + 1e-12)).item()
+        assert rel < 0.06, (name, rel)
+    with pytest.raises(RuntimeError, match="twice"):
+        out.backward(go.cuda())
 
 
 def test_render_rays_pieces_consistent(G, params):

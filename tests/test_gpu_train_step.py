@@ -87,9 +87,11 @@ def test_eager_train_step_equals_autograd_path(G):
     grads_b = [g for gs in ts.grads for g in gs]
     for i, (ga, gb) in enumerate(zip(grads_a, grads_b)):
         assert rel(gb, ga) < 1e-4, (i, rel(gb, ga))
-    for na, nb in zip(nets_a, nets_b):
+    init = (O.init_params(0), O.init_params(None))
+    for na, nb, p0 in zip(nets_a, nets_b, init):
         for (name, pa), (_, pb) in zip(na.named_parameters(), nb.named_parameters()):
-            assert (pa - pb).abs().max().item() < 2e-5, name          # one Adam step moves every weight by ~lr = 3e-3
+            moved = (pa.detach().cpu() - p0[name]).norm().item()   # one Adam step moves every weight by ~lr = 3e-3
+            assert (pa - pb).norm().item() <= 0.02 * moved, name
         # the kernel patched the bf16 images in place: identical to a fresh re-pack of the new weights
         # (re-packing over a copy: bytes the packer never writes - alignment gaps - keep their old content)
         fwd, bwd = nb.packed_weights(), nb.packed_weights_bwd()
@@ -118,12 +120,16 @@ def test_graphed_train_step_replays(G):
         res.append((losses, [p.detach().clone() for n in nets for p in n.param_list()]))
         if graph:
             assert ts.launches_per_step is not None and ts.launches_per_step >= 14
+    init = [v for p in (O.init_params(0), O.init_params(None)) for v in p.values()]
     (l0, p0), (l1, p1) = res
     for a, b in zip(l0, l1):
         assert abs(a - b) < 1e-5 * max(1.0, abs(a)), (l0, l1)
     assert l0[2] != l0[0]
-    for a, b in zip(p0, p1):
-        assert (a - b).abs().max().item() < 5e-5
+    # wgrad sums with atomics (order-dependent rounding) and Adam divides by sqrt(v): an element whose gradient is
+    # rounding noise can move by a full step either way, so the two runs are compared against the size of the update
+    for a, b, p0_ in zip(p0, p1, init):
+        moved = (a.cpu() - p0_).norm().item()
+        assert moved > 0 and (a - b).norm().item() <= 0.02 * moved, ((a - b).norm().item(), moved)
 
 
 def test_graphed_train_step_draws_fresh_randoms(G):
