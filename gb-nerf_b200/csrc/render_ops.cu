@@ -546,7 +546,7 @@ __device__ __forceinline__ void seg_bitonic_sort(float (&v)[KN], int l) {
 }
 
 template <int LANES, int KN, bool DET>
-__global__ void __launch_bounds__(kThreads) sample_merge_cons_kernel(const float* __restrict__ z_vals,
+__global__ void __launch_bounds__(kThreads, 4) sample_merge_cons_kernel(const float* __restrict__ z_vals,
                                                                      const float* __restrict__ weights,
                                                                      const float* __restrict__ u,
                                                                      const float* __restrict__ cdf_in, int64_t R,
@@ -570,11 +570,41 @@ __global__ void __launch_bounds__(kThreads) sample_merge_cons_kernel(const float
   int* const hist = reinterpret_cast<int*>(mrg + S + N);                       // S + 4 counters
   const int64_t ngroups = (R + RPW - 1) / RPW;
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
-  for (int64_t grp = (int64_t)blockIdx.x * kWarpsPerBlock + wib; grp < ngroups; grp += nwarps) {
+  // operands of the NEXT group are fetched into registers while the current one is processed: the loop body is a long
+  // dependent chain (scan -> search -> merge), and without the prefetch every iteration also paid a full DRAM round trip
+  float4 zq_n = make_float4(0.f, 0.f, 0.f, 0.f), wq_n = zq_n;
+  float u_n[DET ? 1 : KN];
+  auto fetch = [&](int64_t g) {
+    const int64_t r0 = g * RPW + sub;
+    const int64_t r1 = r0 < R ? r0 : R - 1;                                    // the odd last half-warp re-does the last ray
+    zq_n = ld_stream4(reinterpret_cast<const float4*>(z_vals + r1 * S + l * 4));
+    if (cdf_in == nullptr) wq_n = ld_stream4(reinterpret_cast<const float4*>(weights + r1 * S + l * 4));
+    if (!DET) {
+      if (KN == 2) {
+        const float2 q = *reinterpret_cast<const float2*>(u + r1 * N + l * KN);
+        u_n[0] = q.x; u_n[KN > 1 ? 1 : 0] = q.y;
+      } else {
+#pragma unroll
+        for (int k = 0; k < KN; k += 4) {
+          const float4 q = ld_stream4(reinterpret_cast<const float4*>(u + r1 * N + l * KN + k));
+          u_n[k] = q.x; u_n[k + 1 < KN ? k + 1 : k] = q.y; u_n[k + 2 < KN ? k + 2 : k] = q.z; u_n[k + 3 < KN ? k + 3 : k] = q.w;
+        }
+      }
+    }
+  };
+  const int64_t grp0 = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
+  if (grp0 < ngroups) fetch(grp0);
+  for (int64_t grp = grp0; grp < ngroups; grp += nwarps) {
     const int64_t ray = grp * RPW + sub;
     const bool valid = ray < R;
-    const int64_t rr = valid ? ray : R - 1;                                    // the odd last half-warp re-does the last ray
-    const float4 zq = *reinterpret_cast<const float4*>(z_vals + rr * S + l * 4);
+    const int64_t rr = valid ? ray : R - 1;
+    const float4 zq = zq_n, wq = wq_n;
+    float uu[KN];
+    if (!DET) {
+#pragma unroll
+      for (int k = 0; k < KN; ++k) uu[k] = u_n[k];
+    }
+    if (grp + nwarps < ngroups) fetch(grp + nwarps);
     const float zz[4] = {zq.x, zq.y, zq.z, zq.w};
     *reinterpret_cast<float4*>(zv + l * 4) = zq;
     float c[4];
@@ -582,7 +612,6 @@ __global__ void __launch_bounds__(kThreads) sample_merge_cons_kernel(const float
 #pragma unroll
       for (int k = 0; k < 4; ++k) c[k] = (l * 4 + k < B) ? __ldg(cdf_in + rr * B + l * 4 + k) : 1.f;
     } else {
-      const float4 wq = *reinterpret_cast<const float4*>(weights + rr * S + l * 4);
       const float ww[4] = {wq.x, wq.y, wq.z, wq.w};
       float run = 0.f;
 #pragma unroll
@@ -612,19 +641,10 @@ __global__ void __launch_bounds__(kThreads) sample_merge_cons_kernel(const float
     }
     __syncwarp();
     // ---- KN consecutive samples per lane --------------------------------------------------------------------------
-    float uu[KN], sv[KN];
+    float sv[KN];
     if (DET) {
 #pragma unroll
       for (int k = 0; k < KN; ++k) uu[k] = linspace01(l * KN + k, N);
-    } else if (KN == 2) {
-      const float2 q = *reinterpret_cast<const float2*>(u + rr * N + l * KN);
-      uu[0] = q.x; uu[1] = q.y;
-    } else {
-#pragma unroll
-      for (int k = 0; k < KN; k += 4) {
-        const float4 q = *reinterpret_cast<const float4*>(u + rr * N + l * KN + k);
-        uu[k] = q.x; uu[k + 1 < KN ? k + 1 : k] = q.y; uu[k + 2 < KN ? k + 2 : k] = q.z; uu[k + 3 < KN ? k + 3 : k] = q.w;
-      }
     }
     float sum = 0.f;
     int los[KN];
@@ -715,8 +735,10 @@ static int launch_sample_merge_cons(const float* z_vals, const float* weights, c
   constexpr int S = 4 * LANES, N = KN * LANES, RPW = 32 / LANES;
   constexpr size_t smem = (size_t)kWarpsPerBlock * RPW * (5 * S + 2 * N + 4) * sizeof(float);
   static_assert(smem <= 48 * 1024, "sample_merge_cons: shared memory above the default limit");
+  // resident CTAs per SM: 4 by registers (__launch_bounds__(256, 4), <= 64 registers), fewer if shared memory says so; a
+  // persistent grid larger than what is resident runs its surplus CTAs as a second, half-empty wave
   const int per_sm = (int)((200 * 1024) / smem);
-  const int grid = persistent_grid((R + RPW - 1) / RPW, per_sm > 8 ? 8 : per_sm);
+  const int grid = persistent_grid((R + RPW - 1) / RPW, per_sm > 4 ? 4 : per_sm);
   if (u) sample_merge_cons_kernel<LANES, KN, false><<<grid, kThreads, smem, stream>>>(z_vals, weights, u, cdf_in, R, z_samples, z_merged, z_std, inds_out);
   else sample_merge_cons_kernel<LANES, KN, true><<<grid, kThreads, smem, stream>>>(z_vals, weights, u, cdf_in, R, z_samples, z_merged, z_std, inds_out);
   return check_launch("sample_merge_cons_kernel");

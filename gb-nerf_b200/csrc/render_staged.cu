@@ -776,8 +776,8 @@ static int launch_fwd_seg(const float* raw, const float* z, const float* rays_d,
                           cudaStream_t stream) {
   constexpr int D = 2;
   const size_t smem = (size_t)kSegWarps * D * 128 * M * (noise ? 24 : 20);
-  const int per_sm = (int)((200 * 1024) / smem) < 1 ? 1 : (int)((200 * 1024) / smem);
-  const int64_t blocks = (R + kSegWarps - 1) / kSegWarps, cap = (int64_t)kNumSMs * (per_sm > 6 ? 6 : per_sm);
+  const int per_sm = (int)((227 * 1024) / (smem + 1024)) < 1 ? 1 : (int)((227 * 1024) / (smem + 1024));   // 1 KB per CTA is reserved
+  const int64_t blocks = (R + kSegWarps - 1) / kSegWarps, cap = (int64_t)kNumSMs * (per_sm > 8 ? 8 : per_sm);
   const int grid = (int)(blocks < cap ? blocks : cap);
   static bool attr = false;
   if (!attr) {
@@ -796,8 +796,8 @@ static int launch_bwd_seg2(const float* raw, const float* z, const float* rays_d
                            const float* g_depth, const float* g_w, float* g_raw, cudaStream_t stream) {
   constexpr int D = 2;
   constexpr size_t smem = (size_t)kSegWarps * D * 128 * M * (20 + (NOISE ? 4 : 0) + (GW ? 4 : 0));
-  constexpr int per_sm = (int)((200 * 1024) / smem) < 1 ? 1 : (int)((200 * 1024) / smem);
-  const int64_t blocks = (R + kSegWarps - 1) / kSegWarps, cap = (int64_t)kNumSMs * (per_sm > 6 ? 6 : per_sm);
+  constexpr int per_sm = (int)((227 * 1024) / (smem + 1024)) < 1 ? 1 : (int)((227 * 1024) / (smem + 1024));   // 1 KB per CTA is reserved
+  const int64_t blocks = (R + kSegWarps - 1) / kSegWarps, cap = (int64_t)kNumSMs * (per_sm > 8 ? 8 : per_sm);
   const int grid = (int)(blocks < cap ? blocks : cap);
   static bool attr = false;
   if (!attr) {
@@ -838,7 +838,9 @@ int launch_composite_bwd_staged(const float* raw, const float* z, const float* r
     return 1;
   }
   if (S != 64 && S != 128) return 0;
-  const int64_t blocks = (R + kStWarps - 1) / kStWarps, cap = (int64_t)kNumSMs * 4;
+  // persistent grid = what is resident: 4 CTAs per SM at K = 2, 3 at K = 4 (80 registers; __launch_bounds__ above) - a
+  // fourth CTA per SM would run as a second, mostly empty wave
+  const int64_t blocks = (R + kStWarps - 1) / kStWarps, cap = (int64_t)kNumSMs * (S == 64 ? 4 : 3);
   const int grid = (int)(blocks < cap ? blocks : cap);
 #define GBN_BW_LAUNCH(KK, NN, GG)                                                                                       \
   do {                                                                                                                  \

@@ -247,7 +247,13 @@ def test_sample_pdf_merge_indices_bit_exact_on_the_production_kernel(G, det, S, 
         w[2, 1:S // 2] = 0.                                  # runs of (almost) equal cdf values
     cdf = O.build_cdf(w[:, 1:-1]).contiguous()
     if det:
-        u, uu = None, torch.linspace(0., 1., N, device="cuda").cpu().expand(R, N).contiguous()
+        # the uniforms of the deterministic branch are torch.linspace(0, 1, N) (helpers:314): the kernel evaluates ATen's
+        # two-sided fp32 formula (csrc/common.cuh linspace01), restated here operation for operation
+        step = np.float32(1.) / np.float32(N - 1)
+        lin = np.array([step * np.float32(i) if i < N // 2 else np.float32(1.) - step * np.float32(N - i - 1) for i in range(N)],
+                       dtype=np.float32)
+        assert np.abs(lin - torch.linspace(0., 1., N).numpy()).max() <= 6e-8     # (torch's CPU and CUDA kernels differ in the last bit too)
+        u, uu = None, torch.from_numpy(lin).expand(R, N).contiguous()
     else:
         u = torch.rand(R, N, generator=g)
         u[:, 0] = cdf[:, (S - 1) // 2]                       # exact hits on a cdf value

@@ -117,7 +117,7 @@ def test_graphed_train_step_replays(G):
             losses.append(ts.step(rays, tgt, tgd).item())
         assert ts.error_codes() == [0, 0, 0, 0]
         assert opt.state_dict()["state"][0]["step"] == 3
-        res.append((losses, [p.detach().clone() for n in nets for p in n.param_list()]))
+        res.append((losses, [p.detach().clone() for n in nets for _, p in n.named_parameters()]))
         if graph:
             assert ts.launches_per_step is not None and ts.launches_per_step >= 14
     init = [v for p in (O.init_params(0), O.init_params(None)) for v in p.values()]
