@@ -44,6 +44,39 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def measure_tf32_peak(dev, sustained_s=3.0):
+    """Dense tf32 peak the way MEASURED_PEAKS.json takes the bf16 one: torch.matmul (cuBLAS) on 8192^3 fp32 operands with
+    TF32 allowed, best of 10 (burst) and back to back for `sustained_s` seconds (sustained, under the power cap)."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a, b = torch.randn(n, n, device=dev), torch.randn(n, n, device=dev)
+        c = torch.empty(n, n, device=dev)
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        torch.cuda.synchronize(dev)
+        best = None
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(a, b, out=c); e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        reps = max(10, int(sustained_s * 1e3 / best))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        flop = 2.0 * n ** 3
+        return {"tf32_tflops": flop / (best * 1e-3) / 1e12, "tf32_tflops_sustained": flop * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12,
+                "how": f"torch.matmul fp32 {n}^3 with allow_tf32 (cuBLAS): best of 10 (burst) and {reps} back to back (sustained)"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -233,13 +266,17 @@ def run_ours(args, rank, world, local_rank):
     mlp_ms = [a.elapsed_time(b) for (name, a, b, pts) in events if name == "mlp"]
     mlp_pts = sum(pts for (name, a, b, pts) in events if name == "mlp")
     achieved = mlp_pts * FLOP_PER_POINT / (sum(mlp_ms) * 1e-3) / 1e12 if mlp_ms else None
-    peak = pk["bf16_tflops_sustained"]
+    peak, peak_source = pk["bf16_tflops_sustained"], pk["source"] + " bf16 sustained"
+    tf32_peaks = None
+    if args.precision == "tf32":      # no tf32 figure in MEASURED_PEAKS.json: measured here, same method
+        tf32_peaks = measure_tf32_peak(dev)
+        peak, peak_source = tf32_peaks["tf32_tflops_sustained"], "measured in this run: cuBLAS tf32 sustained"
     variant = os.environ.get("GBNERF_MLP", "ts") if args.precision == "bf16" else "ss"   # csrc/mlp_aux.cu mlp_variant()
     mlp_kernel_name = {"ts": "nerf_mlp_ts_kernel"}.get(variant, "nerf_mlp_kernel")
     traffic = profile_traffic_bytes()
     roofline = {"kernel": f"{mlp_kernel_name}<{args.precision}> (fused point generation + posenc + 8x256 MLP)",
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak if achieved else None, "peak_source": pk["source"] + " bf16 sustained",
+                "frac": achieved / peak if achieved else None, "peak_source": peak_source, "tf32_peaks": tf32_peaks,
                 "traffic": traffic,
                 "traffic_source": "profiles/r1_mlp_ts_ncu_full.md (dram read+write of the 32768x128 fine-pass launch, ncu --set full)"
                 if traffic else None, "launches_timed": len(mlp_ms), "avg_launch_ms": sum(mlp_ms) / max(1, len(mlp_ms)),

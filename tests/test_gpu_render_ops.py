@@ -29,7 +29,7 @@ def rel_close(a, b, rtol=1e-5, atol=1e-6):
 # ---- stratified depths ------------------------------------------------------------------------------------ #
 @pytest.mark.parametrize("lindisp", [False, True])
 @pytest.mark.parametrize("perturb", [False, True])
-@pytest.mark.parametrize("S", [1, 2, 64, 128, 193])
+@pytest.mark.parametrize("S", [1, 2, 32, 64, 128, 193, 256])
 def test_zvals(G, lindisp, perturb, S):
     g = torch.Generator().manual_seed(7)
     R = 301
