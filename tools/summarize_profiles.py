@@ -47,7 +47,10 @@ WANT = ["gpu__time_duration.sum", "TPC.TriageCompute.sm__pipe_tensor_cycles_acti
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum ", "launch__registers_per_thread", "launch__grid_size",
         "launch__block_size", "launch__shared_mem_per_block_dynamic", "sm__warps_active.avg.pct_of_peak_sustained_active",
-        "smsp__inst_executed.sum ", "sm__inst_executed_pipe_uniform", "launch__occupancy_limit"]
+        "smsp__inst_executed.sum ", "sm__inst_executed_pipe_uniform", "launch__occupancy_limit",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
+        "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_barrier_per_warp_active.pct",
+        "smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_wait_per_warp_active.pct"]
 
 
 def full(src, dst, cmd):
