@@ -42,6 +42,23 @@ __constant__ TsJob c_tsjobs[2][kTsMaxJobs];
 __constant__ TsStep c_tssteps[2][kTsMaxSteps];
 __constant__ TsPackJob c_tspack[2][kTsMaxJobs];
 
+// One issuer's view of one of its jobs, fully resolved on the host (ts_build_issue): see ts_issue_loop.
+enum : uint16_t { TI_A_SMEM = 1, TI_A_DIR = 2, TI_FIRST = 4, TI_PREV_OTHER = 8, TI_NEXT_OTHER = 16, TI_SIGNAL_ORDER = 32 };
+struct TsIssue {
+  uint32_t w[5];        // waits before the job: barrier offset from L::bars (bits 0-15) | odd(completions per tile) << 16 |
+                        // (index of the awaited completion within the tile & 1) << 17 | valid << 31
+  uint32_t wsplit;      // dgrad: barrier of the second instalment of input half 1, waited for in mid-issue (same encoding)
+  uint32_t idesc;       // tcgen05 instruction descriptor
+  uint16_t d_col, a_col;
+  uint16_t jidx;        // index of the job in the tile's job list: ring slot = tile * njobs + jidx
+  uint16_t flags;       // TI_*
+  uint8_t ksteps, nkb, n16, pad;
+  uint16_t commit[3];   // barriers (offsets from L::bars) committed after the job besides the stage's w_empty; 0xffff = none
+  uint16_t pad2;
+};
+static_assert(sizeof(TsIssue) == 48, "TsIssue layout");
+__constant__ TsIssue c_tsissue[2][2][kTsMaxJobs];
+
 #ifdef GBN_TS_DIAG
 constexpr bool kDiag = true;
 #else
@@ -96,6 +113,7 @@ struct TsArgs {
   int trace_tile;
   int64_t stride, P;
   int S, njobs, nsteps;
+  int nissue[2];           // records of issuer 0 / 1 in c_tsissue[program]
   int ready_per_tile[4];
   int order_per_tile;
   int empty1_per_tile;
@@ -232,6 +250,123 @@ __device__ __forceinline__ uint4 ld_smem16(uint32_t addr) {
   return r;
 }
 
+
+// =============================== MMA issuers ===================================================================
+// Two warps: warp 1 issues every job that accumulates into acc0 (WHO = 0), warp 3 those into acc1 (WHO = 1).  The halves
+// are independent accumulators, so no ordering is needed between the two instruction streams; what it buys is that
+// one warp's barrier waits / bookkeeping overlap the other's MMAs.  Each loop is warp-uniform; one elected lane issues.
+//
+// Round 2: the issuing thread was the pace-setter of the whole kernel (in-kernel trace: ~1400 cycles from one job to
+// the next for 512 cycles of tensor work - the TsJob record was decoded field by field, every wait re-derived its
+// barrier and parity from per-tile counters, jobs of the other issuer were walked and skipped).  The host now resolves
+// each issuer's own jobs into TsIssue records (ts_build_issue): final barrier offsets with a two-bit parity rule per
+// wait, the instruction descriptor, the commit targets - and the loop below only loads a record and executes it.
+// The protocol (which barriers, in which order of jobs) is exactly that of the TsJob table; tests/ts_protocol_model.py
+// keeps checking that table.
+template <bool BWD, int WHO>
+__device__ __forceinline__ void ts_issue_loop(const TsArgs& a, uint32_t base, uint32_t abort_addr, uint32_t tmem, int my_tiles,
+                                              int lane) {
+  using L = TsSmemT<BWD>;
+  constexpr int kTsStages = L::NST;
+  constexpr int PROG = BWD ? 1 : 0;
+  const TsIssue* recs = c_tsissue[PROG][WHO];
+  const int nrec = a.nissue[WHO];
+  const uint64_t adesc_enc = smem_desc_sw128(base + L::enc);
+  const uint64_t adesc_dir = smem_desc_sw128(base + L::dir);
+  const uint64_t ring_desc0 = smem_desc_sw128(base + L::ring);
+  const uint32_t bars = base + L::bars;
+  for (int t = 0; t < my_tiles; ++t) {
+    const uint32_t cnt0 = (uint32_t)t * (uint32_t)a.njobs;
+    for (int i = 0; i < nrec; ++i) {
+      const TsIssue rc = recs[i];
+      const uint32_t cnt = cnt0 + rc.jidx;
+      unsigned long long* tr = (a.trace && blockIdx.x == 0 && t == a.trace_tile && lane == 0) ? a.trace : nullptr;
+      if (tr) tr[4 * rc.jidx] = clock64();
+      ts_chaos(a.chaos, 2u * cnt, a.chaos_roles & 2u);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const uint32_t w = rc.w[k];
+        if (w & 0x80000000u)   // parity of completion t * per_tile + idx: ((t & odd(per_tile)) ^ idx) & 1
+          ts_wait(bars + (w & 0xffffu), (((uint32_t)t & (w >> 16)) ^ (w >> 17)) & 1u, abort_addr, a.err,
+                  0x20000000 | (k << 20) | rc.jidx);
+      }
+      // (Probing all of a job's barriers at once - each probe is a ~130-cycle round trip to the barrier unit even when the
+      // phase is long complete - was tried in round 2 and is slower: 903 against ~1000 TFLOP/s; so is polling with
+      // test_wait instead of try_wait: no difference.)
+      const uint32_t s = cnt % kTsStages, par = (cnt / kTsStages) & 1;
+      ts_chaos(a.chaos, 2u * cnt + 1u, a.chaos_roles & 2u);
+      if (tr) tr[4 * rc.jidx + 1] = clock64();
+      if ((rc.flags & TI_PREV_OTHER) && cnt >= (uint32_t)kTsStages)
+        ts_wait_progress(base + L::prog + (WHO ? 0u : 4u), cnt - kTsStages + 1, abort_addr, a.err, 0x26000000 | rc.jidx);
+      ts_wait(base + L::w_full + 8 * s, par, abort_addr, a.err, 0x22000000 | rc.jidx);
+      if (tr) tr[4 * rc.jidx + 2] = clock64();
+      tc_fence_after_sync();
+      const uint64_t bd0 = ring_desc0 + (uint64_t)(s * (kTsStageBytes >> 4));
+      const uint64_t bd1 = bd0 + (uint64_t)((uint32_t)rc.n16 * 128u);            // second K-block image: N rows x 128 B on
+      const uint32_t idesc = rc.idesc;
+      const uint32_t d = tmem + rc.d_col;
+      const uint32_t a_t = tmem + rc.a_col;
+      const uint32_t first = (rc.flags & TI_FIRST) ? 0u : 1u;
+      const bool split = (rc.wsplit & 0x80000000u) != 0u;
+      if (split) {   // K-high job of the dgrad program: the four MMAs whose K ranges arrived first, then the rest
+        if (elect_one()) {
+          umma_bf16_ts(d, a_t, bd0, idesc, first);
+          umma_bf16_ts(d, a_t + 8, bd0 + 2, idesc, 1u);
+          umma_bf16_ts(d, a_t + 32, bd1, idesc, 1u);
+          umma_bf16_ts(d, a_t + 40, bd1 + 2, idesc, 1u);
+        }
+        __syncwarp();
+        ts_chaos(a.chaos, 0x40000000u + cnt, a.chaos_roles & 2u);
+        ts_wait(bars + (rc.wsplit & 0xffffu), (((uint32_t)t & (rc.wsplit >> 16)) ^ (rc.wsplit >> 17)) & 1u, abort_addr, a.err,
+                0x21e00000 | rc.jidx);
+        tc_fence_after_sync();
+      }
+      if (elect_one()) {
+        if (split) {
+          umma_bf16_ts(d, a_t + 16, bd0 + 4, idesc, 1u);
+          umma_bf16_ts(d, a_t + 24, bd0 + 6, idesc, 1u);
+          umma_bf16_ts(d, a_t + 48, bd1 + 4, idesc, 1u);
+          umma_bf16_ts(d, a_t + 56, bd1 + 6, idesc, 1u);
+        } else if (!(rc.flags & TI_A_SMEM) && rc.nkb == 2) {          // the common job: 8 back-to-back MMAs, A from TMEM
+          umma_bf16_ts(d, a_t, bd0, idesc, first);
+          umma_bf16_ts(d, a_t + 8, bd0 + 2, idesc, 1u);
+          umma_bf16_ts(d, a_t + 16, bd0 + 4, idesc, 1u);
+          umma_bf16_ts(d, a_t + 24, bd0 + 6, idesc, 1u);
+          umma_bf16_ts(d, a_t + 32, bd1, idesc, 1u);
+          umma_bf16_ts(d, a_t + 40, bd1 + 2, idesc, 1u);
+          umma_bf16_ts(d, a_t + 48, bd1 + 4, idesc, 1u);
+          umma_bf16_ts(d, a_t + 56, bd1 + 6, idesc, 1u);
+        } else if (rc.flags & TI_A_SMEM) {           // encoding / direction block (4 / 2 steps), padded g_raw block (1 step)
+          const uint64_t adesc = (rc.flags & TI_A_DIR) ? adesc_dir : adesc_enc;
+          umma_bf16(d, adesc, bd0, idesc, first);
+          if (rc.ksteps >= 2) umma_bf16(d, adesc + 2, bd0 + 2, idesc, 1u);
+          if (rc.ksteps == 4) {
+            umma_bf16(d, adesc + 4, bd0 + 4, idesc, 1u);
+            umma_bf16(d, adesc + 6, bd0 + 6, idesc, 1u);
+          }
+        } else {                                     // single K-block from TMEM (not used by the current plans)
+          umma_bf16_ts(d, a_t, bd0, idesc, first);
+          umma_bf16_ts(d, a_t + 8, bd0 + 2, idesc, 1u);
+          umma_bf16_ts(d, a_t + 16, bd0 + 4, idesc, 1u);
+          umma_bf16_ts(d, a_t + 24, bd0 + 6, idesc, 1u);
+        }
+        umma_commit(base + L::w_empty + 8 * s);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          if (rc.commit[k] != 0xffffu) umma_commit(bars + rc.commit[k]);
+        if (rc.flags & TI_SIGNAL_ORDER) mbar_arrive(base + L::order);
+      }
+      __syncwarp();
+      // this stage's next job is the other issuer's: tell it that the fill just consumed has landed (after the MMAs
+      // have been issued, off the critical path; shared memory is coherent within the CTA and both sides use volatile
+      // accesses in program order after / before their mbarrier tests)
+      if ((rc.flags & TI_NEXT_OTHER) && lane == 0)
+        asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(base + L::prog + (WHO ? 4u : 0u)), "r"(cnt + 1) : "memory");
+      if (tr) tr[4 * rc.jidx + 3] = clock64();
+    }
+  }
+}
+
 template <bool BWD>
 __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs a) {
   using L = TsSmemT<BWD>;
@@ -293,137 +428,10 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
         __syncwarp();
         ++cnt;
       }
-  } else if (warp == 1 || warp == 3) {
-    // =============================== MMA issuers ===============================================================
-    // Two warps: warp 1 issues every job that accumulates into acc0, warp 3 those into acc1.  The halves are
-    // independent accumulators, so no ordering is needed between the two instruction streams; what it buys is that
-    // one warp's barrier waits / job bookkeeping (~500 cycles per job, the tensor queue is shallow) overlap the
-    // other's MMAs.  Each loop is warp-uniform; one elected lane issues.
-    const bool second = (warp == 3);
-    uint32_t cnt = 0;
-    constexpr int kAnyWait = TJ_WAIT_ENC | TJ_WAIT_TILE | TJ_WAIT_A0 | TJ_WAIT_A1 | TJ_WAIT_DIR;
-    const uint64_t adesc_enc = smem_desc_sw128(base + L::enc);
-    const uint64_t adesc_dir = smem_desc_sw128(base + L::dir);
-    TsJob nxt = jobs[0];
-    for (int t = 0; t < my_tiles; ++t)
-      for (int j = 0; j < a.njobs; ++j) {
-        const TsJob jb = nxt;
-        nxt = jobs[j + 1 < a.njobs ? j + 1 : 0];   // constant-memory fetch of the next job overlaps this one
-        // (Letting each issuer also wait for the fills of the OTHER issuer's jobs, so that it sees every phase of every
-        // stage, does not work: a warp that reaches such a wait two fills late sees the parity it expects to flip and
-        // blocks until the fill after that, which may be one only it can release.  Tried in round 2: launch failures.)
-        if ((jb.d_col >= kTsAcc1) != second) { ++cnt; continue; }
-        unsigned long long* tr = (a.trace && blockIdx.x == 0 && t == a.trace_tile && lane == 0) ? a.trace : nullptr;
-        if (tr) tr[4 * j] = clock64();
-        bool split = false;
-        uint32_t split_par = 0, split_bar = 0;
-        ts_chaos(a.chaos, 2u * cnt, a.chaos_roles & 2u);
-        if (jb.flags & kAnyWait) {
-          if (jb.flags & TJ_WAIT_ENC) ts_wait(base + L::enc_full, t & 1, abort_addr, a.err, 0x20000000 | j);
-          if (jb.flags & TJ_WAIT_DIR) ts_wait(base + L::dir_full, t & 1, abort_addr, a.err, 0x20800000 | j);
-          if ((jb.flags & TJ_WAIT_TILE) && t > 0) ts_wait(base + L::tile_done, (t - 1) & 1, abort_addr, a.err, 0x23000000 | j);
-          if (jb.flags & TJ_WAIT_A0) {
-            const int b = (jb.wait_buf & 1) * 2;
-            const uint32_t seq = (uint32_t)t * a.ready_per_tile[b] + ((jb.wait_buf >> 1) & 7);
-            ts_wait(base + L::a_ready + 8 * b, seq & 1, abort_addr, a.err, 0x21000000 | j);
-          }
-          if (jb.flags & TJ_WAIT_A1) {
-            // (dgrad program only - its epilogue steps are long; measured -4 % on the forward kernel, +8 % on dgrad)
-            // Input half 1 comes back in two instalments: every epilogue thread hands over its first 32 channels
-            // (barrier a_ready[buf][1]: K 128-159 and 192-223), then its second 32 (a_ready_b[buf]).  The common
-            // 8-MMA job starts on the first instalment and waits for the second in mid-issue (below).
-            const int b = (jb.wait_buf & 1) * 2 + 1;
-            const uint32_t seq = (uint32_t)t * a.ready_per_tile[b] + ((jb.wait_buf >> 4) & 7);
-            ts_wait(base + L::a_ready + 8 * b, seq & 1, abort_addr, a.err, 0x21800000 | j);
-            if constexpr (kSplit) {
-              split_par = seq & 1;
-              split_bar = base + L::a_ready_b + 8 * (jb.wait_buf & 1);
-              if ((jb.flags & TJ_A_SMEM) || jb.nkb != 2 || a.no_split) ts_wait(split_bar, split_par, abort_addr, a.err, 0x21c00000 | j);
-              else split = true;
-            }
-          }
-        }
-        if (jb.flags & TJ_WAIT_EMPTY1) {
-          const uint32_t seq = (uint32_t)t * a.empty1_per_tile + ((jb.wait_buf >> 7) & 1);
-          ts_wait(base + L::acc1_empty, seq & 1, abort_addr, a.err, 0x25000000 | j);
-        }
-        if (jb.flags & TJ_WAIT_ORDER) {
-          const uint32_t seq = (uint32_t)t * a.order_per_tile + ((jb.ksteps >> 4) & 7);
-          ts_wait(base + L::order, seq & 1, abort_addr, a.err, 0x24000000 | j);
-        }
-        const uint32_t s = cnt % kTsStages, par = (cnt / kTsStages) & 1;
-        ts_chaos(a.chaos, 2u * cnt + 1u, a.chaos_roles & 2u);
-        if (tr) tr[4 * j + 1] = clock64();
-        if ((jb.flags & TJ_PREV_OTHER) && cnt >= (uint32_t)kTsStages)
-          ts_wait_progress(base + L::prog + (second ? 0u : 4u), cnt - kTsStages + 1, abort_addr, a.err, 0x26000000 | j);
-        ts_wait(base + L::w_full + 8 * s, par, abort_addr, a.err, 0x22000000 | j);
-        if (tr) tr[4 * j + 2] = clock64();
-        tc_fence_after_sync();
-        const uint32_t N = (uint32_t)jb.n16 * 16;
-        const uint64_t bd0 = smem_desc_sw128(base + L::ring + s * kTsStageBytes);
-        const uint64_t bd1 = bd0 + (uint64_t)(N * 8);                       // second K-block image: N rows x 128 B on
-        const uint32_t idesc = make_idesc(1, 128, N);
-        const uint32_t d = tmem + jb.d_col;
-        const uint32_t a_t = tmem + jb.a_col;
-        const uint32_t first = (jb.flags & TJ_FIRST) ? 0u : 1u;
-        const bool a_smem = (jb.flags & TJ_A_SMEM) != 0;
-        const uint64_t adesc = (jb.flags & TJ_A_DIR) ? adesc_dir : adesc_enc;
-        if (split) {   // K-high job: the four MMAs whose K ranges arrived first, then the rest
-          if (elect_one()) {
-            umma_bf16_ts(d, a_t, bd0, idesc, first);
-            umma_bf16_ts(d, a_t + 8, bd0 + 2, idesc, 1u);
-            umma_bf16_ts(d, a_t + 32, bd1, idesc, 1u);
-            umma_bf16_ts(d, a_t + 40, bd1 + 2, idesc, 1u);
-          }
-          __syncwarp();
-          ts_chaos(a.chaos, 0x40000000u + cnt, a.chaos_roles & 2u);
-          ts_wait(split_bar, split_par, abort_addr, a.err, 0x21e00000 | j);
-          tc_fence_after_sync();
-        }
-        if (elect_one()) {
-          if (split) {
-            umma_bf16_ts(d, a_t + 16, bd0 + 4, idesc, 1u);
-            umma_bf16_ts(d, a_t + 24, bd0 + 6, idesc, 1u);
-            umma_bf16_ts(d, a_t + 48, bd1 + 4, idesc, 1u);
-            umma_bf16_ts(d, a_t + 56, bd1 + 6, idesc, 1u);
-          } else if (!a_smem && jb.nkb == 2) {          // the common job: 8 back-to-back MMAs, A from TMEM
-            umma_bf16_ts(d, a_t, bd0, idesc, first);
-            umma_bf16_ts(d, a_t + 8, bd0 + 2, idesc, 1u);
-            umma_bf16_ts(d, a_t + 16, bd0 + 4, idesc, 1u);
-            umma_bf16_ts(d, a_t + 24, bd0 + 6, idesc, 1u);
-            umma_bf16_ts(d, a_t + 32, bd1, idesc, 1u);
-            umma_bf16_ts(d, a_t + 40, bd1 + 2, idesc, 1u);
-            umma_bf16_ts(d, a_t + 48, bd1 + 4, idesc, 1u);
-            umma_bf16_ts(d, a_t + 56, bd1 + 6, idesc, 1u);
-          } else if (a_smem) {                   // encoding block (4 steps) / padded g_raw block (1 step)
-            umma_bf16(d, adesc, bd0, idesc, first);
-            if ((jb.ksteps & 7) >= 2) umma_bf16(d, adesc + 2, bd0 + 2, idesc, 1u);
-            if ((jb.ksteps & 7) == 4) {
-              umma_bf16(d, adesc + 4, bd0 + 4, idesc, 1u);
-              umma_bf16(d, adesc + 6, bd0 + 6, idesc, 1u);
-            }
-          } else {                               // single K-block from TMEM (not used by the current plans)
-            umma_bf16_ts(d, a_t, bd0, idesc, first);
-            umma_bf16_ts(d, a_t + 8, bd0 + 2, idesc, 1u);
-            umma_bf16_ts(d, a_t + 16, bd0 + 4, idesc, 1u);
-            umma_bf16_ts(d, a_t + 24, bd0 + 6, idesc, 1u);
-          }
-          umma_commit(base + L::w_empty + 8 * s);
-          if (jb.flags & TJ_COMMIT_ENC) umma_commit(base + L::enc_empty);
-          if (jb.flags & TJ_COMMIT_DIR) umma_commit(base + L::dir_empty);
-          if (jb.flags & TJ_COMMIT_ACC0) umma_commit(base + L::acc_full);
-          if (jb.flags & TJ_COMMIT_ACC1) umma_commit(base + L::acc_full + 8);
-          if (jb.flags & TJ_SIGNAL_ORDER) mbar_arrive(base + L::order);
-        }
-        __syncwarp();
-        // this stage's next job is the other issuer's: tell it that the fill just consumed has landed (after the MMAs
-        // have been issued, off the critical path; shared memory is coherent within the CTA and both sides use volatile
-        // accesses in program order after / before their mbarrier tests)
-        if ((jb.ksteps & kTjNextOther) && lane == 0)
-          asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(base + L::prog + (second ? 4u : 0u)), "r"(cnt + 1) : "memory");
-        if (tr) tr[4 * j + 3] = clock64();
-        ++cnt;
-      }
+  } else if (warp == 1) {
+    ts_issue_loop<BWD, 0>(a, base, abort_addr, tmem, my_tiles, lane);
+  } else if (warp == 3) {
+    ts_issue_loop<BWD, 1>(a, base, abort_addr, tmem, my_tiles, lane);
   } else if (warp == 2) {
     // =============================== backward: gate producer ====================================================
     // streams the two H-stash block images whose sign gates the next epilogue step into a double-buffered staging
@@ -879,6 +887,56 @@ const TsPlan& ts_plan(int bwd) {
   return g_ts_plan[bwd ? 1 : 0];
 }
 
+
+// TsJob table -> per-issuer TsIssue records (see ts_issue_loop).  Barrier offsets are relative to L::bars.
+static int g_ts_nissue[2][2];
+template <bool BWD>
+static void ts_build_issue(const TsPlan& p, std::vector<TsIssue> (&out)[2]) {
+  using L = TsSmemT<BWD>;
+  static const bool no_split = [] { const char* e = getenv("GBNERF_TS_SPLIT"); return e && e[0] == '0'; }();
+  auto W = [](uint32_t bar_abs, int per_tile, int idx) {
+    return (bar_abs - L::bars) | ((uint32_t)(per_tile & 1) << 16) | ((uint32_t)(idx & 1) << 17) | 0x80000000u;
+  };
+  for (size_t j = 0; j < p.jobs.size(); ++j) {
+    const TsJob& jb = p.jobs[j];
+    TsIssue r{};
+    int nw = 0;
+    auto add = [&](uint32_t w) { if (nw < 5) r.w[nw] = w; ++nw; };
+    if (jb.flags & TJ_WAIT_ENC) add(W(L::enc_full, 1, 0));
+    if (jb.flags & TJ_WAIT_DIR) add(W(L::dir_full, 1, 0));
+    if (jb.flags & TJ_WAIT_TILE) add(W(L::tile_done, 1, 1));     // completion t - 1; tile 0 passes on the fresh barrier
+    if (jb.flags & TJ_WAIT_A0) {
+      const int b = (jb.wait_buf & 1) * 2;
+      add(W(L::a_ready + 8 * b, p.ready_per_tile[b], (jb.wait_buf >> 1) & 7));
+    }
+    if (jb.flags & TJ_WAIT_A1) {
+      const int b = (jb.wait_buf & 1) * 2 + 1;
+      const int idx = (jb.wait_buf >> 4) & 7;
+      add(W(L::a_ready + 8 * b, p.ready_per_tile[b], idx));
+      if (BWD) {   // two-instalment hand-over of input half 1: second barrier up front, or in mid-issue for the common job
+        const uint32_t w2 = W(L::a_ready_b + 8 * (jb.wait_buf & 1), p.ready_per_tile[b], idx);
+        if ((jb.flags & TJ_A_SMEM) || jb.nkb != 2 || no_split) add(w2); else r.wsplit = w2;
+      }
+    }
+    if (jb.flags & TJ_WAIT_EMPTY1) add(W(L::acc1_empty, p.empty1_per_tile, (jb.wait_buf >> 7) & 1));
+    if (jb.flags & TJ_WAIT_ORDER) add(W(L::order, p.order_per_tile, (jb.ksteps >> 4) & 7));
+    if (nw > 5) abort();   // a plan that needs more wait slots must widen TsIssue
+    r.idesc = make_idesc(1, 128, (uint32_t)jb.n16 * 16);
+    r.d_col = jb.d_col; r.a_col = jb.a_col; r.jidx = (uint16_t)j;
+    r.flags = (uint16_t)(((jb.flags & TJ_A_SMEM) ? TI_A_SMEM : 0) | ((jb.flags & TJ_A_DIR) ? TI_A_DIR : 0) |
+                         ((jb.flags & TJ_FIRST) ? TI_FIRST : 0) | ((jb.flags & TJ_PREV_OTHER) ? TI_PREV_OTHER : 0) |
+                         ((jb.ksteps & kTjNextOther) ? TI_NEXT_OTHER : 0) | ((jb.flags & TJ_SIGNAL_ORDER) ? TI_SIGNAL_ORDER : 0));
+    r.ksteps = jb.ksteps & 7; r.nkb = jb.nkb; r.n16 = jb.n16;
+    int nc = 0;
+    r.commit[0] = r.commit[1] = r.commit[2] = 0xffff;
+    if (jb.flags & TJ_COMMIT_ENC) r.commit[nc++] = (uint16_t)(L::enc_empty - L::bars);
+    if (jb.flags & TJ_COMMIT_DIR) r.commit[nc++] = (uint16_t)(L::dir_empty - L::bars);
+    if (jb.flags & TJ_COMMIT_ACC0) r.commit[nc++] = (uint16_t)(L::acc_full - L::bars);
+    if (jb.flags & TJ_COMMIT_ACC1) { if (nc >= 3) abort(); r.commit[nc++] = (uint16_t)(L::acc_full + 8 - L::bars); }
+    out[jb.d_col >= kTsAcc1 ? 1 : 0].push_back(r);
+  }
+}
+
 static int ts_ensure_device(cudaStream_t stream) {
   int dev = 0;
   GBN_CUDA(cudaGetDevice(&dev));
@@ -893,6 +951,16 @@ static int ts_ensure_device(cudaStream_t stream) {
                                      pr * kTsMaxSteps * sizeof(TsStep), cudaMemcpyHostToDevice));
     GBN_CUDA(cudaMemcpyToSymbol(c_tspack, p.pack.data(), p.pack.size() * sizeof(TsPackJob),
                                      pr * kTsMaxJobs * sizeof(TsPackJob), cudaMemcpyHostToDevice));
+  }
+  for (int pr = 0; pr < 2; ++pr) {
+    std::vector<TsIssue> iss[2];
+    if (pr == 0) ts_build_issue<false>(ts_plan(0), iss); else ts_build_issue<true>(ts_plan(1), iss);
+    for (int who = 0; who < 2; ++who) {
+      GBN_REQUIRE((int)iss[who].size() <= kTsMaxJobs, "TS issue table overflow");
+      g_ts_nissue[pr][who] = (int)iss[who].size();
+      GBN_CUDA(cudaMemcpyToSymbol(c_tsissue, iss[who].data(), iss[who].size() * sizeof(TsIssue),
+                                  (size_t)(pr * 2 + who) * kTsMaxJobs * sizeof(TsIssue), cudaMemcpyHostToDevice));
+    }
   }
   if (g_ts_wd_host_ptr == nullptr) {   // watchdog post-mortem record (zero-copy host memory, one per process)
     void* hp = nullptr;
@@ -1095,6 +1163,7 @@ int ts_forward(const void* packed, const float* ro, const float* rd, const float
   a.packed = pk; a.ro = ro; a.rd = rd; a.z = z; a.pts = pts; a.emb = emb; a.vd = vd; a.raw = raw;
   a.stash_h = static_cast<uint8_t*>(stash); a.err = err; a.stride = stride; a.P = R * S; a.S = S;
   a.njobs = (int)p.jobs.size(); a.nsteps = (int)p.steps.size();
+  a.nissue[0] = g_ts_nissue[0][0]; a.nissue[1] = g_ts_nissue[0][1];
   for (int i = 0; i < 4; ++i) a.ready_per_tile[i] = p.ready_per_tile[i];
   a.order_per_tile = p.order_per_tile;
   a.empty1_per_tile = p.empty1_per_tile;
@@ -1122,6 +1191,7 @@ int ts_backward_data(const void* packed_bwd, const float* g_raw, int64_t P, cons
   a.stash_g = static_cast<uint8_t*>(stash_g);
   a.err = err; a.P = P; a.S = 1;
   a.njobs = (int)p.jobs.size(); a.nsteps = (int)p.steps.size();
+  a.nissue[0] = g_ts_nissue[1][0]; a.nissue[1] = g_ts_nissue[1][1];
   for (int i = 0; i < 4; ++i) a.ready_per_tile[i] = p.ready_per_tile[i];
   a.order_per_tile = p.order_per_tile;
   a.empty1_per_tile = p.empty1_per_tile;
