@@ -115,3 +115,49 @@ def test_watchdog_record_is_empty_before_any_launch(lib):
     assert lib.watchdog_report() is None
     from gbnerf_b200 import ops
     ops._raise_if_watchdog_fired()
+
+
+def test_proxy_fence_precedes_every_release_of_a_bulk_copied_buffer_read_with_ordinary_loads():
+    """Regression guard for the round-1 nondeterminism: a shared-memory buffer filled by a bulk copy (async
+    proxy) and read with ordinary loads (generic proxy) must see `fence.proxy.async` before the mbarrier arrival that hands
+    it back to the bulk-copy producer - an mbarrier hand-over alone does not order generic reads before async writes.
+    The barrier protocol model cannot see this (its phases are correct either way), so the two places are pinned in the
+    source: the gate staging of the dgrad epilogue and the G-tile stages read by wgrad's bias warps."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ts = open(os.path.join(root, "gb-nerf_b200", "csrc", "mlp_ts.cu")).read()
+    i = ts.index("mbar_arrive(base + L::m_empty + 8 * b);")
+    before = ts[ts.rindex("ld_smem16(hb", 0, i):i]
+    assert "fence_proxy_async_smem();" in before, "dgrad epilogue: no proxy fence between the gate reads and the m_empty arrival"
+    wg = open(os.path.join(root, "gb-nerf_b200", "csrc", "mlp_wgrad.cu")).read()
+    j = wg.index("const uint32_t v = *reinterpret_cast<const uint32_t*>(blkp + off);")
+    k = wg.index("mbar_arrive(base + L::empty + 8 * s);", j)
+    assert "fence_proxy_async_smem();" in wg[j:k], "wgrad bias warps: no proxy fence between the tile reads and the stage release"
+    # the only other generic reads of bulk-copied shared memory would be new code: flag any ld.shared helper use in the
+    # TS kernels outside the gate staging
+    assert len(re.findall(r"ld_smem16\(", ts)) == 2, "a new ld_smem16 reader appeared: check its release path (DESIGN 3.2)"
+
+
+def test_reference_staging_recipe(tmp_path):
+    """oracle/make_ref.py copies the reference hot path byte for byte (container only: needs /root/reference)."""
+    import hashlib
+    import importlib.util
+    import json
+    import pytest
+    if not os.path.isfile("/root/reference/run.py"):
+        pytest.skip("reference tree not present (GPU box)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("make_ref", os.path.join(root, "oracle", "make_ref.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.OUT = str(tmp_path / "_ref")
+    out = mod.make("/root/reference")
+    man = json.load(open(os.path.join(out, "MANIFEST.json")))
+    for rel in ("DS_NeRF/run_nerf_helpers.py", "DS_NeRF/loss.py"):
+        assert hashlib.sha256(open(os.path.join(out, rel), "rb").read()).hexdigest() == man["files"][rel] == \
+            hashlib.sha256(open(os.path.join("/root/reference", rel), "rb").read()).hexdigest()
+    src = open("/root/reference/run.py").read().split("\n")
+    staged = open(os.path.join(out, "run_hotpath.py")).read()
+    for name, (lo, hi) in man["functions"].items():
+        assert "\n".join(src[lo - 1:hi]) in staged, name
+    assert set(man["functions"]) == {"batchify", "run_network", "batchify_rays", "render", "render_rays", "create_nerf"}
