@@ -171,6 +171,15 @@ def create_nerf(args):
     if getattr(args, "alpha_model_path", None) is not None:
         raise NotImplementedError("alpha_model_path / NeRF_RGB is outside the B200 hot path (SURVEY.md §8)")
     precision = getattr(args, "precision", None)
+    # the kernels serve the network the reference ships (aconfig_1 + --no_tcnn): say so here, at construction, instead of
+    # at the first forward call
+    if not (args.netdepth == 8 and args.netwidth == 256 and input_ch == 63 and input_ch_views == 27 and args.use_viewdirs
+            and (args.N_importance <= 0 or (args.netdepth_fine == 8 and args.netwidth_fine == 256))):
+        raise NotImplementedError(
+            "gbnerf_b200.create_nerf: the B200 kernels implement the reference's shipped network only - netdepth 8, "
+            "netwidth 256, multires 10, multires_views 4, use_viewdirs, i_embed 0 (got netdepth "
+            f"{args.netdepth}/{getattr(args, 'netdepth_fine', None)}, netwidth {args.netwidth}/{getattr(args, 'netwidth_fine', None)}, "
+            f"input channels {input_ch}+{input_ch_views}, use_viewdirs {args.use_viewdirs})")
     model = NeRF(D=args.netdepth, W=args.netwidth, input_ch=input_ch, output_ch=output_ch, skips=skips,
                  input_ch_views=input_ch_views, use_viewdirs=args.use_viewdirs, precision=precision).to(device)
     model = SingleDeviceParallel(model)

@@ -411,3 +411,41 @@ def test_high_sample_config_against_oracle(G, params):
     assert (rgb.cpu() - want["rgb_map"])[ok].abs().max().item() < 2.5 * TOL["tf32"]
     dz = (z - want["z_vals"]).abs()
     assert dz.median().item() < 1e-4 and (dz > 5e-3).float().mean().item() < 0.02
+
+
+def test_pytest_determinism_hook(G, params):
+    """render_rays(pytest=True) - the reference's determinism hook (run.py:2310-2313, helpers:321-329, 380-383): every random
+    tensor is replaced by numpy draws after np.random.seed(0) at each site (uniform even for the noise).  The CUDA path
+    with the hook on must equal the oracle fed exactly those tensors (tests/test_oracle_vs_reference.py pins that form
+    against the unmodified reference), and two calls must agree bit for bit."""
+    import numpy as np
+    nets, nq = build_path(G, params, "tf32")
+    R = 41
+    rays = O.synthetic_rays(R, seed=21)
+    def draw(*shape):
+        np.random.seed(0)
+        return torch.Tensor(np.random.rand(*shape))
+    rnd = dict(t_rand=draw(R, 64), noise0=draw(R, 64), u=draw(R, 64), noise1=draw(R, 128))
+    kw = dict(lindisp=True, perturb=1.0, N_importance=64, network_fine=nets[1], white_bkgd=True, raw_noise_std=1.0, retraw=True)
+    with torch.no_grad():
+        a = G.render_rays(rays.cuda(), nets[0], nq, 64, pytest=True, **kw)
+        b = G.render_rays(rays.cuda(), nets[0], nq, 64, pytest=True, **kw)
+    want = O.render_rays(rays, params[0], params[1], 64, 64, lindisp=True, white_bkgd=True, retraw=True, **rnd)
+    for k in ("rgb_map", "z_vals", "weights", "raw"):
+        assert torch.equal(a[k], b[k]), k
+    assert (a["rgb0"].cpu() - want["rgb0"]).abs().max().item() < TOL["tf32"]
+    ok = want["raw"][:, -1, 3].abs() > 2 * TOL["tf32"]       # far-plane alpha is a step function of sign(sigma)
+    assert (a["rgb_map"].cpu() - want["rgb_map"])[ok].abs().max().item() < 2.5 * TOL["tf32"]
+    dz = (a["z_vals"].cpu() - want["z_vals"]).abs()
+    assert dz.median().item() < 1e-5
+
+
+def test_create_nerf_rejects_geometries_the_kernels_do_not_serve(G, tmp_path):
+    base = dict(multires=10, multires_views=4, i_embed=0, use_viewdirs=True, N_samples=64, N_importance=64, netdepth=8,
+                netdepth_fine=8, netwidth=256, netwidth_fine=256, alpha_model_path=None, no_coarse=False, netchunk=65536,
+                lrate=3e-3, basedir=str(tmp_path), expname="exp", ft_path=None, no_reload=True, perturb=1.0,
+                white_bkgd=True, raw_noise_std=1.0, dataset_type="llff", no_ndc=True, lindisp=True, sigma_loss=False)
+    (tmp_path / "exp").mkdir()
+    for bad in (dict(netwidth=128), dict(netdepth_fine=4), dict(multires=6), dict(use_viewdirs=False)):
+        with pytest.raises(NotImplementedError, match="shipped network"):
+            G.create_nerf(types.SimpleNamespace(**dict(base, **bad)))

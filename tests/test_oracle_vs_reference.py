@@ -74,3 +74,29 @@ def test_depth_to_normals(ref):
     n_ref = ref["depth2normal_geo"](pts, 7)
     n_got = O.depth2normal_geo(pts.contiguous(), 7)
     torch.testing.assert_close(n_got, n_ref, rtol=1e-5, atol=1e-6)
+
+
+def pytest_hook_randoms(R, S, N, std):
+    """What pytest=True substitutes for the random tensors (run.py:2310-2313, helpers:321-329, 380-383): numpy draws
+    after np.random.seed(0) at EACH site, uniform even for the noise."""
+    import numpy as np
+    def draw(*shape):
+        np.random.seed(0)
+        return torch.Tensor(np.random.rand(*shape))
+    return dict(t_rand=draw(R, S), noise0=draw(R, S) * std, u=draw(R, N), noise1=draw(R, S + N) * std)
+
+
+def test_pytest_determinism_hook(ref, tmp_path):
+    """render_rays(pytest=True) of the UNMODIFIED reference == the oracle fed the tensors the hook substitutes."""
+    args = ref_loader.default_args(tmp_path)
+    torch.manual_seed(0)
+    kw_train, _, *_ = ref["create_nerf"](args)
+    pc, pf = O.init_params(0), O.init_params(None)
+    R = 23
+    rays = O.synthetic_rays(R, seed=21)
+    with torch.no_grad():
+        kw = {k: v for k, v in kw_train.items() if k not in ("use_viewdirs", "ndc")}   # render() consumes those two
+        got = ref["render_rays"](rays, pytest=True, **kw)
+        want = O.render_rays(rays, pc, pf, 64, 64, lindisp=True, white_bkgd=True, **pytest_hook_randoms(R, 64, 64, 1.0))
+    for k in ("rgb_map", "disp_map", "acc_map", "depth_map", "weights", "z_vals", "rgb0", "z_std"):
+        torch.testing.assert_close(got[k], want[k], rtol=2e-5, atol=2e-6, equal_nan=True)
