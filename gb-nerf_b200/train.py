@@ -167,7 +167,7 @@ class TrainStep:
         call("gbn_loss_seed", _p(self.out1[0]), _p(self.out0[0]), _p(self.out1[1]), _p(self.target_rgb), _p(self.target_disp),
              R, self.R_global, self.depth_lambda, _p(self.g_rgb), _p(self.g_rgb0), _p(self.g_disp), _p(self.loss), st)
         # ---- backward: fine network first (its all-reduce then overlaps the coarse network's backward) ----------
-        works = []
+        works = {}
         for net in (1, 0):
             Sn = SF if net else S
             raw, z, noise = (self.raw1, self.z1, noise1) if net else (self.raw0, self.z0, noise0)
@@ -180,15 +180,16 @@ class TrainStep:
                  self.ptrs[net]["g"], C.c_void_p(self.ws_b[net].data_ptr() + 256), st)
             if self.world > 1:
                 if self.overlap:
-                    works.append(tdist.all_reduce(self.flat[net], op=tdist.ReduceOp.SUM, async_op=True))
+                    works[net] = tdist.all_reduce(self.flat[net], op=tdist.ReduceOp.SUM, async_op=True)
                 else:
                     tdist.all_reduce(self.flat[net], op=tdist.ReduceOp.SUM)
-        for w in works:
-            w.wait()
         # ---- optimizer: torch.optim.Adam arithmetic + bf16 weight images patched in place, one launch per network ---
+        # (fine network first: its all-reduce finished long ago, its Adam launch overlaps the coarse network's all-reduce)
         b1, b2 = self.group["betas"]
         call("gbn_adam_tick", _p(self.step_dev), _p(self.lr_dev), float(b1), float(b2), _p(self.scalars), st)
-        for net in (0, 1):
+        for net in (1, 0):
+            if net in works:
+                works[net].wait()
             q = self.ptrs[net]
             call("gbn_adam_step_repack_dev", q["p"], q["g"], q["m"], q["v"], _p(self.scalars), float(b1), float(b2),
                  float(self.group["eps"]), _p(self.packed[net][0]), _p(self.packed[net][1]), st)
