@@ -48,7 +48,8 @@ def stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-@pytest.mark.parametrize("R,S", [(1, 64), (2, 64), (77, 64), (4737 * 2 + 1, 64), (77, 128), (31, 192), (9, 40)])
+@pytest.mark.parametrize("R,S", [(1, 64), (2, 64), (77, 64), (4737 * 2 + 1, 64), (77, 128), (31, 192), (9, 40),
+                                 (1, 384), (613, 384), (37, 256), (19, 512), (5, 1024)])   # 128 M: the segment-walk kernels
 @pytest.mark.parametrize("noise", [False, True])
 def test_composite_forward_and_backward_stay_inside(G, R, S, noise):
     g = torch.Generator().manual_seed(R + S)
@@ -70,7 +71,8 @@ def test_composite_forward_and_backward_stay_inside(G, R, S, noise):
     ar2.check()
 
 
-@pytest.mark.parametrize("R,S,N", [(1, 64, 64), (133, 64, 64), (50, 128, 256), (41, 64, 32), (23, 37, 11)])
+@pytest.mark.parametrize("R,S,N", [(1, 64, 64), (133, 64, 64), (50, 128, 256), (41, 64, 32), (23, 37, 11), (3, 32, 32), (7, 32, 32),
+                                   (1185 * 2 + 1, 64, 128), (77, 128, 64), (77, 128, 128)])
 @pytest.mark.parametrize("det", [True, False])
 def test_sample_merge_stays_inside(G, R, S, N, det):
     g = torch.Generator().manual_seed(R + N)
@@ -81,6 +83,28 @@ def test_sample_merge_stays_inside(G, R, S, N, det):
     smp, merged, std = ar.out(R, N), ar.out(R, S + N), ar.out(R)
     G._lib.call("gbn_sample_pdf_merge", ptr(z), ptr(w), ptr(u), R, S, N, ptr(smp), ptr(merged), ptr(std), stream())
     ar.check()
+    # the extended entry point: int32 indices out (carved from the same kind of arena, viewed as int32)
+    ar2 = Arena()
+    inds_f, merged2, std2 = ar2.out(R, N), ar2.out(R, S + N), ar2.out(R)
+    G._lib.call("gbn_sample_pdf_merge_ex", ptr(z), ptr(w), ptr(u), None, R, S, N, None, ptr(merged2), ptr(std2), ptr(inds_f), stream())
+    ar2.check()
+    assert torch.equal(merged2, merged)
+    inds = inds_f.view(torch.int32)
+    assert int(inds.min()) >= 0 and int(inds.max()) <= S - 1
+
+
+@pytest.mark.parametrize("R,S", [(1, 64), (301, 64), (5, 128), (77, 32), (3, 256), (41, 50)])
+@pytest.mark.parametrize("perturb", [False, True])
+def test_zvals_stays_inside(G, R, S, perturb):
+    g = torch.Generator().manual_seed(R + S)
+    rays = torch.rand(R, 11, generator=g).cuda()
+    rays[:, 6], rays[:, 7] = 1.2, 8.0
+    t = torch.rand(R, S, generator=g).cuda() if perturb else None
+    ar = Arena()
+    z = ar.out(R, S)
+    G._lib.call("gbn_zvals_stratified", ptr(rays[:, 6:7]), ptr(rays[:, 7:8]), 11, R, S, 1, ptr(t), ptr(z), stream())
+    ar.check()
+    assert (z[:, 1:] >= z[:, :-1]).all() and float(z.min()) >= 1.2 - 1e-5 and float(z.max()) <= 8.0 + 1e-5
 
 
 @pytest.mark.parametrize("H,W", [(7, 9), (33, 50)])

@@ -89,7 +89,8 @@ def test_composite_golden(G, golden):
     assert torch.isnan(disp[0]).item() and acc[0].item() == 0 and depth[0].item() == 0
 
 
-@pytest.mark.parametrize("R,S", [(1, 64), (33, 2), (257, 64), (100, 128), (19, 192), (50, 384), (7, 1000)])
+@pytest.mark.parametrize("R,S", [(1, 64), (33, 2), (257, 64), (100, 128), (19, 192), (50, 384), (7, 1000), (131, 256), (45, 512),
+                                 (9, 1024), (1030, 384)])   # S = 128 M >= 384: composite_fwd_seg_kernel
 def test_composite_vs_oracle(G, R, S):
     g = torch.Generator().manual_seed(R * 1000 + S)
     raw = torch.randn(R, S, 4, generator=g)
@@ -131,7 +132,7 @@ def test_composite_backward_golden(G, golden):
             rel_close(gr[1:], g[f"graw_wb{int(wb)}_dw{int(dw)}"][1:], rtol=1e-4, atol=1e-6)
 
 
-@pytest.mark.parametrize("S", [64, 128, 200])
+@pytest.mark.parametrize("S", [64, 128, 200, 256, 384, 512, 1024])   # 128 M >= 256: composite_bwd_seg_kernel
 def test_composite_backward_vs_autograd(G, S):
     g = torch.Generator().manual_seed(S)
     R = 129
