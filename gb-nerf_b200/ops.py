@@ -556,6 +556,10 @@ class _Tcnn(torch.autograd.Function):
                 raise ValueError(f"NeRF_TCNN takes [P,6] rows (point, direction), got {tuple(a0.shape)}")
             R, S, z = a0.shape[0], 1, None
         need_grad = grad_mode and any(ctx.needs_input_grad[7:])
+        if grad_mode and any(ctx.needs_input_grad[3:7]):
+            raise NotImplementedError(
+                "gbnerf_b200: gradients with respect to rays / depths / input rows of NeRF_TCNN are not implemented "
+                "(the reference's training loop needs none, run.py:2346); detach the inputs")
         stash = torch.empty(R * S, 32, device=table.device, dtype=torch.float16) if need_grad else None
         if mode == "rays":
             raw = tcnn_forward_raw(table, R, S, rays_o=a0, rays_d=a1, viewdirs=a2, z=z, stash=stash)
