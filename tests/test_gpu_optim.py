@@ -35,7 +35,7 @@ def test_fused_adam_matches_torch_adam_and_repacks_in_place(G):
     ref = torch.optim.Adam(a.parameters(), lr=3e-3, betas=(0.9, 0.999))
     opt = G.FusedAdam(b.parameters(), lr=3e-3, betas=(0.9, 0.999))
     assert isinstance(opt, torch.optim.Adam)
-    in_place = G._lib.load().gbn_mlp_variant() == 1   # env GBNERF_MLP=ss/tq: other image layouts, re-packed lazily
+    in_place = G._lib.load().gbn_mlp_variant() == 1   # env GBNERF_MLP=ss: another image layout, re-packed lazily
     n0 = G._lib.kernel_launches()
     b.packed_weights(), b.packed_weights_bwd()
     n_pack = G._lib.kernel_launches() - n0
