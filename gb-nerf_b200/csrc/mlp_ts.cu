@@ -283,6 +283,15 @@ __device__ __forceinline__ void ts_issue_loop(const TsArgs& a, uint32_t base, ui
       unsigned long long* tr = (a.trace && blockIdx.x == 0 && t == a.trace_tile && lane == 0) ? a.trace : nullptr;
       if (tr) tr[4 * rc.jidx] = clock64();
       ts_chaos(a.chaos, 2u * cnt, a.chaos_roles & 2u);
+      // The ring guard first (it must precede any test of the stage's full barrier, and up here its shared-memory poll is
+      // off the path between the operands' hand-over and the first MMA), then the operands, then the weight stage.
+      // Tried in round 2 and slower, on one box against this order (1,059 TFLOP/s): probing all of a job's barriers at
+      // once (903), a blocking wait for the weight stage before the operands (1,007), a non-blocking probe of it before
+      // the operands (1,041), polling with test_wait instead of try_wait (no difference) - every extra probe of an
+      // mbarrier is a ~130-cycle round trip for the issuing warp, whether or not the phase is complete.
+      const uint32_t s = cnt % kTsStages, par = (cnt / kTsStages) & 1;
+      if ((rc.flags & TI_PREV_OTHER) && cnt >= (uint32_t)kTsStages)
+        ts_wait_progress(base + L::prog + (WHO ? 0u : 4u), cnt - kTsStages + 1, abort_addr, a.err, 0x26000000 | rc.jidx);
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
         const uint32_t w = rc.w[k];
@@ -290,14 +299,8 @@ __device__ __forceinline__ void ts_issue_loop(const TsArgs& a, uint32_t base, ui
           ts_wait(bars + (w & 0xffffu), (((uint32_t)t & (w >> 16)) ^ (w >> 17)) & 1u, abort_addr, a.err,
                   0x20000000 | (k << 20) | rc.jidx);
       }
-      // (Probing all of a job's barriers at once - each probe is a ~130-cycle round trip to the barrier unit even when the
-      // phase is long complete - was tried in round 2 and is slower: 903 against ~1000 TFLOP/s; so is polling with
-      // test_wait instead of try_wait: no difference.)
-      const uint32_t s = cnt % kTsStages, par = (cnt / kTsStages) & 1;
       ts_chaos(a.chaos, 2u * cnt + 1u, a.chaos_roles & 2u);
       if (tr) tr[4 * rc.jidx + 1] = clock64();
-      if ((rc.flags & TI_PREV_OTHER) && cnt >= (uint32_t)kTsStages)
-        ts_wait_progress(base + L::prog + (WHO ? 0u : 4u), cnt - kTsStages + 1, abort_addr, a.err, 0x26000000 | rc.jidx);
       ts_wait(base + L::w_full + 8 * s, par, abort_addr, a.err, 0x22000000 | rc.jidx);
       if (tr) tr[4 * rc.jidx + 2] = clock64();
       tc_fence_after_sync();
