@@ -15,7 +15,7 @@ step is captured once and replayed per step, so the ~150 launches / allocations 
 (0.55 ms of a 5 ms step at 4096 rays, most of a 0.7 ms step at 512 rays per GPU) collapse into one graph launch.
 
 Kernel sequence per replay (all in libgbnerf.so unless noted):
-  torch RNG x4 (t_rand, noise0, u, noise1) -> zvals -> MLP fwd+stash (coarse) -> composite -> sample+merge ->
+  torch RNG x2 (one uniform draw for t_rand and u, one normal draw for the two noise tensors) -> zvals -> MLP fwd+stash (coarse) -> composite -> sample+merge ->
   MLP fwd+stash (fine) -> composite -> loss_seed -> composite bwd (fine) -> dgrad -> wgrad -> [NCCL all-reduce fine]
   -> composite bwd (coarse) -> dgrad -> wgrad -> [NCCL all-reduce coarse] -> adam_tick -> adam+repack x2.
 """
@@ -80,7 +80,11 @@ class TrainStep:
         f = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float32)
         self.rays = f(R, 11)                      # o(3) d(3) near far viewdir(3): the batch of run.py:1726-1736
         self.target_rgb, self.target_disp = f(R, 3), f(R)
-        self.t_rand, self.noise0, self.u, self.noise1 = f(R, S), f(R, S), f(R, N), f(R, S + N)
+        # random tensors: one buffer for the two uniform draws and one for the two normal draws (two RNG launches per step
+        # instead of four; the draws are i.i.d., so how they are batched does not change their distribution)
+        self._uniform, self._normal = f(R * (S + N)), f(R * (2 * S + N))
+        self.t_rand, self.u = self._uniform[:R * S].view(R, S), self._uniform[R * S:].view(R, N)
+        self.noise0, self.noise1 = self._normal[:R * S].view(R, S), self._normal[R * S:].view(R, S + N)
         self.z0, self.raw0, self.w0 = f(R, S), f(R, S, 4), f(R, S)
         self.z1, self.raw1, self.w1, self.zstd = f(R, S + N), f(R, S + N, 4), f(R, S + N), f(R)
         self.out0 = [f(R, 3), f(R), f(R), f(R)]   # rgb0, disp0, acc0, depth0
@@ -95,7 +99,9 @@ class TrainStep:
         # one flat gradient buffer per network, aliased by p.grad (so optimizer / checkpoint code sees gradients)
         self.nets = [self.coarse, self.fine]
         self.params = [n.param_list() for n in self.nets]
-        self.flat = [torch.zeros(sum(p.numel() for p in ps), device=dev) for ps in self.params]
+        sizes = [sum(p.numel() for p in ps) for ps in self.params]
+        self.flat_all = torch.zeros(sum(sizes), device=dev)                # one buffer: one memset per step
+        self.flat = [self.flat_all[:sizes[0]], self.flat_all[sizes[0]:]]
         self.grads = []
         for ps, flat in zip(self.params, self.flat):
             off, views = 0, []
@@ -138,19 +144,22 @@ class TrainStep:
         o, d, near, far, vd = rays[:, 0:3], rays[:, 3:6], rays[:, 6:7], rays[:, 7:8], rays[:, 8:11]
         pitch = 11
         rnd = randoms or {}
-        # random tensors in the reference's consumption order (run.py:2307, helpers:377, helpers:318, helpers:377)
+        # the four random tensors of run.py:2307, helpers:377 (twice) and helpers:318; `randoms` injects them (parity tests)
         t_rand = noise0 = u = noise1 = None
-        if self.perturb > 0.:
-            t_rand = self.t_rand.copy_(rnd["t_rand"]) if "t_rand" in rnd else self.t_rand.uniform_()
-        if self.noise_std > 0.:
-            noise0 = self.noise0.copy_(rnd["noise0"]) if "noise0" in rnd else self.noise0.normal_(0., self.noise_std)
-        if self.perturb != 0.:
-            u = self.u.copy_(rnd["u"]) if "u" in rnd else self.u.uniform_()
-        if self.noise_std > 0.:
-            noise1 = self.noise1.copy_(rnd["noise1"]) if "noise1" in rnd else self.noise1.normal_(0., self.noise_std)
+        if rnd:
+            if self.perturb > 0.:
+                t_rand, u = self.t_rand.copy_(rnd["t_rand"]), self.u.copy_(rnd["u"])
+            if self.noise_std > 0.:
+                noise0, noise1 = self.noise0.copy_(rnd["noise0"]), self.noise1.copy_(rnd["noise1"])
+        else:
+            if self.perturb > 0.:
+                self._uniform.uniform_()
+                t_rand, u = self.t_rand, self.u
+            if self.noise_std > 0.:
+                self._normal.normal_(0., self.noise_std)
+                noise0, noise1 = self.noise0, self.noise1
         self.loss.zero_()
-        for flat in self.flat:
-            flat.zero_()                                                     # wgrad accumulates
+        self.flat_all.zero_()                                                # wgrad accumulates
 
         # ---- forward --------------------------------------------------------------------------------------
         call("gbn_zvals_stratified", _p(near), _p(far), pitch, R, S, int(self.lindisp), _p(t_rand), _p(self.z0), st)
