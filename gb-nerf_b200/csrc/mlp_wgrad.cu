@@ -311,9 +311,19 @@ static void make_items(WgItem* items, bool with_dir) {
   const int nitems = with_dir ? kWgItems : kWgItems - 1;   // the direction item needs the forward's dir stash block
   int cost[kWgItems], total = 0;
   for (int i = 0; i < nitems; ++i) { cost[i] = items[i].m_blocks + items[i].n_blocks; total += cost[i]; }
-  int given = 0, share[kWgItems];
-  for (int i = 0; i < nitems; ++i) { share[i] = kNumSMs * cost[i] / total; if (share[i] < 1) share[i] = 1; given += share[i]; }
-  for (int i = 0; given < kNumSMs; i = (i + 1) % nitems) if (cost[i] == 8) { ++share[i]; ++given; }
+  // Every CTA of an item streams the same share of its tiles, and the kernel ends with its slowest CTA: minimise the
+  // largest bytes-per-CTA over the items (greedy: the next CTA goes to the item whose CTAs carry the most).  Round 1
+  // rounded proportional shares down and handed the remainder to the widest items, which left the direction item at
+  // 0.75 units per CTA against a mean of 0.63 - the whole launch ran 19 % behind its mean (ncu: 79 % of the copy peak).
+  int share[kWgItems];
+  (void)total;
+  for (int i = 0; i < nitems; ++i) share[i] = 1;
+  for (int given = nitems; given < kNumSMs; ++given) {
+    int best = 0;
+    for (int i = 1; i < nitems; ++i)
+      if (cost[i] * share[best] > cost[best] * share[i]) best = i;     // cost[i] / share[i] > cost[best] / share[best]
+    ++share[best];
+  }
   int c = 0;
   for (int i = 0; i < nitems; ++i) { items[i].cta_begin = (uint16_t)c; c += share[i]; items[i].cta_end = (uint16_t)c; }
   for (int i = nitems; i < kWgItems; ++i) { items[i].cta_begin = items[i].cta_end = 0xffff; }
