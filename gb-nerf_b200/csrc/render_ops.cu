@@ -54,35 +54,65 @@ __global__ void __launch_bounds__(256) zvals_kernel(const float* __restrict__ ne
   }
 }
 
-// Same arithmetic for S in {32, 64, 128, 256} (the render path): a thread keeps ONE sample index, so linspace(0, 1, S)[s]
-// is evaluated once per thread instead of three times per element, the int64 division by S is gone, and the neighbours'
-// depths of the stratified jitter come from shared memory instead of being recomputed (12 -> 3 IEEE divisions per element;
-// the generic kernel ran at 12 % of the HBM copy peak).
+// Same arithmetic for S in {32, 64, 128, 256} (the render path): a thread owns FOUR consecutive samples of a ray, so
+// linspace(0, 1, S) is evaluated once per thread (six values: its four samples and their two neighbours), the int64
+// division by S is gone, the jitter is read and the depths are written as 16-byte streaming accesses, and two rays per
+// thread are in flight at a time.  (The generic kernel ran at 12 % of the HBM copy peak; a first fixed-S version with one
+// 4-byte element per thread and the neighbours exchanged through shared memory at 20 %: ~1 MB in flight per wave.)
 template <int S>
 __global__ void __launch_bounds__(256) zvals_fixed_kernel(const float* __restrict__ near, const float* __restrict__ far,
                                                           int64_t stride, int64_t R, int lindisp,
                                                           const float* __restrict__ t_rand, float* __restrict__ z) {
-  constexpr int RPB = 256 / S;
-  __shared__ float zs[256];
-  const int s = threadIdx.x % S, rl = threadIdx.x / S;
-  const float t = linspace01(s, S), omt = __fsub_rn(1.f, t);
-  for (int64_t r0 = (int64_t)blockIdx.x * RPB; r0 < R; r0 += (int64_t)gridDim.x * RPB) {
-    const int64_t r = r0 + rl;
-    const bool valid = r < R;
-    const float n = valid ? __ldg(near + r * stride) : 1.f, f = valid ? __ldg(far + r * stride) : 2.f;
-    float zc;
-    if (lindisp) zc = __fdiv_rn(1.f, __fadd_rn(__fmul_rn(__fdiv_rn(1.f, n), omt), __fmul_rn(__fdiv_rn(1.f, f), t)));
-    else zc = __fadd_rn(__fmul_rn(n, omt), __fmul_rn(f, t));
-    if (t_rand != nullptr) {
-      zs[threadIdx.x] = zc;
-      __syncthreads();
-      const float zp = s > 0 ? zs[threadIdx.x - 1] : zc, zn = s < S - 1 ? zs[threadIdx.x + 1] : zc;
-      __syncthreads();
-      const float lo = s > 0 ? __fmul_rn(.5f, __fadd_rn(zc, zp)) : zc;
-      const float hi = s < S - 1 ? __fmul_rn(.5f, __fadd_rn(zn, zc)) : zc;
-      if (valid) zc = __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), ld_stream(t_rand + r * S + s)));
+  constexpr int TPR = S / 4, RPB = 256 / TPR;          // threads per ray, rays per block iteration
+  const int q = threadIdx.x % TPR, rl = threadIdx.x / TPR, s0 = 4 * q;
+  float t[6], omt[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const int s = min(max(s0 - 1 + k, 0), S - 1);
+    t[k] = linspace01(s, S);
+    omt[k] = __fsub_rn(1.f, t[k]);
+  }
+  auto depths = [&](float n, float f, float (&zc)[6]) {
+    if (lindisp) {
+      const float in = __fdiv_rn(1.f, n), inf = __fdiv_rn(1.f, f);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) zc[k] = __fdiv_rn(1.f, __fadd_rn(__fmul_rn(in, omt[k]), __fmul_rn(inf, t[k])));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) zc[k] = __fadd_rn(__fmul_rn(n, omt[k]), __fmul_rn(f, t[k]));
     }
-    if (valid) st_stream(z + r * S + s, zc);
+  };
+  auto jitter = [&](const float (&zc)[6], float4 u) {
+    float o[4];
+    const float uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int s = s0 + k;
+      const float c = zc[k + 1];
+      const float lo = s > 0 ? __fmul_rn(.5f, __fadd_rn(c, zc[k])) : c;
+      const float hi = s < S - 1 ? __fmul_rn(.5f, __fadd_rn(zc[k + 2], c)) : c;
+      o[k] = __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), uu[k]));
+    }
+    return make_float4(o[0], o[1], o[2], o[3]);
+  };
+  const int64_t step = (int64_t)gridDim.x * RPB;
+  for (int64_t r0 = (int64_t)blockIdx.x * RPB + rl; r0 < R; r0 += 2 * step) {
+    const int64_t r1 = r0 + step;
+    const bool two = r1 < R;
+    float4 u0 = make_float4(0.f, 0.f, 0.f, 0.f), u1 = u0;
+    if (t_rand != nullptr) {
+      u0 = ld_stream4(reinterpret_cast<const float4*>(t_rand + r0 * S) + q);
+      if (two) u1 = ld_stream4(reinterpret_cast<const float4*>(t_rand + r1 * S) + q);
+    }
+    float zc[6];
+    depths(__ldg(near + r0 * stride), __ldg(far + r0 * stride), zc);
+    st_stream4(reinterpret_cast<float4*>(z + r0 * S) + q,
+               t_rand != nullptr ? jitter(zc, u0) : make_float4(zc[1], zc[2], zc[3], zc[4]));
+    if (two) {
+      depths(__ldg(near + r1 * stride), __ldg(far + r1 * stride), zc);
+      st_stream4(reinterpret_cast<float4*>(z + r1 * S) + q,
+                 t_rand != nullptr ? jitter(zc, u1) : make_float4(zc[1], zc[2], zc[3], zc[4]));
+    }
   }
 }
 
@@ -518,13 +548,13 @@ __global__ void __launch_bounds__(kThreads) sample_merge_kernel(const float* __r
   }
 }
 
-template <int STEPS, bool UPPER>   // #{j < n : a[j] <= v} (UPPER) or #{j < n : a[j] < v}, n < 2^STEPS... n <= 2^STEPS - 1 + 1
+template <int STEPS, bool UPPER, int STRIDE = 1>   // #{j < n : a[j] <= v} (UPPER) or #{j < n : a[j] < v}, n <= 2^STEPS
 __device__ __forceinline__ int count_below(const float* a, int n, float v) {
   int lo = 0;
 #pragma unroll
   for (int s = STEPS - 1; s >= 0; --s) {
     const int probe = lo + (1 << s);
-    const float x = a[min(probe, n) - 1];
+    const float x = a[STRIDE * (min(probe, n) - 1)];
     const bool take = probe <= n && (UPPER ? x <= v : x < v);
     lo = take ? probe : lo;
   }
@@ -544,7 +574,8 @@ __device__ __forceinline__ int count_below(const float* a, int n, float v) {
 // Searches are the same fixed-depth upper-bound walks as in sample_merge_fast_kernel; `inds_out` returns their result
 // (= torch.searchsorted(cdf, u, right=True), helpers:333) and `cdf_in` replaces the cdf built from the weights, which
 // together let the test assert bit-exact indices on this kernel given the same cdf and uniforms.
-// 125-190 warp instructions per ray against 465 for sample_merge_fast_kernel<2,2> (profiles/).
+// ~290 warp instructions and ~75 shared-memory wavefronts per 64 + 64 ray (465 instructions for the round-1 kernel); the
+// kernel is bound by the shared-memory pipe and the issue slots together (profiles/r2_sample_cons_ncu.md).
 template <int LANES, int KN>
 __device__ __forceinline__ void seg_bitonic_sort(float (&v)[KN], int l) {
   constexpr int N = LANES * KN;
@@ -594,9 +625,12 @@ __global__ void __launch_bounds__(kThreads, 4) sample_merge_cons_kernel(const fl
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int sub = lane / LANES, l = lane % LANES;
   float* const base = smem + ((size_t)wib * RPW + sub) * kPerRay;
+  // deterministic path: (cdf[i], bin midpoint[i]) pairs, one 8-byte gather per end of a sample's bin; the random-u path
+  // searches the cdf (unit stride keeps its probes on fewer banks) and keeps the two arrays apart
+  float2* const cb = reinterpret_cast<float2*>(base);
   float* const cdf = base;
-  float* const bn = cdf + S;
-  float* const zv = bn + S;
+  float* const bn = base + S;
+  float* const zv = base + 2 * S;
   float* const smp = zv + S;
   float* const mrg = smp + N;
   int* const hist = reinterpret_cast<int*>(mrg + S + N);                       // S + 4 counters
@@ -624,6 +658,11 @@ __global__ void __launch_bounds__(kThreads, 4) sample_merge_cons_kernel(const fl
       }
     }
   };
+  // deterministic samples: u = linspace(0, 1, N) is the same for every ray - this lane's KN values, once
+  float ud[KN];
+#pragma unroll
+  for (int k = 0; k < KN; ++k) ud[k] = linspace01(l * KN + k, N);
+  int* const fh = reinterpret_cast<int*>(smp);                                 // DET: histogram of first-sample indices (below)
   const int64_t grp0 = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
   if (grp0 < ngroups) fetch(grp0);
   for (int64_t grp = grp0; grp < ngroups; grp += nwarps) {
@@ -663,41 +702,120 @@ __global__ void __launch_bounds__(kThreads, 4) sample_merge_cons_kernel(const fl
 #pragma unroll
       for (int k = 0; k < 4; ++k) c[k] = (excl + c[k]) * rtot;                 // cdf[i] = sum_{1 <= m <= i} q_m / sum q
     }
-    *reinterpret_cast<float4*>(cdf + l * 4) = make_float4(c[0], c[1], c[2], c[3]);
     const float znext = __shfl_down_sync(kFullMask, zz[0], 1, LANES);
-    *reinterpret_cast<float4*>(bn + l * 4) = make_float4(.5f * (zz[1] + zz[0]), .5f * (zz[2] + zz[1]), .5f * (zz[3] + zz[2]),
-                                                         .5f * (znext + zz[3]));
+    if constexpr (DET) {
+      *reinterpret_cast<float4*>(cb + l * 4) = make_float4(c[0], .5f * (zz[1] + zz[0]), c[1], .5f * (zz[2] + zz[1]));
+      *reinterpret_cast<float4*>(cb + l * 4 + 2) = make_float4(c[2], .5f * (zz[3] + zz[2]), c[3], .5f * (znext + zz[3]));
+    } else {
+      *reinterpret_cast<float4*>(cdf + l * 4) = make_float4(c[0], c[1], c[2], c[3]);
+      *reinterpret_cast<float4*>(bn + l * 4) = make_float4(.5f * (zz[1] + zz[0]), .5f * (zz[2] + zz[1]), .5f * (zz[3] + zz[2]),
+                                                           .5f * (znext + zz[3]));
+    }
     if (DET) {
       *reinterpret_cast<int4*>(hist + l * 4) = make_int4(0, 0, 0, 0);
       if (l == 0) *reinterpret_cast<int4*>(hist + S) = make_int4(0, 0, 0, 0);
+      if constexpr (KN % 4 == 0) {
+#pragma unroll
+        for (int k = 0; k < KN; k += 4) *reinterpret_cast<int4*>(fh + l * KN + k) = make_int4(0, 0, 0, 0);
+      } else {
+#pragma unroll
+        for (int k = 0; k < KN; k += 2) *reinterpret_cast<int2*>(fh + l * KN + k) = make_int2(0, 0);
+      }
     }
     __syncwarp();
     // ---- KN consecutive samples per lane --------------------------------------------------------------------------
     float sv[KN];
+    int inds[KN];
     if (DET) {
+      // searchsorted(cdf, u, right=True)[j] = #{i : cdf[i] <= u_j}.  The u_j are ascending and known in closed form, so
+      // the search is turned around: f_i = #{j : u_j < cdf[i]} (the first sample at or above cdf[i]) follows from one
+      // multiplication and two exact comparisons against linspace values, cdf[i] <= u_j  <=>  f_i <= j, and the index of
+      // sample j is a prefix sum over a histogram of the f_i - the cdf entries stay in registers and 6 dependent,
+      // bank-conflicting shared-memory probes per sample (70 % of this kernel's shared-memory wavefronts) disappear.
 #pragma unroll
-      for (int k = 0; k < KN; ++k) uu[k] = linspace01(l * KN + k, N);
+      for (int k = 0; k < KN; ++k) uu[k] = ud[k];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (l * 4 + k < B) {
+          // j0 = trunc(cdf * (N - 1)): u_j < cdf for every j < j0 (margin 1 / (N - 1) against rounding errors of 1e-7), and
+          // u_{j0 + 2} > cdf for the same reason, so f is j0 plus the outcome of two exact comparisons; linspace01() is
+          // evaluated branch-free (both sides of its two-sided formula, then a select)
+          const float ck = c[k];
+          int j0 = (int)(ck * (float)(N - 1));
+          j0 = j0 < 0 ? 0 : (j0 > N ? N : j0);
+          constexpr float kStep = 1.f / (float)(N - 1);
+          const float a0 = (float)j0, b0 = (float)(N - 1 - j0);
+          const float ua = j0 < N / 2 ? __fmul_rn(kStep, a0) : __fsub_rn(1.f, __fmul_rn(kStep, b0));
+          const float ub = j0 + 1 < N / 2 ? __fmul_rn(kStep, a0 + 1.f) : __fsub_rn(1.f, __fmul_rn(kStep, b0 - 1.f));
+          const int f = j0 + ((j0 < N && ua < ck) ? 1 + ((j0 + 1 < N && ub < ck) ? 1 : 0) : 0);
+          if (f < N) atomicAdd(&fh[f], 1);
+        }
+      }
+      __syncwarp();
+      int run = 0;
+      if constexpr (KN % 4 == 0) {
+#pragma unroll
+        for (int k = 0; k < KN; k += 4) {
+          const int4 q = *reinterpret_cast<const int4*>(fh + l * KN + k);
+          inds[k] = run + q.x; inds[k + 1] = inds[k] + q.y; inds[k + 2] = inds[k + 1] + q.z; inds[k + 3] = inds[k + 2] + q.w;
+          run = inds[k + 3];
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < KN; k += 2) {
+          const int2 q = *reinterpret_cast<const int2*>(fh + l * KN + k);
+          inds[k] = run + q.x; inds[k + 1] = inds[k] + q.y;
+          run = inds[k + 1];
+        }
+      }
+      int incl = run;
+#pragma unroll
+      for (int o = 1; o < LANES; o <<= 1) {
+        const int t = __shfl_up_sync(kFullMask, incl, o, LANES);
+        if (l >= o) incl += t;
+      }
+#pragma unroll
+      for (int k = 0; k < KN; ++k) inds[k] += incl - run;
+    } else {
+#pragma unroll
+      for (int k = 0; k < KN; ++k) inds[k] = count_below<LOGB, true>(cdf, B, uu[k]);
     }
     float sum = 0.f;
     int los[KN];
 #pragma unroll
     for (int k = 0; k < KN; ++k) {
-      const int ind = count_below<LOGB, true>(cdf, B, uu[k]);
+      const int ind = inds[k];
       const int lo = ind - 1 < 0 ? 0 : ind - 1;
       const int hi = ind > B - 1 ? B - 1 : ind;
-      const float c0 = cdf[lo], c1 = cdf[hi];
-      float den = c1 - c0;
+      float2 p0, p1;
+      if constexpr (DET) { p0 = cb[lo]; p1 = cb[hi]; }
+      else { p0 = make_float2(cdf[lo], bn[lo]); p1 = make_float2(cdf[hi], bn[hi]); }
+      float den = p1.x - p0.x;
       if (den < 1e-5f) den = 1.f;
-      const float t = __fdividef(uu[k] - c0, den);
-      const float b0 = bn[lo], b1 = bn[hi];
-      sv[k] = fmaf(t, b1 - b0, b0);
+      const float t = __fdividef(uu[k] - p0.x, den);
+      sv[k] = fmaf(t, p1.y - p0.y, p0.y);
       sum += sv[k];
       los[k] = lo;
-      if (inds_out != nullptr && valid) inds_out[ray * N + l * KN + k] = ind;
+    }
+    if (inds_out != nullptr) {                                                 // test hook: uniform branch, off in the render path
+#pragma unroll
+      for (int k = 0; k < KN; ++k)
+        if (valid) inds_out[ray * N + l * KN + k] = inds[k];
     }
     if (z_samples != nullptr && valid) {
+      if constexpr (KN % 4 == 0) {
+        if ((reinterpret_cast<uintptr_t>(z_samples) & 15) == 0) {
 #pragma unroll
-      for (int k = 0; k < KN; ++k) st_stream(z_samples + ray * N + l * KN + k, sv[k]);
+          for (int k = 0; k < KN; k += 4)
+            st_stream4(reinterpret_cast<float4*>(z_samples + ray * N + l * KN + k), make_float4(sv[k], sv[k + 1], sv[k + 2], sv[k + 3]));
+        } else {
+#pragma unroll
+          for (int k = 0; k < KN; ++k) st_stream(z_samples + ray * N + l * KN + k, sv[k]);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < KN; ++k) st_stream(z_samples + ray * N + l * KN + k, sv[k]);
+      }
     }
     if (z_std != nullptr) {                                                    // std(unbiased=False), run.py:2370
 #pragma unroll
@@ -752,9 +870,18 @@ __global__ void __launch_bounds__(kThreads, 4) sample_merge_cons_kernel(const fl
       const int nvalid = (int)((R - first) < RPW ? (R - first) : RPW);
       float4* out = reinterpret_cast<float4*>(z_merged + first * (S + N));
       constexpr int per_ray4 = (S + N) / 4;
-      for (int idx = lane; idx < nvalid * per_ray4; idx += 32) {
-        const int r = idx / per_ray4, o = idx - r * per_ray4;
-        st_stream4(out + idx, *reinterpret_cast<const float4*>(wm + (size_t)r * kPerRay + 3 * S + N + 4 * o));
+      if (nvalid == RPW && (RPW * per_ray4) % 32 == 0) {                       // whole groups: fixed trip count
+#pragma unroll
+        for (int it = 0; it < (RPW * per_ray4) / 32; ++it) {
+          const int idx = it * 32 + lane;
+          const int r = idx / per_ray4, o = idx - r * per_ray4;
+          st_stream4(out + idx, *reinterpret_cast<const float4*>(wm + r * kPerRay + 3 * S + N + 4 * o));
+        }
+      } else {
+        for (int idx = lane; idx < nvalid * per_ray4; idx += 32) {
+          const int r = idx / per_ray4, o = idx - r * per_ray4;
+          st_stream4(out + idx, *reinterpret_cast<const float4*>(wm + (size_t)r * kPerRay + 3 * S + N + 4 * o));
+        }
       }
     }
     __syncwarp();
@@ -770,6 +897,7 @@ static int launch_sample_merge_cons(const float* z_vals, const float* weights, c
   // resident CTAs per SM: 4 by registers (__launch_bounds__(256, 4), <= 64 registers), fewer if shared memory says so; a
   // persistent grid larger than what is resident runs its surplus CTAs as a second, half-empty wave
   const int per_sm = (int)((200 * 1024) / smem);
+  // (5 or 6 CTAs per SM at 48 / 40 registers: no faster - the kernel is bound by shared-memory wavefronts and issue slots)
   const int grid = persistent_grid((R + RPW - 1) / RPW, per_sm > 4 ? 4 : per_sm);
   if (u) sample_merge_cons_kernel<LANES, KN, false><<<grid, kThreads, smem, stream>>>(z_vals, weights, u, cdf_in, R, z_samples, z_merged, z_std, inds_out);
   else sample_merge_cons_kernel<LANES, KN, true><<<grid, kThreads, smem, stream>>>(z_vals, weights, u, cdf_in, R, z_samples, z_merged, z_std, inds_out);
@@ -832,7 +960,9 @@ extern "C" int gbn_zvals_stratified(const float* near, const float* far, int64_t
   GBN_REQUIRE(R >= 0 && S >= 1 && ray_stride >= 1, "zvals_stratified: bad sizes R=%lld S=%d", (long long)R, S);
   const int64_t blocks = (R * S + 255) / 256;
   const int grid = (int)(blocks < kNumSMs * 8 ? blocks : kNumSMs * 8);
-#define GBN_ZV(SS) if (S == SS) { zvals_fixed_kernel<SS><<<grid, 256, 0, (cudaStream_t)stream>>>(near, far, ray_stride, R, lindisp, t_rand, z); return check_launch("zvals_fixed_kernel"); }
+  const bool vec = ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(t_rand)) & 15) == 0;
+#define GBN_ZV(SS) if (S == SS && vec) { const int64_t bl = (R * (SS / 4) + 255) / 256; const int g = (int)(bl < kNumSMs * 8 ? bl : kNumSMs * 8); \
+    zvals_fixed_kernel<SS><<<g, 256, 0, (cudaStream_t)stream>>>(near, far, ray_stride, R, lindisp, t_rand, z); return check_launch("zvals_fixed_kernel"); }
   GBN_ZV(64) GBN_ZV(128) GBN_ZV(32) GBN_ZV(256)
 #undef GBN_ZV
   zvals_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(near, far, ray_stride, R, S, lindisp, t_rand, z);

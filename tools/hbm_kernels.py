@@ -6,7 +6,7 @@ launch list for ncu (cold-cache device time + DRAM bytes per launch):
         --log-file gpurun_out/hbm_launches.csv python tools/hbm_kernels.py 65536 once
 
 Algorithmic bytes per ray are SURVEY 8d's.  Replaces tools/hbm_roofline.py of round 1 (whose
-graph-replay harness read a plain 1 GiB copy at 46 % of the driver's copy figure: it counted one direction of the copy).
+graph-replay harness read a plain 1 GiB copy at 46 % of the driver's copy figure: a captured `copy_` is a memcpy node).
 Every launch goes through the C ABI directly with pre-allocated outputs, NSETS input sets are used round-robin so that
 no launch finds its operands in the 126 MB L2, and a plain torch copy of 1 GiB is timed the same way as the yardstick."""
 import ctypes as C
@@ -41,15 +41,26 @@ def nsets(bytes_per_set):
 
 
 def timed(name, bytes_alg, launch, sets):
-    """launch(i) enqueues one launch on input set i"""
+    """launch(i) enqueues one launch on input set i.  The `reps` launches are captured into ONE CUDA graph and the replay
+    is timed: issued from Python through ctypes a launch costs ~10 us of host time, which a 10-30 us kernel cannot hide
+    (late round 2: the small launches of this table were host-bound, not HBM-bound, in the first version)."""
     reps = 1 if ONCE else max(6, 2 * sets)
     for i in range(1 if ONCE else sets):
         launch(i % sets)
     torch.cuda.synchronize()
+    if ONCE:
+        return
+    side = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
+            for i in range(reps):
+                launch(i % sets)
+    g.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(reps):
-        launch(i % sets)
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / reps
@@ -58,10 +69,12 @@ def timed(name, bytes_alg, launch, sets):
 
 
 def bench_copy():
-    n = 1 << 30
-    a = [torch.empty(n, dtype=torch.uint8, device=dev) for _ in range(2)]
-    b = torch.empty(n, dtype=torch.uint8, device=dev)
-    timed("torch copy_ 1 GiB (read + write)", 2 * n, lambda i: b.copy_(a[i % 2]), 2)
+    # an elementwise KERNEL as the yardstick: inside a graph `copy_` of a contiguous buffer becomes a memcpy node, which
+    # the copy engines serve at ~3 TB/s (that, not a byte-count slip, was round 1's "46 % copy")
+    n = 1 << 28
+    a = [torch.empty(n, dtype=torch.float32, device=dev) for _ in range(2)]
+    b = torch.empty(n, dtype=torch.float32, device=dev)
+    timed("torch add(x, 1) 1 GiB (read + write)", 8 * n, lambda i: torch.add(a[i % 2], 1.0, out=b), 2)
 
 
 def bench_composite(S, noise, bwd):
