@@ -91,6 +91,11 @@ __device__ __forceinline__ void wg_wait(uint32_t bar, uint32_t parity, uint32_t 
 __device__ __forceinline__ void red_add(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
+// four adjacent floats in one reduction (16-byte aligned address): a quarter of the instructions and L2 transactions of
+// the flush, which is a fixed ~50 us tail of every wgrad launch
+__device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgArgs a) {
   using L = WgSmem;
@@ -216,13 +221,21 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgArgs a)
         if (w.head == 1) { keep = (n_out == 3); n_out = 0; }         // alpha_linear.weight is [1, 256]
         if (w.head == 2) { keep = (n_out < 3); n_out = keep ? n_out : 0; }   // rgb_linear.weight is [3, 128]
         float* dst = a.w[w.layer] + (size_t)n_out * w.ld + w.col0;
+        const bool vec4 = ((w.ld | w.col0) & 3) == 0 && (w.n_valid & 3) == 0 && (reinterpret_cast<uintptr_t>(a.w[w.layer]) & 15) == 0;
         for (int c0 = 0; c0 < w.n_blocks * 64; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(lane_addr + hf * 256 + c0, v);
           tmem_ld_wait();
+          if (vec4) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (keep && c0 + i < w.n_valid) red_add(dst + c0 + i, __uint_as_float(v[i]));
+            for (int i = 0; i < 32; i += 4)
+              if (keep && c0 + i < w.n_valid)
+                red_add4(dst + c0 + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (keep && c0 + i < w.n_valid) red_add(dst + c0 + i, __uint_as_float(v[i]));
+          }
         }
       }
       tc_fence_before_sync();

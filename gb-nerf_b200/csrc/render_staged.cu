@@ -606,6 +606,10 @@ __global__ void __launch_bounds__(kSegThreads) composite_fwd_seg_kernel(
   }
 }
 
+// The raw [S, 4] block of a ray is stored TRANSPOSED within each 128-sample segment (slot 32 c + l for sample 4 l + c): a
+// lane owns four consecutive samples, and with the row-major image its 16-byte reads are 64 bytes apart from lane to
+// lane - a 4-way bank conflict on every float4 and 16-way on the scalar .w reads, which made the shared-memory pipe
+// (68 % busy in ncu) and not HBM the limit of this kernel.  The bulk-copy side stays conflict-free and coalesced.
 template <int M, int D, bool NOISE, bool GW>
 __global__ void __launch_bounds__(kSegThreads) composite_bwd_seg_kernel(
     const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ noise,
@@ -628,7 +632,8 @@ __global__ void __launch_bounds__(kSegThreads) composite_bwd_seg_kernel(
     const uint32_t dst = ring_u32 + (uint32_t)(i % D) * ray_bytes;
     const float4* rsrc = reinterpret_cast<const float4*>(raw) + ray * S;
 #pragma unroll
-    for (int k = 0; k < 4 * M; ++k) cp_async16(dst + (k * 32 + lane) * 16, rsrc + k * 32 + lane);
+    for (int k = 0; k < 4 * M; ++k)   // transposed within each 128-sample segment: sample 4 l + c of a segment -> slot 32 c + l
+      cp_async16(dst + ((k >> 2) * 128 + (lane & 3) * 32 + (k & 3) * 8 + (lane >> 2)) * 16, rsrc + k * 32 + lane);
 #pragma unroll
     for (int k = 0; k < M; ++k) {
       cp_async16(dst + off_z + (k * 32 + lane) * 16, reinterpret_cast<const float4*>(z + ray * S) + k * 32 + lane);
@@ -685,7 +690,7 @@ __global__ void __launch_bounds__(kSegThreads) composite_bwd_seg_kernel(
         const float zn = k < 3 ? zz[k < 3 ? k + 1 : k] : znext;
         const float dl = (seg == M - 1 && lane == 31 && k == 3) ? 1e10f : (zn - zz[k]);
         dlt[k] = dl * dnorm;
-        pre[k] = sraw[base + k].w + nz[k];
+        pre[k] = sraw[seg * 128 + k * 32 + lane].w + nz[k];
         e[k] = __expf(-fmaxf(pre[k], 0.f) * dlt[k]);
         a[k] = 1.f - e[k];
         tl[k] = prod;
@@ -737,7 +742,7 @@ __global__ void __launch_bounds__(kSegThreads) composite_bwd_seg_kernel(
       float run = 0.f;
 #pragma unroll
       for (int k = 3; k >= 0; --k) {
-        const float4 rw = sraw[base + k];
+        const float4 rw = sraw[seg * 128 + k * 32 + lane];
         T[k] = t0[seg] * tl[k];
         w[k] = a[k] * T[k];
         G[k] = gdep * zz[k] + gacc + gw[k];
@@ -752,7 +757,7 @@ __global__ void __launch_bounds__(kSegThreads) composite_bwd_seg_kernel(
       float4* out = reinterpret_cast<float4*>(g_raw) + ray * S + base;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float4 rw = sraw[base + k];
+        const float4 rw = sraw[seg * 128 + k * 32 + lane];
         const float f = (1.f - a[k]) + 1e-10f;
         const float dalpha = G[k] * T[k] - __fdividef(suf[k] + later, f);
         const float cr = fast_sigmoid(rw.x), cg = fast_sigmoid(rw.y), cb = fast_sigmoid(rw.z);
