@@ -23,12 +23,21 @@ constexpr int kMaxJobs = 160;
 constexpr int kNumPlans = 3;          // 0 forward bf16, 1 forward tf32, 2 backward (dgrad) bf16
 constexpr int kPlanBwd = 2;
 
-// Training stash (bf16 only): per 128-point tile, 16 KB blocks that are byte images of the kernel's shared-memory
-// K-blocks ([128 rows x 128 B], 128-byte swizzle), so every consumer moves them with plain bulk copies.
+// Training stash (bf16 only): per 128-point tile, 16 KB blocks of [128 points x 64 channels].  Inside a block:
+//   [half (64 points)][chunk (8 channels = 16 B)][64 points][16 B]     (stash_chunk_off below)
+// so that (i) a warp of the epilogue (32 consecutive points, thread == point) writes each chunk as 512 contiguous
+// bytes straight from its registers - round 1/2 staged a 128-byte-swizzled row-major image in shared memory and bulk-stored
+// it, which cost the forward 35 % - (ii) a 64-point half block is 8 contiguous KB for wgrad's bulk copies and
+// IS the no-swizzle MN-major UMMA operand (core matrix = 8 points x 8 channels = 128 contiguous bytes, 128 B between
+// core matrices along the points, 1 KB along the channels), and (iii) dgrad's gate reads are conflict-free.
 //   H (written by the forward): h_l block b -> 4*l + b (l = 0..7) | feature -> 32..35 | hv -> 36,37 | enc -> 38 |
 //                               per-point view-direction encoding (27 of 64 channels) -> 39
 //   G (written by dgrad): g_hv -> 0,1 | g_feature -> 2..5 | g_l block b -> 6 + 4*l + b | g_raw (padded) -> 38
 constexpr int kStashBlocks = 40;
+// byte offset inside a stash block of the 16-byte chunk c (channels 8c .. 8c+7) of point r
+__host__ __device__ constexpr uint32_t stash_chunk_off(uint32_t r, uint32_t c) {
+  return (r >> 6) * 8192u + c * 1024u + (r & 63u) * 16u;
+}
 constexpr size_t kStashTileBytes = (size_t)kStashBlocks * kBlkBytes;
 constexpr int kHFeat = 32, kHHv = 36, kHEnc = 38, kHDir = 39;
 constexpr int kGHv = 0, kGFeat = 2, kGLayer0 = 6, kGRaw = 38;

@@ -114,7 +114,7 @@ __device__ __forceinline__ void st_global16(void* p, uint32_t a, uint32_t b, uin
 }
 
 // 32 consecutive output channels of one row -> the swizzled K-block in shared memory (bf16: 4 chunks of 16 B at
-// chunk0.., tf32: 8 chunks) and, when `gblk` is given, the same bytes to the stash block image in HBM
+// chunk0.., tf32: 8 chunks) and, when `gblk` (the BASE of a stash block) is given, the same values to that block in HBM
 template <bool BF16>
 __device__ __forceinline__ void store_group32(uint32_t row_addr, uint8_t* gblk, int row, int chunk0,
                                               const float (&f)[32], bool relu, bool to_smem = true) {
@@ -127,7 +127,7 @@ __device__ __forceinline__ void store_group32(uint32_t row_addr, uint8_t* gblk, 
         w[i] = relu ? pack_bf16_relu(f[c * 8 + 2 * i], f[c * 8 + 2 * i + 1]) : pack_bf16(f[c * 8 + 2 * i], f[c * 8 + 2 * i + 1]);
       const uint32_t off = ((uint32_t)((chunk0 + c) ^ (row & 7)) << 4);
       if (to_smem) st_smem16(row_addr + off, w[0], w[1], w[2], w[3]);
-      if (gblk != nullptr) st_global16(gblk + off, w[0], w[1], w[2], w[3]);
+      if (gblk != nullptr) st_global16(gblk + stash_chunk_off((uint32_t)row, (uint32_t)(chunk0 + c)), w[0], w[1], w[2], w[3]);
     }
   } else {
 #pragma unroll
@@ -288,13 +288,13 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) nerf_mlp_kernel(const MlpArgs 
         if (tr) tr[1] = clock64();
         if (t > 0) wait_bar(base + L::enc_empty, (t - 1) & 1, abort_addr, a.err, 0x30000000 | t);
         if (tr) tr[2] = clock64();
-        uint8_t* gblk = a.stash_g + (size_t)tile * kStashTileBytes + (size_t)kGRaw * kBlkBytes + row_off;
+        uint8_t* gblk = a.stash_g + (size_t)tile * kStashTileBytes + (size_t)kGRaw * kBlkBytes;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const uint32_t w0 = c == 0 ? pack_bf16(g.x, g.y) : 0u, w1 = c == 0 ? pack_bf16(g.z, g.w) : 0u;
           const uint32_t off = ((uint32_t)(c ^ (row & 7)) << 4);
           st_smem16(base + L::enc + row_off + off, w0, w1, 0u, 0u);
-          st_global16(gblk + off, w0, w1, 0u, 0u);
+          st_global16(gblk + stash_chunk_off((uint32_t)row, (uint32_t)c), w0, w1, 0u, 0u);
         }
       } else {
         float e[64];
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) nerf_mlp_kernel(const MlpArgs 
         if (t > 0) wait_bar(base + L::enc_empty, (t - 1) & 1, abort_addr, a.err, 0x30000000 | t);
         if (tr) tr[2] = clock64();
         uint8_t* gblk = (C::BF16 && a.stash_h != nullptr)
-                            ? a.stash_h + (size_t)tile * kStashTileBytes + (size_t)kHEnc * kBlkBytes + row_off : nullptr;
+                            ? a.stash_h + (size_t)tile * kStashTileBytes + (size_t)kHEnc * kBlkBytes : nullptr;
         // 64 channels: bf16 -> one K-block (8 chunks); tf32 -> two K-blocks (8 chunks each)
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
@@ -364,8 +364,8 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) nerf_mlp_kernel(const MlpArgs 
       float sigma_acc = 0.f;
       unsigned long long* tr = (a.trace && blockIdx.x == 0 && t == a.trace_tile && (threadIdx.x & 127) == 0)
                                    ? a.trace + 960 + wg * 128 : nullptr;
-      uint8_t* const tile_h = (C::BF16 && a.stash_h != nullptr) ? a.stash_h + (size_t)tile * kStashTileBytes + row_off : nullptr;
-      uint8_t* const tile_g = (C::BWD) ? a.stash_g + (size_t)tile * kStashTileBytes + row_off : nullptr;
+      uint8_t* const tile_h = (C::BF16 && a.stash_h != nullptr) ? a.stash_h + (size_t)tile * kStashTileBytes : nullptr;
+      uint8_t* const tile_g = (C::BWD) ? a.stash_g + (size_t)tile * kStashTileBytes : nullptr;
       for (int u = 0; u < C::NUNITS; ++u) {
         const EpiUnit eu = c_epi[PROG][u];
         if (eu.mode == EPI_OUT) break;
@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) nerf_mlp_kernel(const MlpArgs 
               const uint8_t* hb = tile_h + (size_t)(eu.mask_blk + b) * kBlkBytes;
 #pragma unroll
               for (int c = 0; c < 4; ++c)
-                hm[c] = __ldg(reinterpret_cast<const uint4*>(hb + ((uint32_t)((g * 4 + c) ^ (row & 7)) << 4)));
+                hm[c] = __ldg(reinterpret_cast<const uint4*>(hb + stash_chunk_off((uint32_t)row, (uint32_t)(g * 4 + c))));
             }
           }
           uint32_t v[32];

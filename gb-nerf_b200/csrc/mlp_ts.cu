@@ -8,7 +8,8 @@
 //   warp 2      TMEM allocator; dgrad: gate producer (bulk-loads the H-stash blocks that gate the next step)
 //   warps 4-7   per-tile input block (forward: points + positional + direction encoding, backward: padded g_raw) -> smem
 //   warps 8-15  epilogue: accumulator half -> registers (tcgen05.ld) -> +bias/ReLU (or ReLU gate) -> bf16 ->
-//               tcgen05.st into the other A buffer (the next layer's operand) [+ training stash to HBM]
+//               tcgen05.st into the other A buffer (the next layer's operand) [+ training stash: 16-byte stores straight
+//               from the registers, a warp covers 512 contiguous bytes per chunk (layout: stash_chunk_off)]
 // Hand-overs (mbarriers): acc_full[h] (commit of a half's last MMA -> epilogue), a_ready[buf][h] (epilogue -> issuers:
 // input half h of the next layer is in TMEM), acc1_empty (half 1 has been read out, ~600 cycles before a_ready), and in
 // the dgrad program a_ready_b[buf] (second 32-channel instalment of input half 1).
@@ -67,16 +68,16 @@ constexpr bool kDiag = false;
 constexpr int kTsThreads = 512;
 constexpr int kTsStageBytes = 32768;
 
-// Shared memory: input block | weight ring | stash-out staging (2 block images, one per epilogue warpgroup) |
-// [backward: gate staging, 2 x 2 block images] | [forward: bias table] | barriers
+// Shared memory: input block | weight ring | [backward: gate staging, 2 x 2 stash blocks] | [forward: bias table] |
+// barriers.  (The training stash leaves through registers -> global since late round 2; the 32 KB staging area it used to
+// take is gone.)
 template <bool BWD>
 struct TsSmemT {
   static constexpr int NST = BWD ? 3 : 4;
   static constexpr uint32_t enc = 0;
   static constexpr uint32_t dir = enc + kBlkBytes;                       // forward only: view-direction encoding block
   static constexpr uint32_t ring = dir + (BWD ? 0 : kBlkBytes);
-  static constexpr uint32_t ostage = ring + NST * kTsStageBytes;
-  static constexpr uint32_t mstage = ostage + 2 * kBlkBytes;
+  static constexpr uint32_t mstage = ring + NST * kTsStageBytes;
   static constexpr uint32_t bias = mstage + (BWD ? 4 * kBlkBytes : 0);
   static constexpr uint32_t bars = bias + (BWD ? 0 : kTsBiasFloats * 4);
   static constexpr uint32_t w_full = bars;
@@ -236,14 +237,6 @@ __device__ __forceinline__ void ts_st_global16(void* p, uint32_t a, uint32_t b, 
   asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// bulk async store shared -> global (one 16 KB stash block image per call), tracked by bulk async-groups
-__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void wg_bar(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory"); }
 __device__ __forceinline__ uint4 ld_smem16(uint32_t addr) {
   uint4 r;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
@@ -519,13 +512,14 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
       ts_chaos(a.chaos, (unsigned)t, a.chaos_roles & 8u);
       if (t > 0) ts_wait(base + L::enc_empty, (t - 1) & 1, abort_addr, a.err, 0x30000000 | t);
       uint8_t* gblk = nullptr;
-      if constexpr (BWD) gblk = a.stash_g + (size_t)tile * kStashTileBytes + (size_t)kGRaw * kBlkBytes + row_off;
-      else if (a.stash_h != nullptr) gblk = a.stash_h + (size_t)tile * kStashTileBytes + (size_t)kHEnc * kBlkBytes + row_off;
+      if constexpr (BWD) gblk = a.stash_g + (size_t)tile * kStashTileBytes + (size_t)kGRaw * kBlkBytes;
+      else if (a.stash_h != nullptr) gblk = a.stash_h + (size_t)tile * kStashTileBytes + (size_t)kHEnc * kBlkBytes;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const uint32_t off = ((uint32_t)(c ^ (row & 7)) << 4);
         st_smem16(base + L::enc + row_off + off, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
-        if (gblk != nullptr) ts_st_global16(gblk + off, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+        if (gblk != nullptr)
+          ts_st_global16(gblk + stash_chunk_off((uint32_t)row, (uint32_t)c), w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
       }
       fence_proxy_async_smem();
       mbar_arrive(base + L::enc_full);
@@ -553,7 +547,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
           }
         }
         if (t > 0) ts_wait(base + L::dir_empty, (t - 1) & 1, abort_addr, a.err, 0x31000000 | t);
-        uint8_t* db = a.stash_h != nullptr ? a.stash_h + (size_t)tile * kStashTileBytes + (size_t)kHDir * kBlkBytes + row_off : nullptr;
+        uint8_t* db = a.stash_h != nullptr ? a.stash_h + (size_t)tile * kStashTileBytes + (size_t)kHDir * kBlkBytes : nullptr;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           uint32_t q[4] = {0u, 0u, 0u, 0u};
@@ -563,7 +557,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
           }
           const uint32_t off = ((uint32_t)(c ^ (row & 7)) << 4);
           st_smem16(base + L::dir + row_off + off, q[0], q[1], q[2], q[3]);
-          if (db != nullptr) ts_st_global16(db + off, q[0], q[1], q[2], q[3]);
+          if (db != nullptr) ts_st_global16(db + stash_chunk_off((uint32_t)row, (uint32_t)c), q[0], q[1], q[2], q[3]);
         }
         fence_proxy_async_smem();
         mbar_arrive(base + L::dir_full);
@@ -576,8 +570,6 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) << 5) << 16);
     const uint32_t row_off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
     const float* sbias = reinterpret_cast<const float*>(gen + L::bias);
-    const bool storer = (threadIdx.x & 127) == 0;      // issues this warpgroup's bulk stash stores
-    const uint32_t my_ostage = base + L::ostage + wg * kBlkBytes;
     uint32_t accpar = 0, mc = 0;
     for (int t = 0; t < my_tiles; ++t) {
       const int64_t tile = blockIdx.x + (int64_t)t * gridDim.x;
@@ -620,24 +612,20 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
           if constexpr (BWD) gout = a.stash_g + (size_t)tile * kStashTileBytes + (size_t)(st.out_blk + wg) * kBlkBytes;
           else if (a.stash_h != nullptr) gout = a.stash_h + (size_t)tile * kStashTileBytes + (size_t)(st.out_blk + wg) * kBlkBytes;
         }
-        if (gout != nullptr) {       // the previous bulk store must have finished reading the staging block
-          if (storer) bulk_wait_read0();
-          wg_bar(wg);
-        }
         // both 32-channel groups in flight at once: two tcgen05.ld, one wait, then the arithmetic, two tcgen05.st
         uint4 hm[2][4];
         if constexpr (BWD) {
           if (kDiag && st.mode == EPI_MASK && a.gate_direct) {
-            const uint4* hg = reinterpret_cast<const uint4*>(a.stash_h + (size_t)tile * kStashTileBytes +
-                                                             (size_t)(st.mask_blk + wg) * kBlkBytes + row_off);
+            const uint8_t* hg = a.stash_h + (size_t)tile * kStashTileBytes + (size_t)(st.mask_blk + wg) * kBlkBytes;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) hm[c >> 2][c & 3] = __ldg(hg + (c ^ (row & 7)));
+            for (int c = 0; c < 8; ++c)
+              hm[c >> 2][c & 3] = __ldg(reinterpret_cast<const uint4*>(hg + stash_chunk_off((uint32_t)row, (uint32_t)c)));
           } else if (st.mode == EPI_MASK) {
             const uint32_t b = mc & 1;
             ts_wait(base + L::m_full + 8 * b, (mc >> 1) & 1, abort_addr, a.err, 0x41000000 | (si << 8) | wg);
-            const uint32_t hb = base + L::mstage + (b * 2 + wg) * kBlkBytes + row_off;
+            const uint32_t hb = base + L::mstage + (b * 2 + wg) * kBlkBytes;   // byte image of the stash block
 #pragma unroll
-            for (int c = 0; c < 8; ++c) hm[c >> 2][c & 3] = ld_smem16(hb + ((uint32_t)(c ^ (row & 7)) << 4));
+            for (int c = 0; c < 8; ++c) hm[c >> 2][c & 3] = ld_smem16(hb + stash_chunk_off((uint32_t)row, (uint32_t)c));
 #ifdef GBN_TS_DIAG
             if (a.fix & 2u) {
 #pragma unroll
@@ -660,12 +648,11 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
               // gate check: the same 128 bytes straight from the H stash; on a mismatch log where, when, and whether the
               // wrong chunk equals the gates of the NEXT fill of this staging buffer (two EPI_MASK steps ahead) or of the
               // PREVIOUS one.  Record: [tile, si | warp << 8 | lane << 16, mc, chunk mask | next << 8 | prev << 16, clock]
-              const uint4* hg = reinterpret_cast<const uint4*>(a.stash_h + (size_t)tile * kStashTileBytes +
-                                                               (size_t)(st.mask_blk + wg) * kBlkBytes + row_off);
+              const uint8_t* hg = a.stash_h + (size_t)tile * kStashTileBytes + (size_t)(st.mask_blk + wg) * kBlkBytes;
               unsigned bad = 0;
 #pragma unroll
               for (int c = 0; c < 8; ++c) {
-                const uint4 g = __ldg(hg + (c ^ (row & 7))), h = hm[c >> 2][c & 3];
+                const uint4 g = __ldg(reinterpret_cast<const uint4*>(hg + stash_chunk_off((uint32_t)row, (uint32_t)c))), h = hm[c >> 2][c & 3];
                 if (g.x != h.x || g.y != h.y || g.z != h.z || g.w != h.w) bad |= 1u << c;
               }
               if (bad) {
@@ -687,12 +674,12 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
                   const uint4 h = hm[c >> 2][c & 3];
                   if (tile_next < ntiles_all) {
                     const uint4 g = __ldg(reinterpret_cast<const uint4*>(a.stash_h + (size_t)tile_next * kStashTileBytes +
-                                                                       (size_t)(blk_next + wg) * kBlkBytes + row_off) + (c ^ (row & 7)));
+                                                                       (size_t)(blk_next + wg) * kBlkBytes + stash_chunk_off((uint32_t)row, (uint32_t)c)));
                     if (g.x == h.x && g.y == h.y && g.z == h.z && g.w == h.w) eq_next |= 1u << c;
                   }
                   if (tile_prev >= 0) {
                     const uint4 g = __ldg(reinterpret_cast<const uint4*>(a.stash_h + (size_t)tile_prev * kStashTileBytes +
-                                                                       (size_t)(blk_prev + wg) * kBlkBytes + row_off) + (c ^ (row & 7)));
+                                                                       (size_t)(blk_prev + wg) * kBlkBytes + stash_chunk_off((uint32_t)row, (uint32_t)c)));
                     if (g.x == h.x && g.y == h.y && g.z == h.z && g.w == h.w) eq_prev |= 1u << c;
                   }
                 }
@@ -758,17 +745,12 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
               mbar_arrive(base + L::a_ready + 8 * (st.out_buf * 2 + 1));
             }
           }
-          if (gout != nullptr) {
+          if (gout != nullptr) {   // training stash: a warp's 32 consecutive points make every chunk 512 contiguous bytes
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-              st_smem16(my_ostage + row_off + ((uint32_t)((g * 4 + c) ^ (row & 7)) << 4), w[4 * c], w[4 * c + 1], w[4 * c + 2],
-                        w[4 * c + 3]);
+              ts_st_global16(gout + stash_chunk_off((uint32_t)row, (uint32_t)(g * 4 + c)), w[4 * c], w[4 * c + 1], w[4 * c + 2],
+                             w[4 * c + 3]);
           }
-        }
-        if (gout != nullptr) {       // block image complete in shared memory -> one 16 KB bulk store per warpgroup
-          fence_proxy_async_smem();
-          wg_bar(wg);
-          if (storer) bulk_s2g(gout, my_ostage, kBlkBytes);
         }
         ts_chaos(a.chaos, 0x20000000u + (unsigned)(t * 64 + si), a.chaos_roles & 32u);
         if (!st.no_act) {
@@ -782,7 +764,6 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_ts_kernel(const TsArgs
       tc_fence_before_sync();
       mbar_arrive(base + L::tile_done);
     }
-    if (storer) bulk_wait0();
   }
 
   tc_fence_before_sync();

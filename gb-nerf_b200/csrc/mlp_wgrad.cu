@@ -3,8 +3,8 @@
 // nn.Linear modules of run_nerf_helpers.py:88-104.
 //
 //   wgrad_tc_kernel     dW_l[n,k] = sum_p G_l[p,n] H_{l-1}[p,k] for the ten wide layers on tcgen05: both operands are
-//                       the stash block images themselves ([128 points x 64 channels], 128B swizzle), consumed as
-//                       MN-major UMMA operands (M = out channel, N = in channel, K = points), fp32 accumulators for
+//                       the stash half blocks themselves ([8-channel chunk][64 points][16 B], mlp_layout.h), consumed as
+//                       no-swizzle MN-major UMMA operands (M = out channel, N = in channel, K = points), fp32 accumulators for
 //                       a whole 256x256 weight gradient in TMEM (2 x 256 columns), split-K over point tiles across
 //                       CTAs, flushed with red.global.add.  Bias gradients (column sums of G) are taken from the
 //                       same shared-memory tiles by otherwise idle warps.
@@ -12,6 +12,8 @@
 //                       g_raw block (M = 128 filled by loading it twice; rows 0..2 / 3 are the gradients).
 //   viewdir_grad_kernel the 27 direction columns of views_linears.0 (constant along a ray, folded into a per-ray
 //                       bias in the forward): per-ray sums of g_hv, then an outer product with enc(viewdir).
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "common.cuh"
@@ -66,12 +68,15 @@ struct WgSmem {
   static constexpr uint32_t alloc = total + 1024;
 };
 
-// MN-major operand, 128-byte swizzle (cute: ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO))): 64 contiguous channels per
-// 128-byte row, rows = the K (point) index 128 B apart, 8-row groups SBO apart, 64-channel groups LBO apart
-__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+// MN-major operand without swizzle (cute INTERLEAVE: ((T,1,m),(8,k)):((1,T,SBO),(1T,LBO)), T = 8 bf16 = 16 B): a core
+// matrix is 8 K rows (points) x 16 B of MN (8 channels) = 128 contiguous bytes; core matrices are LBO apart along K
+// (128 B: the next 8 points of the same chunk) and SBO apart along MN (1 KB: the next 8-channel chunk, uniform across the
+// half blocks of a stage because a half block is exactly 8 chunks)
+__device__ __forceinline__ uint64_t smem_desc_mn_interleave(uint32_t addr, uint32_t lbo, uint32_t sbo) {
   return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+         ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
+constexpr uint32_t kWgLbo = 128, kWgSbo = 1024;
 
 __device__ __forceinline__ void wg_wait(uint32_t bar, uint32_t parity, uint32_t abort_addr, int* err, int code) {
   if (mbar_try_wait(bar, parity)) return;
@@ -160,12 +165,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgArgs a)
       const uint32_t sa = base + L::ring + s * kWgStageBytes, sb = sa + 4 * kWgHalf;
       if (elect_one()) {
         for (int hf = 0; hf < nhalves; ++hf) {
-          const uint64_t adesc = smem_desc_mn_sw128(sa + hf * 2 * kWgHalf, kWgHalf, 1024);
-          const uint64_t bdesc = smem_desc_mn_sw128(sb, kWgHalf, 1024);
+          const uint64_t adesc = smem_desc_mn_interleave(sa + hf * 2 * kWgHalf, kWgLbo, kWgSbo);
+          const uint64_t bdesc = smem_desc_mn_interleave(sb, kWgLbo, kWgSbo);
           const uint32_t d = tmem + hf * 256;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)   // 16 points = 16 rows of 128 B = 2048 B -> +128 in the address field
-            umma_bf16(d, adesc + 128 * k, bdesc + 128 * k, idesc, (i == 0 && k == 0) ? 0u : 1u);
+          for (int k = 0; k < 4; ++k)   // 16 points = two 8-point core-matrix rows of 128 B -> +16 in the address field
+            umma_bf16(d, adesc + 16 * k, bdesc + 16 * k, idesc, (i == 0 && k == 0) ? 0u : 1u);
         }
         umma_commit(base + L::empty + 8 * s);
         if (i == nstages - 1) umma_commit(base + L::done);
@@ -173,22 +178,35 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgArgs a)
       __syncwarp();
     }
   } else if (warp >= 4 && warp < 8) {
-    // ---- bias gradient: column sums of the G tile, two adjacent channels (one 32-bit word) per thread ---------
-    const int t = threadIdx.x - 128;            // 0..127 -> channels 2t, 2t+1
-    const int blk = t >> 5, wd = t & 31;        // 64-channel block, word within the 128-byte row
-    const bool active = w.do_bias && blk < w.m_blocks;
-    float s0 = 0.f, s1 = 0.f;
+    // ---- bias gradient: column sums of the G tile.  Warp q owns the 8-channel chunks q, q + 4, ... of the tile, a lane
+    // the points lane and lane + 32 of the stage: one conflict-free 16-byte read per chunk and point, eight running sums
+    // per chunk in registers, and one shuffle reduction per channel at the very end
+    const int q = warp - 4;
+    constexpr int kMaxChunks = 8;                                     // (4 blocks x 8 chunks) / 4 warps
+    const int nchunks = !w.do_bias ? 0 : (w.head ? (q == 0 ? 1 : 0) : w.m_blocks * 2);   // chunks of this warp
+    float acc[kMaxChunks][8];
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[c][e] = 0.f;
     for (int64_t i = 0; i < nstages; ++i) {
       const uint32_t s = (uint32_t)(i % kWgStages), par = (uint32_t)((i / kWgStages) & 1);
       wg_wait(base + L::full + 8 * s, par, abort_addr, a.err, 0x52000000 | (int)s);
-      if (active) {
-        const uint8_t* blkp = gen + L::ring + s * kWgStageBytes + blk * kWgHalf;
-#pragma unroll 8
-        for (int r = 0; r < 64; ++r) {
-          const uint32_t off = (uint32_t)r * 128u + ((uint32_t)((wd >> 2) ^ (r & 7)) << 4) + (uint32_t)(wd & 3) * 4u;
-          const uint32_t v = *reinterpret_cast<const uint32_t*>(blkp + off);
-          s0 += __uint_as_float(v << 16);
-          s1 += __uint_as_float(v & 0xffff0000u);
+      const uint8_t* tile = gen + L::ring + s * kWgStageBytes;
+#pragma unroll
+      for (int c = 0; c < kMaxChunks; ++c) {
+        if (c < nchunks) {
+          const uint8_t* cp = tile + (size_t)(q + 4 * c) * 1024;       // chunk (q + 4c): block (q + 4c) / 8, chunk % 8 - contiguous
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint4 v = *reinterpret_cast<const uint4*>(cp + (lane + 32 * h) * 16);
+            const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              acc[c][2 * e] += __uint_as_float(wv[e] << 16);
+              acc[c][2 * e + 1] += __uint_as_float(wv[e] & 0xffff0000u);
+            }
+          }
         }
       }
       // generic-proxy reads of a bulk-copied stage, then the stage goes back to the bulk-copy producer: proxy fence
@@ -197,15 +215,27 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgArgs a)
       __syncwarp();
       if (lane == 0) mbar_arrive(base + L::empty + 8 * s);
     }
-    if (active && nstages > 0) {
-      if (w.head == 0) {
-        red_add(a.b[w.layer] + 2 * t, s0);
-        red_add(a.b[w.layer] + 2 * t + 1, s1);
-      } else if (w.head == 1) {          // g_raw channels: (r, g, b, sigma)
-        if (t == 1) red_add(a.b[w.layer], s1);
-      } else {
-        if (t == 0) { red_add(a.b[w.layer], s0); red_add(a.b[w.layer] + 1, s1); }
-        if (t == 1) red_add(a.b[w.layer] + 2, s0);
+    if (nstages > 0) {
+#pragma unroll
+      for (int c = 0; c < kMaxChunks; ++c) {
+        if (c < nchunks) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float v = acc[c][e];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            acc[c][e] = v;
+          }
+          if (lane < 8) {
+            float mine = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) mine = lane == e ? acc[c][e] : mine;
+            const int ch = (q + 4 * c) * 8 + lane;                     // channel within the item's M rows
+            if (w.head == 0) red_add(a.b[w.layer] + ch, mine);
+            else if (w.head == 1) { if (ch == 3) red_add(a.b[w.layer], mine); }      // g_raw channels: (r, g, b, sigma)
+            else if (ch < 3) red_add(a.b[w.layer] + ch, mine);
+          }
+        }
       }
     }
   } else if (warp >= 8) {
@@ -248,7 +278,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgArgs a)
 }
 
 __device__ __forceinline__ float stash_bf16(const uint8_t* tile, int blk, int row, int col) {
-  const uint32_t off = (uint32_t)blk * kBlkBytes + tc::sw128_offset((uint32_t)row, (uint32_t)(col >> 3)) + (uint32_t)(col & 7) * 2u;
+  const uint32_t off = (uint32_t)blk * kBlkBytes + stash_chunk_off((uint32_t)row, (uint32_t)(col >> 3)) + (uint32_t)(col & 7) * 2u;
   return __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(tile + off)) << 16);
 }
 

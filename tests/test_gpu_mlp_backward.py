@@ -21,12 +21,10 @@ def G():
 
 
 def decode_stash(stash, ntiles):
-    """uint8 stash -> bf16 [ntiles, 39, 128 rows, 64 channels] with the 128-byte swizzle undone."""
-    x = stash.view(torch.bfloat16).view(ntiles, N_BLOCKS, 128, 8, 8)
-    r = torch.arange(128, device=stash.device)[:, None]
-    c = torch.arange(8, device=stash.device)[None, :]
-    idx = (c ^ (r & 7))[None, None, :, :, None].expand(ntiles, N_BLOCKS, 128, 8, 8)
-    return torch.gather(x, 3, idx).reshape(ntiles, N_BLOCKS, 128, 64).float().cpu()
+    """uint8 stash -> bf16 [ntiles, blocks, 128 points, 64 channels]; a block is [half (64 points)][chunk (8 channels)]
+    [64 points][8 channels] (csrc/mlp_layout.h, stash_chunk_off)."""
+    x = stash.view(torch.bfloat16).view(ntiles, N_BLOCKS, 2, 8, 64, 8)      # half, chunk, point, channel
+    return x.permute(0, 1, 2, 4, 3, 5).reshape(ntiles, N_BLOCKS, 128, 64).float().cpu()
 
 
 def rows(dec, blk0, nblk, P):

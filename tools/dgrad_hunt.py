@@ -52,11 +52,8 @@ def dgrad(out):
 
 
 def unswizzle(blk):
-    """uint8 [16384] block image -> float [128 rows, 64 channels]"""
-    x = blk.view(torch.bfloat16).view(128, 8, 8)
-    r = torch.arange(128, device=blk.device)[:, None]
-    c = torch.arange(8, device=blk.device)[None, :]
-    return torch.gather(x, 1, (c ^ (r & 7))[:, :, None].expand(128, 8, 8)).reshape(128, 64).float()
+    """uint8 [16384] stash block -> float [128 points, 64 channels] (layout: csrc/mlp_layout.h, stash_chunk_off)"""
+    return blk.view(torch.bfloat16).view(2, 8, 64, 8).permute(0, 2, 1, 3).reshape(128, 64).float()
 
 
 def tile_rows(stash, tile, blk0, nblk):
