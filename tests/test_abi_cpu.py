@@ -130,7 +130,7 @@ def test_proxy_fence_precedes_every_release_of_a_bulk_copied_buffer_read_with_or
     before = ts[ts.rindex("ld_smem16(hb", 0, i):i]
     assert "fence_proxy_async_smem();" in before, "dgrad epilogue: no proxy fence between the gate reads and the m_empty arrival"
     wg = open(os.path.join(root, "gb-nerf_b200", "csrc", "mlp_wgrad.cu")).read()
-    j = wg.index("const uint32_t v = *reinterpret_cast<const uint32_t*>(blkp + off);")
+    j = wg.index("const uint4 v = *reinterpret_cast<const uint4*>(cp + (lane + 32 * h) * 16);")
     k = wg.index("mbar_arrive(base + L::empty + 8 * s);", j)
     assert "fence_proxy_async_smem();" in wg[j:k], "wgrad bias warps: no proxy fence between the tile reads and the stage release"
     # the only other generic reads of bulk-copied shared memory would be new code: flag any ld.shared helper use in the
