@@ -73,7 +73,7 @@ constexpr int kTsStageBytes = 32768;
 // take is gone.)
 template <bool BWD>
 struct TsSmemT {
-  static constexpr int NST = BWD ? 3 : 4;
+  static constexpr int NST = 4;   // (the dgrad program had 3 while a 32 KB stash staging area shared its shared memory)
   static constexpr uint32_t enc = 0;
   static constexpr uint32_t dir = enc + kBlkBytes;                       // forward only: view-direction encoding block
   static constexpr uint32_t ring = dir + (BWD ? 0 : kBlkBytes);

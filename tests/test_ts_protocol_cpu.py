@@ -21,7 +21,7 @@ def plans():
 
 def test_tables_are_the_documented_shape(plans):
     fwd, bwd = plans[0], plans[1]
-    assert (len(fwd.jobs), fwd.stages, len(bwd.jobs), bwd.stages) == (42, 4, 37, 3)
+    assert (len(fwd.jobs), fwd.stages, len(bwd.jobs), bwd.stages) == (42, 4, 37, 4)
     # two issuers, one ring: the jobs whose stage was last used by the other issuer carry the guard flag
     for p in (fwd, bwd):
         n = len(p.jobs)
@@ -47,12 +47,15 @@ def test_dgrad_protocol_is_clean_without_the_split_handover(plans):
 
 
 def test_model_reproduces_the_ring_alias_when_the_guard_is_off(plans):
-    """Validation of the model itself: without ts_wait_progress the dgrad program (3 stages, 4 jobs per layer) lets
-    half 1's issuer test a stage on the other issuer's phase when weight fills are slow - the launch failure seen on
-    the GPU (profiles/r1_ring_alias.md)."""
+    """Validation of the model itself: without ts_wait_progress the dgrad program on a THREE-stage ring (4 jobs per layer;
+    what the kernel had until the stash staging area left its shared memory) lets half 1's issuer test a stage on the
+    other issuer's phase when weight fills are slow - the launch failure seen on the GPU (profiles/r1_ring_alias.md)."""
+    import copy
+    three = copy.copy(plans[1])
+    three.stages = 3
     hits = 0
     for seed in range(12):
-        errs = M.simulate(plans[1], tiles=4, seed=seed, cold=1.0, guard=False)
+        errs = M.simulate(three, tiles=4, seed=seed, cold=1.0, guard=False)
         hits += any(e.split(": ", 1)[1].startswith(("alias", "rearm")) or "weight stage" in e for e in errs)
     assert hits >= 3, hits
 
