@@ -608,8 +608,10 @@ __global__ void __launch_bounds__(kSegThreads) composite_fwd_seg_kernel(
 
 // The raw [S, 4] block of a ray is stored TRANSPOSED within each 128-sample segment (slot 32 c + l for sample 4 l + c): a
 // lane owns four consecutive samples, and with the row-major image its 16-byte reads are 64 bytes apart from lane to
-// lane - a 4-way bank conflict on every float4 and 16-way on the scalar .w reads, which made the shared-memory pipe
-// (68 % busy in ncu) and not HBM the limit of this kernel.  The bulk-copy side stays conflict-free and coalesced.
+// lane - a 4-way bank conflict on every float4 and 16-way on the scalar .w reads (shared-memory pipe 68 % busy in ncu,
+// 33 % with this placement).  The bulk-copy side stays conflict-free and coalesced.  The kernel itself gained only 2 %:
+// at 384 samples it holds 12 warps per SM (two whole rays per warp in shared memory) and is bound by the latency of its
+// two passes over the ray, not by a pipe.
 template <int M, int D, bool NOISE, bool GW>
 __global__ void __launch_bounds__(kSegThreads) composite_bwd_seg_kernel(
     const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ noise,
