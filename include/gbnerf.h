@@ -133,8 +133,10 @@ int gbn_mlp_forward(const void* packed, int precision, const float* rays_o, cons
                     int S, float* raw, void* workspace, void* stash, void* stream);
 
 /* Training stash (bf16 only).  When `stash` is non-NULL the forward also writes, per 128-point tile, the bf16
- * activations the backward needs (8 hidden layers, feature, view-branch hidden, point encoding) as 16 KB block
- * images of its shared-memory tiles: gbn_mlp_stash_bytes(P) bytes, 128-byte aligned. */
+ * activations the backward needs (8 hidden layers, feature, view-branch hidden, point and direction encoding) as
+ * 16 KB blocks of [128 points x 64 channels], laid out [64-point half][8-channel chunk][64 points][16 B]: opaque to
+ * the caller, consumed by gbn_mlp_backward_data / gbn_mlp_backward_weights.  gbn_mlp_stash_bytes(P) bytes,
+ * 128-byte aligned. */
 size_t gbn_mlp_stash_bytes(int64_t P);
 
 /* Diagnostic: when buf is non-NULL (device memory, >= 16 KiB, zeroed by the caller), CTA 0 of every following MLP
