@@ -1,0 +1,542 @@
+// Two tiles in flight per CTA ("T2"): the inference form of the bf16 TMEM-operand MLP (included by mlp_ts.cu, inside
+// namespace gbn; same packed weight image, same inputs and outputs as nerf_mlp_ts_kernel<fwd> without a stash).
+//
+// Why: one 128-point tile per SM leaves the tensor pipe idle while the epilogue converts an accumulator half and the
+// issuer waits for the hand-over - a ~2,700-cycle dependency chain per layer against 2,048 cycles of tensor work
+// (DESIGN 3.1).  A second tile fills those gaps, but the four-region layout (acc0 | acc1 | A0 | A1) already takes all
+// 512 TMEM columns for ONE tile.  Here a tile owns 256 columns:
+//     slot s:  A_s = [256 s, 256 s + 128)   activations, 128 rows x 256 bf16, overwritten IN PLACE
+//              ACC_s = [256 s + 128, 256 s + 256)   one 128-channel accumulator half
+// A layer runs as: MMAs of output half 0 -> epilogue reads ACC, converts, KEEPS the 128 bf16 channels in registers ->
+// MMAs of half 1 (ACC again) -> epilogue reads ACC, and - every MMA that reads A_s has completed by then - stores
+// both halves over A_s.  Each slot has its own issuing warp and its own epilogue warpgroup, so the two tiles drift into
+// anti-phase by themselves: one slot's MMAs run while the other's epilogue works.
+//
+//   warp 0      weight producer: every slab is fetched ONCE for both slots (half the L2 -> shared-memory stream)
+//   warp 1, 3   MMA issuer of slot 0 / slot 1; both walk the same slab sequence, w_empty counts two commits
+//   warp 2      TMEM allocator
+//   warps 4-7   per-tile input blocks (positional + direction encoding) of both slots
+//   warps 8-11  epilogue of slot 0 (thread == row, 128 channels per step);  warps 12-15: slot 1
+// alpha_linear (256 -> 1) and rgb_linear (128 -> 3) run on the CUDA cores inside the epilogue that produces their
+// input (same bf16 operands and fp32 accumulation as the tiny MMAs of the one-tile kernel; 640 FMAs per point), which
+// removes their accumulator columns and two hand-overs per tile.
+
+constexpr int kT2MaxJobs = 48, kT2MaxSteps = 24;
+enum : uint16_t {
+  T2_WAIT_ENC = 1, T2_WAIT_DIR = 2, T2_WAIT_A = 4, T2_WAIT_EMPTY = 8, T2_FIRST = 16, T2_A_ENC = 32, T2_A_DIR = 64,
+  T2_COMMIT_ACC = 128, T2_COMMIT_ENC = 256, T2_COMMIT_DIR = 512, T2_TILE_FIRST = 1024
+};
+struct T2Job {
+  uint32_t w_off;       // slab offset in the packed image (the kTsFwd image, unchanged)
+  uint16_t bytes16;     // slab bytes / 16
+  uint16_t flags;
+  uint16_t a_col;       // column of the first K-block of A inside the slot's A region
+  uint8_t ksteps;       // shared-memory A operand: 16-wide K steps (4 encoding, 2 direction)
+  uint8_t nkb;
+  uint32_t pad;
+};
+static_assert(sizeof(T2Job) == 16, "T2Job layout");
+enum : uint8_t { T2_HOLD = 0, T2_FLUSH = 1, T2_OUT = 2 };
+struct T2Step {
+  uint8_t mode, relu, dot, pad;   // dot: this layer's output feeds alpha_linear (sigma accumulates in the epilogue)
+  uint16_t bias_off, pad2;
+};
+static_assert(sizeof(T2Step) == 8, "T2Step layout");
+__constant__ T2Job c_t2jobs[kT2MaxJobs];
+__constant__ T2Step c_t2steps[kT2MaxSteps];
+
+struct T2Smem {
+  static constexpr int NST = 4;
+  static constexpr uint32_t enc = 0;                                   // [2] encoding block per slot
+  static constexpr uint32_t dir = enc + 2 * kBlkBytes;                 // [2] direction block per slot
+  static constexpr uint32_t ring = dir + 2 * kBlkBytes;
+  static constexpr uint32_t bias = ring + NST * kTsStageBytes;
+  static constexpr uint32_t walpha = bias + kTsBiasFloats * 4;         // 256 floats
+  static constexpr uint32_t wrgb = walpha + 256 * 4;                   // 128 x float4 (r, g, b, 0)
+  static constexpr uint32_t bars = wrgb + 128 * 16;
+  static constexpr uint32_t w_full = bars;
+  static constexpr uint32_t w_empty = w_full + 8 * NST;
+  static constexpr uint32_t acc_full = w_empty + 8 * NST;              // [slot]
+  static constexpr uint32_t acc_empty = acc_full + 16;
+  static constexpr uint32_t a_ready = acc_empty + 16;
+  static constexpr uint32_t enc_full = a_ready + 16;
+  static constexpr uint32_t enc_empty = enc_full + 16;
+  static constexpr uint32_t dir_full = enc_empty + 16;
+  static constexpr uint32_t dir_empty = dir_full + 16;
+  static constexpr uint32_t tmem_ptr = dir_empty + 16;
+  static constexpr uint32_t abort_flag = tmem_ptr + 4;
+  static constexpr uint32_t total = abort_flag + 4;
+  static constexpr uint32_t alloc = total + 1024;
+};
+static_assert(T2Smem::alloc <= 232448, "shared memory budget");
+static_assert((T2Smem::bars & 7) == 0 && (T2Smem::wrgb & 15) == 0 && (T2Smem::bias & 15) == 0, "alignment");
+
+struct T2Args {
+  const uint8_t* packed;
+  const float* ro; const float* rd; const float* z; const float* pts; const float* emb; const float* vd;
+  float* raw;
+  int* err;
+  int64_t stride, P;
+  int S, njobs, nsteps;
+  uint32_t off_alpha[2], off_rgb;
+};
+
+__device__ __forceinline__ float t2_bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float t2_bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+// 32 accumulator columns + bias (-> ReLU) -> 16 bf16x2 words
+template <bool RELU>
+__device__ __forceinline__ void t2_convert(const uint32_t (&v)[32], const float* bias32, uint32_t* w) {
+  const float4* bp = reinterpret_cast<const float4*>(bias32);
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const float4 bb = bp[i >> 2];
+    float f0, f1, f2, f3;
+    add_f32x2(v[i], v[i + 1], bb.x, bb.y, f0, f1);
+    add_f32x2(v[i + 2], v[i + 3], bb.z, bb.w, f2, f3);
+    w[i >> 1] = RELU ? pack_bf16_relu(f0, f1) : pack_bf16(f0, f1);
+    w[(i >> 1) + 1] = RELU ? pack_bf16_relu(f2, f3) : pack_bf16(f2, f3);
+  }
+}
+// sigma += <32 bf16 channels, 32 fp32 weights>
+__device__ __forceinline__ float t2_dot32(const uint32_t* w, const float* wa32, float acc) {
+  const float4* ap = reinterpret_cast<const float4*>(wa32);
+#pragma unroll
+  for (int i = 0; i < 16; i += 2) {
+    const float4 a = ap[i >> 1];
+    acc = fmaf(t2_bf16_lo(w[i]), a.x, acc);
+    acc = fmaf(t2_bf16_hi(w[i]), a.y, acc);
+    acc = fmaf(t2_bf16_lo(w[i + 1]), a.z, acc);
+    acc = fmaf(t2_bf16_hi(w[i + 1]), a.w, acc);
+  }
+  return acc;
+}
+// rgb += hv[32 channels] . W_rgb^T   (wrgb: float4 (r, g, b, 0) per input channel)
+__device__ __forceinline__ void t2_rgb32(const uint32_t* w, const float4* wr, float& r, float& g, float& b) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float lo = t2_bf16_lo(w[i]), hi = t2_bf16_hi(w[i]);
+    const float4 a = wr[2 * i], c = wr[2 * i + 1];
+    r = fmaf(lo, a.x, r); g = fmaf(lo, a.y, g); b = fmaf(lo, a.z, b);
+    r = fmaf(hi, c.x, r); g = fmaf(hi, c.y, g); b = fmaf(hi, c.z, b);
+  }
+}
+
+template <int SLOT>
+__device__ __noinline__ void t2_issue_loop(int* err, int njobs, uint32_t base, uint32_t abort_addr, uint32_t tmem, int my_pairs) {
+  using L = T2Smem;
+  const uint64_t adesc_enc = smem_desc_sw128(base + L::enc + SLOT * kBlkBytes);
+  const uint64_t adesc_dir = smem_desc_sw128(base + L::dir + SLOT * kBlkBytes);
+  const uint64_t ring_desc0 = smem_desc_sw128(base + L::ring);
+  const uint32_t idesc = make_idesc(1, 128, 128);
+  const uint32_t d = tmem + 256u * SLOT + 128u, a_base = tmem + 256u * SLOT;
+  const uint32_t b_acc_full = base + L::acc_full + 8 * SLOT, b_acc_empty = base + L::acc_empty + 8 * SLOT;
+  const uint32_t b_a_ready = base + L::a_ready + 8 * SLOT;
+  const uint32_t b_enc_full = base + L::enc_full + 8 * SLOT, b_enc_empty = base + L::enc_empty + 8 * SLOT;
+  const uint32_t b_dir_full = base + L::dir_full + 8 * SLOT, b_dir_empty = base + L::dir_empty + 8 * SLOT;
+  uint32_t s = 0, par = 0, ph_a = 0, ph_e = 0;
+  for (int it = 0; it < my_pairs; ++it) {
+    for (int j = 0; j < njobs; ++j) {
+      const T2Job rc = c_t2jobs[j];
+      const uint32_t fl = rc.flags;
+      if (fl & T2_WAIT_ENC) ts_wait(b_enc_full, (uint32_t)it & 1u, abort_addr, err, 0x72000000 | (SLOT << 16) | j);
+      if (fl & T2_WAIT_DIR) ts_wait(b_dir_full, (uint32_t)it & 1u, abort_addr, err, 0x73000000 | (SLOT << 16) | j);
+      if (fl & T2_WAIT_A) { ts_wait(b_a_ready, ph_a, abort_addr, err, 0x74000000 | (SLOT << 16) | j); ph_a ^= 1u; }
+      if ((fl & T2_WAIT_EMPTY) && !((fl & T2_TILE_FIRST) && it == 0)) {
+        ts_wait(b_acc_empty, ph_e, abort_addr, err, 0x75000000 | (SLOT << 16) | j);
+        ph_e ^= 1u;
+      }
+      ts_wait(base + L::w_full + 8 * s, par, abort_addr, err, 0x76000000 | (SLOT << 16) | j);
+      tc_fence_after_sync();
+      const uint64_t bd0 = ring_desc0 + (uint64_t)(s * (kTsStageBytes >> 4));
+      const uint64_t bd1 = bd0 + 1024u;        // second K-block image: 128 rows x 128 B further on
+      const uint32_t first = (fl & T2_FIRST) ? 0u : 1u;
+      if (elect_one()) {
+        if (!(fl & (T2_A_ENC | T2_A_DIR))) {   // 8 MMAs, A = two K-blocks (64 K each) of the slot's activations in TMEM
+          const uint32_t a_t = a_base + rc.a_col;
+          umma_bf16_ts(d, a_t, bd0, idesc, first);
+          umma_bf16_ts(d, a_t + 8, bd0 + 2, idesc, 1u);
+          umma_bf16_ts(d, a_t + 16, bd0 + 4, idesc, 1u);
+          umma_bf16_ts(d, a_t + 24, bd0 + 6, idesc, 1u);
+          umma_bf16_ts(d, a_t + 32, bd1, idesc, 1u);
+          umma_bf16_ts(d, a_t + 40, bd1 + 2, idesc, 1u);
+          umma_bf16_ts(d, a_t + 48, bd1 + 4, idesc, 1u);
+          umma_bf16_ts(d, a_t + 56, bd1 + 6, idesc, 1u);
+        } else {
+          const uint64_t adesc = (fl & T2_A_DIR) ? adesc_dir : adesc_enc;
+          umma_bf16(d, adesc, bd0, idesc, first);
+          umma_bf16(d, adesc + 2, bd0 + 2, idesc, 1u);
+          if (rc.ksteps == 4) {
+            umma_bf16(d, adesc + 4, bd0 + 4, idesc, 1u);
+            umma_bf16(d, adesc + 6, bd0 + 6, idesc, 1u);
+          }
+        }
+        umma_commit(base + L::w_empty + 8 * s);
+        if (fl & T2_COMMIT_ACC) umma_commit(b_acc_full);
+        if (fl & T2_COMMIT_ENC) umma_commit(b_enc_empty);
+        if (fl & T2_COMMIT_DIR) umma_commit(b_dir_empty);
+      }
+      __syncwarp();
+      if (++s == (uint32_t)L::NST) { s = 0; par ^= 1u; }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_t2_kernel(const T2Args a) {
+  using L = T2Smem;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* const gen = smem_raw + (base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ntiles = (a.P + kTileRows - 1) / kTileRows;
+  const int64_t npairs = (ntiles + 1) >> 1;
+  const int my_pairs = (int)((npairs - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  const uint32_t abort_addr = base + L::abort_flag;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < L::NST; ++i) { mbar_init(base + L::w_full + 8 * i, 1); mbar_init(base + L::w_empty + 8 * i, 2); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(base + L::acc_full + 8 * s, 1);
+      mbar_init(base + L::acc_empty + 8 * s, 128);
+      mbar_init(base + L::a_ready + 8 * s, 128);
+      mbar_init(base + L::enc_full + 8 * s, 128);
+      mbar_init(base + L::enc_empty + 8 * s, 1);
+      mbar_init(base + L::dir_full + 8 * s, 128);
+      mbar_init(base + L::dir_empty + 8 * s, 1);
+    }
+    *reinterpret_cast<volatile uint32_t*>(gen + L::abort_flag) = 0;
+    mbar_init_fence();
+  }
+  if (warp == 2) tmem_alloc(base + L::tmem_ptr, kTmemCols);
+  {
+    const float* gb = reinterpret_cast<const float*>(a.packed + reinterpret_cast<const uint32_t*>(a.packed)[2]);
+    float* sb = reinterpret_cast<float*>(gen + L::bias);
+    for (int i = threadIdx.x; i < kTsBiasFloats; i += blockDim.x) sb[i] = __ldg(gb + i);
+    // alpha_linear.weight[0, :] and rgb_linear.weight[0:3, :] decoded from their bf16 slabs (row n of a 16-row
+    // K-block image: sw128_offset(n, chunk))
+    float* wa = reinterpret_cast<float*>(gen + L::walpha);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+      const int kp = i >> 7, kb = (i >> 6) & 1, kk = i & 63;
+      const uint16_t bits = __ldg(reinterpret_cast<const uint16_t*>(a.packed + a.off_alpha[kp] + kb * 2048 + kk * 2));
+      wa[i] = __uint_as_float((uint32_t)bits << 16);
+    }
+    float* wr = reinterpret_cast<float*>(gen + L::wrgb);
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+      const int k = i >> 2, n = i & 3, kb = k >> 6, kk = k & 63;
+      float v = 0.f;
+      if (n < 3) {
+        const uint16_t bits = __ldg(reinterpret_cast<const uint16_t*>(
+            a.packed + a.off_rgb + kb * 2048 + sw128_offset((uint32_t)n, (uint32_t)(kk >> 3)) + (kk & 7) * 2));
+        v = __uint_as_float((uint32_t)bits << 16);
+      }
+      wr[i] = v;
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + L::tmem_ptr);
+
+
+  if (warp == 0) {
+    // =============================== weight producer: one fill per slab, consumed by both issuers ===================
+    uint32_t s = 0, par = 0;
+    for (int it = 0; it < my_pairs; ++it)
+      for (int j = 0; j < a.njobs; ++j) {
+        ts_wait(base + L::w_empty + 8 * s, par ^ 1u, abort_addr, a.err, 0x71000000 | j);
+        const uint32_t bytes = (uint32_t)c_t2jobs[j].bytes16 * 16;
+        const uint8_t* src = a.packed + c_t2jobs[j].w_off;
+        if (elect_one()) {
+          mbar_expect_tx(base + L::w_full + 8 * s, bytes);
+          tma_bulk_g2s(base + L::ring + s * kTsStageBytes, src, bytes, base + L::w_full + 8 * s);
+        }
+        __syncwarp();
+        if (++s == (uint32_t)L::NST) { s = 0; par ^= 1u; }
+      }
+  } else if (warp == 1) {
+    t2_issue_loop<0>(a.err, a.njobs, base, abort_addr, tmem, my_pairs);
+  } else if (warp == 3) {
+    t2_issue_loop<1>(a.err, a.njobs, base, abort_addr, tmem, my_pairs);
+  } else if (warp >= 4 && warp < 8) {
+    // =============================== per-tile input blocks of both slots: thread == row =============================
+    const int row = threadIdx.x - 128;
+    const uint32_t row_off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
+    for (int it = 0; it < my_pairs; ++it) {
+      const int64_t tile0 = 2 * ((int64_t)blockIdx.x + (int64_t)it * gridDim.x);
+#pragma unroll 1
+      for (int sl = 0; sl < 2; ++sl) {
+        const int64_t p = (tile0 + sl) * kTileRows + row;
+        uint32_t w[32];
+        {
+          float e[64];
+          if (p < a.P) {
+            if (a.emb != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 63; ++i) e[i] = __ldg(a.emb + p * GBN_EMB_CH + i);
+            } else {
+              float x[3];
+              if (a.pts != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) x[i] = __ldg(a.pts + p * 3 + i);
+              } else {
+                const int64_t r = p / a.S;
+                const float zz = __ldg(a.z + p);
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                  x[i] = __fadd_rn(__ldg(a.ro + r * a.stride + i), __fmul_rn(__ldg(a.rd + r * a.stride + i), zz));
+              }
+#pragma unroll
+              for (int i = 0; i < 3; ++i) {
+                float sc[20];
+                posenc_axis<10>(x[i], sc);
+                e[i] = x[i];
+#pragma unroll
+                for (int k = 0; k < 10; ++k) { e[3 + 6 * k + i] = sc[2 * k]; e[6 + 6 * k + i] = sc[2 * k + 1]; }
+              }
+            }
+            e[63] = 0.f;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) e[i] = 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) w[i] = pack_bf16(e[2 * i], e[2 * i + 1]);
+        }
+        if (it > 0) ts_wait(base + L::enc_empty + 8 * sl, (uint32_t)(it - 1) & 1u, abort_addr, a.err, 0x78000000 | (sl << 16) | it);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t off = ((uint32_t)(c ^ (row & 7)) << 4);
+          st_smem16(base + L::enc + sl * kBlkBytes + row_off + off, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(base + L::enc_full + 8 * sl);
+      }
+#pragma unroll 1
+      for (int sl = 0; sl < 2; ++sl) {
+        const int64_t p = (tile0 + sl) * kTileRows + row;
+        float e[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) e[i] = 0.f;
+        if (p < a.P) {
+          if (a.emb != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 27; ++i) e[i] = __ldg(a.emb + p * GBN_EMB_CH + GBN_PTS_CH + i);
+          } else {
+            const int64_t r = p / a.S;
+#pragma unroll
+            for (int ax = 0; ax < 3; ++ax) {
+              const float x = __ldg(a.vd + r * a.stride + ax);
+              float sc[8];
+              posenc_axis<4>(x, sc);
+              e[ax] = x;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) { e[3 + 6 * k + ax] = sc[2 * k]; e[6 + 6 * k + ax] = sc[2 * k + 1]; }
+            }
+          }
+        }
+        if (it > 0) ts_wait(base + L::dir_empty + 8 * sl, (uint32_t)(it - 1) & 1u, abort_addr, a.err, 0x79000000 | (sl << 16) | it);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint32_t q[4] = {0u, 0u, 0u, 0u};
+          if (c < 4) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) q[i] = pack_bf16(e[8 * c + 2 * i], e[8 * c + 2 * i + 1]);
+          }
+          const uint32_t off = ((uint32_t)(c ^ (row & 7)) << 4);
+          st_smem16(base + L::dir + sl * kBlkBytes + row_off + off, q[0], q[1], q[2], q[3]);
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(base + L::dir_full + 8 * sl);
+      }
+    }
+  } else if (warp >= 8) {
+    // =============================== epilogue of one slot: thread == row, 128 channels per step ======================
+    const int slot = (warp - 8) >> 2;
+    const int row = ((warp & 3) << 5) | lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) << 5) << 16);
+    const uint32_t acc = lane_addr + 256u * slot + 128u, abuf = lane_addr + 256u * slot;
+    const uint32_t b_acc_full = base + L::acc_full + 8 * slot, b_acc_empty = base + L::acc_empty + 8 * slot;
+    const uint32_t b_a_ready = base + L::a_ready + 8 * slot;
+    const float* sbias = reinterpret_cast<const float*>(gen + L::bias);
+    const float* walpha = reinterpret_cast<const float*>(gen + L::walpha);
+    const float4* wrgb = reinterpret_cast<const float4*>(gen + L::wrgb);
+    uint32_t ph = 0;
+    for (int it = 0; it < my_pairs; ++it) {
+      const int64_t tile = 2 * ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) + slot;
+      const int64_t p = tile * kTileRows + row;
+      float sigma = 0.f;
+      uint32_t held[64];   // output half 0 of the current layer (bf16x2), waiting for half 1
+      for (int si = 0; si < a.nsteps; ++si) {
+        const T2Step st = c_t2steps[si];
+        ts_wait(b_acc_full, ph, abort_addr, a.err, 0x7a000000 | (slot << 16) | si);
+        ph ^= 1u;
+        tc_fence_after_sync();
+        const float* bias = sbias + st.bias_off;
+        // One 32-column group in flight at a time: the 64 registers of the held half leave room for no more
+        // (512 threads x 128 registers is the whole register file).
+        uint32_t v[32];
+        if (st.mode == T2_HOLD) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            tmem_ld32(acc + 32 * c, v);
+            tmem_ld_wait();
+            if (c == 3) {                      // ACC_s is in registers: the MMAs of half 1 may overwrite it
+              tc_fence_before_sync();
+              mbar_arrive(b_acc_empty);
+            }
+            if (st.relu) t2_convert<true>(v, bias + 32 * c, &held[16 * c]);
+            else t2_convert<false>(v, bias + 32 * c, &held[16 * c]);
+          }
+          if (st.dot) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) sigma = t2_dot32(&held[16 * c], walpha + 32 * c, sigma);
+          }
+        } else if (st.mode == T2_FLUSH) {
+          // every MMA of this layer has completed (acc_full follows the last one): A_s may be overwritten in place
+          tmem_ld32(acc, v);
+          {
+            uint32_t w[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) w[i] = held[16 * c + i];
+              tmem_st16(abuf + 16 * c, w);
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t w[16];
+            if (c > 0) tmem_ld32(acc + 32 * c, v);
+            tmem_ld_wait();
+            if (st.relu) t2_convert<true>(v, bias + 128 + 32 * c, w); else t2_convert<false>(v, bias + 128 + 32 * c, w);
+            tmem_st16(abuf + 64 + 16 * c, w);
+            if (st.dot) sigma = t2_dot32(w, walpha + 128 + 32 * c, sigma);
+          }
+          tmem_st_wait();
+          tc_fence_before_sync();
+          mbar_arrive(b_a_ready);              // next layer's input is in A_s (and ACC_s has been read out)
+        } else {
+          // views_linears.0 output (128 channels) -> ReLU -> rgb_linear on the CUDA cores -> (r, g, b, sigma)
+          float cr = 0.f, cg = 0.f, cb = 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t w[16];
+            tmem_ld32(acc + 32 * c, v);
+            tmem_ld_wait();
+            if (c == 3) {                      // the next tile's layer 0 may start on ACC_s
+              tc_fence_before_sync();
+              mbar_arrive(b_acc_empty);
+            }
+            t2_convert<true>(v, bias + 32 * c, w);
+            t2_rgb32(w, wrgb + 32 * c, cr, cg, cb);
+          }
+          if (p < a.P) {
+            float4 o;
+            o.x = cr + sbias[kBiasRgb + 0];
+            o.y = cg + sbias[kBiasRgb + 1];
+            o.z = cb + sbias[kBiasRgb + 2];
+            o.w = sigma + sbias[kBiasAlpha];
+            st_stream4(reinterpret_cast<float4*>(a.raw) + p, o);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, kTmemCols);
+}
+
+// ---- host: job / step tables from the forward plan's slab list -------------------------------------------------------
+struct T2Tables {
+  std::vector<T2Job> jobs;
+  std::vector<T2Step> steps;
+  uint32_t off_alpha[2], off_rgb;
+  bool ok;
+};
+
+static T2Tables t2_build(const TsPlan& p) {
+  T2Tables t{};
+  t.ok = true;
+  auto slab = [&](int layer, int row0, int col0, int nkb) -> const TsPackJob* {
+    for (const TsPackJob& q : p.pack)
+      if (q.layer == layer && q.row0 == row0 && q.col0 == col0 && q.nkb == nkb) return &q;
+    t.ok = false;
+    return &p.pack[0];
+  };
+  auto job = [&](const TsPackJob* q, int flags, int a_col, int ksteps) {
+    T2Job j{};
+    j.w_off = q->w_off; j.bytes16 = (uint16_t)(q->nkb * q->rows * 8); j.flags = (uint16_t)flags; j.a_col = (uint16_t)a_col;
+    j.ksteps = (uint8_t)ksteps; j.nkb = q->nkb;
+    if (q->rows != 128) t.ok = false;
+    t.jobs.push_back(j);
+  };
+  auto step = [&](int mode, int relu, int dot, int bias_off) {
+    T2Step s{};
+    s.mode = (uint8_t)mode; s.relu = (uint8_t)relu; s.dot = (uint8_t)dot; s.bias_off = (uint16_t)bias_off;
+    t.steps.push_back(s);
+  };
+  // layer 0: A = the slot's encoding block
+  job(slab(0, 0, 0, 1), T2_WAIT_ENC | T2_TILE_FIRST | T2_WAIT_EMPTY | T2_FIRST | T2_A_ENC | T2_COMMIT_ACC, 0, 4);
+  job(slab(0, 128, 0, 1), T2_WAIT_EMPTY | T2_FIRST | T2_A_ENC | T2_COMMIT_ACC, 0, 4);
+  step(T2_HOLD, 1, 0, 0); step(T2_FLUSH, 1, 0, 0);
+  auto wide = [&](int layer, int c0, bool skip) {
+    for (int h = 0; h < 2; ++h) {
+      job(slab(layer, 128 * h, c0, 2), (h == 0 ? T2_WAIT_A : T2_WAIT_EMPTY) | T2_FIRST, 0, 4);
+      job(slab(layer, 128 * h, c0 + 128, 2), skip ? 0 : T2_COMMIT_ACC, 64, 4);
+      if (skip) job(slab(layer, 128 * h, 0, 1), T2_A_ENC | T2_COMMIT_ACC | (h == 1 ? T2_COMMIT_ENC : 0), 0, 4);
+    }
+  };
+  for (int l = 1; l <= 7; ++l) {
+    wide(l, l == 5 ? 63 : 0, l == 5);
+    step(T2_HOLD, 1, l == 7, 256 * l); step(T2_FLUSH, 1, l == 7, 256 * l);
+  }
+  wide(LIN_FEATURE, 0, false);
+  step(T2_HOLD, 0, 0, kBiasFeat); step(T2_FLUSH, 0, 0, kBiasFeat);
+  job(slab(LIN_VIEWS, 0, 0, 2), T2_WAIT_A | T2_FIRST, 0, 4);
+  job(slab(LIN_VIEWS, 0, 128, 2), 0, 64, 4);
+  job(slab(LIN_VIEWS, 0, 256, 1), T2_WAIT_DIR | T2_A_DIR | T2_COMMIT_ACC | T2_COMMIT_DIR, 0, 2);
+  step(T2_OUT, 1, 0, kTsBiasViews);
+  // alpha / rgb slabs (16 rows): decoded to fp32 in the kernel prologue
+  t.off_alpha[0] = t.off_alpha[1] = t.off_rgb = 0;
+  for (const TsPackJob& q : p.pack) {
+    if (q.layer == LIN_ALPHA && q.rows == 16 && q.nkb == 2) t.off_alpha[q.col0 >= 128 ? 1 : 0] = q.w_off;
+    if (q.layer == LIN_RGB && q.rows == 16 && q.nkb == 2) t.off_rgb = q.w_off;
+  }
+  if (!t.off_alpha[0] || !t.off_alpha[1] || !t.off_rgb) t.ok = false;
+  if ((int)t.jobs.size() > kT2MaxJobs || (int)t.steps.size() > kT2MaxSteps) t.ok = false;
+  return t;
+}
+
+static T2Tables g_t2;
+
+// GBNERF_MLP_T2=0 keeps inference on the one-tile kernel
+static bool t2_enabled() {
+  static const bool on = [] { const char* e = getenv("GBNERF_MLP_T2"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
+static int t2_upload() {   // called from ts_ensure_device (per device)
+  if (g_t2.jobs.empty()) g_t2 = t2_build(ts_plan(0));
+  GBN_REQUIRE(g_t2.ok, "T2 job table does not match the forward plan");
+  GBN_CUDA(cudaMemcpyToSymbol(c_t2jobs, g_t2.jobs.data(), g_t2.jobs.size() * sizeof(T2Job), 0, cudaMemcpyHostToDevice));
+  GBN_CUDA(cudaMemcpyToSymbol(c_t2steps, g_t2.steps.data(), g_t2.steps.size() * sizeof(T2Step), 0, cudaMemcpyHostToDevice));
+  GBN_CUDA(cudaFuncSetAttribute(nerf_mlp_t2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2Smem::alloc));
+  return GBN_OK;
+}
+
+static int t2_forward(const void* packed, const float* ro, const float* rd, const float* vd, int64_t stride, const float* z,
+                      const float* pts, const float* emb, int64_t R, int S, float* raw, int* err, cudaStream_t stream) {
+  T2Args a{};
+  a.packed = reinterpret_cast<const uint8_t*>(packed);
+  a.ro = ro; a.rd = rd; a.z = z; a.pts = pts; a.emb = emb; a.vd = vd; a.raw = raw; a.err = err;
+  a.stride = stride; a.P = R * S; a.S = S;
+  a.njobs = (int)g_t2.jobs.size(); a.nsteps = (int)g_t2.steps.size();
+  a.off_alpha[0] = g_t2.off_alpha[0]; a.off_alpha[1] = g_t2.off_alpha[1]; a.off_rgb = g_t2.off_rgb;
+  const int64_t ntiles = (a.P + kTileRows - 1) / kTileRows;
+  const int64_t npairs = (ntiles + 1) / 2;
+  const int grid = (int)(npairs < kNumSMs ? npairs : kNumSMs);
+  nerf_mlp_t2_kernel<<<grid, kTsThreads, T2Smem::alloc, stream>>>(a);
+  return check_launch("nerf_mlp_t2_kernel");
+}

@@ -921,6 +921,8 @@ static void ts_build_issue(const TsPlan& p, std::vector<TsIssue> (&out)[2]) {
   }
 }
 
+#include "mlp_t2.cuh"   // two tiles in flight per CTA: the inference kernel (same packed image)
+
 static int ts_ensure_device(cudaStream_t stream) {
   int dev = 0;
   GBN_CUDA(cudaGetDevice(&dev));
@@ -962,6 +964,7 @@ static int ts_ensure_device(cudaStream_t stream) {
   }
   GBN_CUDA(cudaFuncSetAttribute(nerf_mlp_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TsSmemT<false>::alloc));
   GBN_CUDA(cudaFuncSetAttribute(nerf_mlp_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TsSmemT<true>::alloc));
+  { const int rc2 = t2_upload(); if (rc2 != GBN_OK) return rc2; }
   g_ts_init[dev] = true;
   return GBN_OK;
 }
@@ -1143,6 +1146,13 @@ int ts_forward(const void* packed, const float* ro, const float* rd, const float
   int* err = reinterpret_cast<int*>(workspace);
   GBN_CUDA(cudaMemsetAsync(err, 0, 256, stream));
   const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
+  {
+    unsigned long long* trace = nullptr; int trace_tile = 0;
+    mlp_get_trace(&trace, &trace_tile);
+    // inference (no stash, no in-kernel trace requested): two tiles in flight per CTA
+    if (stash == nullptr && trace == nullptr && t2_enabled())
+      return t2_forward(packed, ro, rd, vd, stride, z, pts, emb, R, S, raw, err, stream);
+  }
   TsArgs a{};
   a.packed = pk; a.ro = ro; a.rd = rd; a.z = z; a.pts = pts; a.emb = emb; a.vd = vd; a.raw = raw;
   a.stash_h = static_cast<uint8_t*>(stash); a.err = err; a.stride = stride; a.P = R * S; a.S = S;
