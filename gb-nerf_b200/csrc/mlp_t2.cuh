@@ -33,7 +33,9 @@ struct T2Job {
   uint16_t a_col;       // column of the first K-block of A inside the slot's A region
   uint8_t ksteps;       // shared-memory A operand: 16-wide K steps (4 encoding, 2 direction)
   uint8_t nkb;
-  uint32_t pad;
+  uint8_t glen;         // first job of an MMA group (the jobs of one accumulator half): jobs in the group, else 0
+  uint8_t pad;
+  uint16_t gflags;      // first job of a group: the wait flags of all its jobs
 };
 static_assert(sizeof(T2Job) == 16, "T2Job layout");
 enum : uint8_t { T2_HOLD = 0, T2_FLUSH = 1, T2_OUT = 2 };
@@ -53,7 +55,8 @@ struct T2Smem {
   static constexpr uint32_t bias = ring + NST * kTsStageBytes;
   static constexpr uint32_t walpha = bias + kTsBiasFloats * 4;         // 256 floats
   static constexpr uint32_t wrgb = walpha + 256 * 4;                   // 128 x float4 (r, g, b, 0)
-  static constexpr uint32_t bars = wrgb + 128 * 16;
+  static constexpr uint32_t red = wrgb + 128 * 16;                     // [slot][row] float4: (r, g, b, sigma) partial sums of wg 1
+  static constexpr uint32_t bars = red + 2 * 128 * 16;
   static constexpr uint32_t w_full = bars;
   static constexpr uint32_t w_empty = w_full + 8 * NST;
   static constexpr uint32_t acc_full = w_empty + 8 * NST;              // [slot]
@@ -63,7 +66,8 @@ struct T2Smem {
   static constexpr uint32_t enc_empty = enc_full + 16;
   static constexpr uint32_t dir_full = enc_empty + 16;
   static constexpr uint32_t dir_empty = dir_full + 16;
-  static constexpr uint32_t tmem_ptr = dir_empty + 16;
+  static constexpr uint32_t lead = dir_empty + 16;                     // u32 pad | u32: MMA groups whose issue has been released (turn)
+  static constexpr uint32_t tmem_ptr = lead + 8;
   static constexpr uint32_t abort_flag = tmem_ptr + 4;
   static constexpr uint32_t total = abort_flag + 4;
   static constexpr uint32_t alloc = total + 1024;
@@ -79,6 +83,10 @@ struct T2Args {
   int64_t stride, P;
   int S, njobs, nsteps;
   uint32_t off_alpha[2], off_rgb;
+  unsigned long long* trace;   // optional clock64 timeline of CTA 0, pair iteration trace_it (tools/t2_trace.py):
+  int mode;                    // kernel variant (GBNERF_T2_MODE): see the MODE template parameter
+  int trace_it;                // [(slot*48 + job)*4 ..] issuer: start, operands ready, weights landed, issued |
+                               // [512 + (slot*24 + step)*4 ..] epilogue: wait start, accumulator ready, handed over, step done
 };
 
 __device__ __forceinline__ float t2_bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
@@ -123,7 +131,8 @@ __device__ __forceinline__ void t2_rgb32(const uint32_t* w, const float4* wr, fl
 }
 
 template <int SLOT>
-__device__ __noinline__ void t2_issue_loop(int* err, int njobs, uint32_t base, uint32_t abort_addr, uint32_t tmem, int my_pairs) {
+__device__ __noinline__ void t2_issue_loop(int* err, int njobs, uint32_t base, uint32_t abort_addr, uint32_t tmem, int my_pairs,
+                                           unsigned long long* trace, int trace_it) {
   using L = T2Smem;
   const uint64_t adesc_enc = smem_desc_sw128(base + L::enc + SLOT * kBlkBytes);
   const uint64_t adesc_dir = smem_desc_sw128(base + L::dir + SLOT * kBlkBytes);
@@ -139,6 +148,8 @@ __device__ __noinline__ void t2_issue_loop(int* err, int njobs, uint32_t base, u
     for (int j = 0; j < njobs; ++j) {
       const T2Job rc = c_t2jobs[j];
       const uint32_t fl = rc.flags;
+      unsigned long long* tr = (kDiag && trace && blockIdx.x == 0 && it == trace_it && (threadIdx.x & 31) == 0) ? trace + (SLOT * 48 + j) * 4 : nullptr;
+      if (tr) tr[0] = clock64();
       if (fl & T2_WAIT_ENC) ts_wait(b_enc_full, (uint32_t)it & 1u, abort_addr, err, 0x72000000 | (SLOT << 16) | j);
       if (fl & T2_WAIT_DIR) ts_wait(b_dir_full, (uint32_t)it & 1u, abort_addr, err, 0x73000000 | (SLOT << 16) | j);
       if (fl & T2_WAIT_A) { ts_wait(b_a_ready, ph_a, abort_addr, err, 0x74000000 | (SLOT << 16) | j); ph_a ^= 1u; }
@@ -146,7 +157,9 @@ __device__ __noinline__ void t2_issue_loop(int* err, int njobs, uint32_t base, u
         ts_wait(b_acc_empty, ph_e, abort_addr, err, 0x75000000 | (SLOT << 16) | j);
         ph_e ^= 1u;
       }
+      if (tr) tr[1] = clock64();
       ts_wait(base + L::w_full + 8 * s, par, abort_addr, err, 0x76000000 | (SLOT << 16) | j);
+      if (tr) tr[2] = clock64();
       tc_fence_after_sync();
       const uint64_t bd0 = ring_desc0 + (uint64_t)(s * (kTsStageBytes >> 4));
       const uint64_t bd1 = bd0 + 1024u;        // second K-block image: 128 rows x 128 B further on
@@ -177,11 +190,107 @@ __device__ __noinline__ void t2_issue_loop(int* err, int njobs, uint32_t base, u
         if (fl & T2_COMMIT_DIR) umma_commit(b_dir_empty);
       }
       __syncwarp();
+      if (tr) tr[3] = clock64();
       if (++s == (uint32_t)L::NST) { s = 0; par ^= 1u; }
     }
   }
 }
 
+// Mode 2: a group's MMAs (16 for a wide layer half) are issued back to back after ALL of the group's waits - operands,
+// the turn, every weight stage of the group - and the turn passes to the other issuer just before the group's last job
+// is issued, so that the other issuer's wake-up and probes run in the shadow of those MMAs.  Global group order:
+// slot 0 group 0, slot 1 group 0, slot 0 group 1, ...
+template <int SLOT>
+__device__ __noinline__ void t2_issue_groups(int* err, int njobs, uint32_t base, uint32_t abort_addr, uint32_t tmem, int my_pairs,
+                                             unsigned long long* trace, int trace_it) {
+  using L = T2Smem;
+  const uint64_t adesc_enc = smem_desc_sw128(base + L::enc + SLOT * kBlkBytes);
+  const uint64_t adesc_dir = smem_desc_sw128(base + L::dir + SLOT * kBlkBytes);
+  const uint64_t ring_desc0 = smem_desc_sw128(base + L::ring);
+  const uint32_t idesc = make_idesc(1, 128, 128);
+  const uint32_t d = tmem + 256u * SLOT + 128u, a_base = tmem + 256u * SLOT;
+  const uint32_t b_acc_full = base + L::acc_full + 8 * SLOT, b_acc_empty = base + L::acc_empty + 8 * SLOT;
+  const uint32_t b_a_ready = base + L::a_ready + 8 * SLOT;
+  const uint32_t b_enc_full = base + L::enc_full + 8 * SLOT, b_enc_empty = base + L::enc_empty + 8 * SLOT;
+  const uint32_t b_dir_full = base + L::dir_full + 8 * SLOT, b_dir_empty = base + L::dir_empty + 8 * SLOT;
+  const uint32_t turn_addr = base + L::lead + 4;
+  uint32_t s = 0, par = 0, ph_a = 0, ph_e = 0, g = (uint32_t)SLOT;
+  for (int it = 0; it < my_pairs; ++it) {
+    int j = 0;
+    while (j < njobs) {
+      const T2Job r0 = c_t2jobs[j];
+      const uint32_t fl = r0.gflags;
+      const int glen = r0.glen;
+      unsigned long long* tr = (kDiag && trace && blockIdx.x == 0 && it == trace_it && (threadIdx.x & 31) == 0) ? trace + (SLOT * 48 + j) * 4 : nullptr;
+      if (tr) tr[0] = clock64();
+      // The group's weight stages first: they landed long ago (the ring runs a group ahead), and probing them here takes
+      // their round trips off the path between the operands' hand-over and the first MMA.
+      {
+        uint32_t ss = s, pp = par;
+        for (int k = 0; k < glen; ++k) {
+          ts_wait(base + L::w_full + 8 * ss, pp, abort_addr, err, 0x76000000 | (SLOT << 16) | (j + k));
+          if (++ss == (uint32_t)L::NST) { ss = 0; pp ^= 1u; }
+        }
+      }
+      if (fl & T2_WAIT_ENC) ts_wait(b_enc_full, (uint32_t)it & 1u, abort_addr, err, 0x72000000 | (SLOT << 16) | j);
+      if (fl & T2_WAIT_DIR) ts_wait(b_dir_full, (uint32_t)it & 1u, abort_addr, err, 0x73000000 | (SLOT << 16) | j);
+      if (fl & T2_WAIT_A) { ts_wait(b_a_ready, ph_a, abort_addr, err, 0x74000000 | (SLOT << 16) | j); ph_a ^= 1u; }
+      if ((fl & T2_WAIT_EMPTY) && !((fl & T2_TILE_FIRST) && it == 0)) {
+        ts_wait(b_acc_empty, ph_e, abort_addr, err, 0x75000000 | (SLOT << 16) | j);
+        ph_e ^= 1u;
+      }
+      if (tr) tr[1] = clock64();
+      ts_wait_progress(turn_addr, g, abort_addr, err, 0x77000000 | (SLOT << 16) | j);
+      if (tr) tr[2] = clock64();
+      tc_fence_after_sync();
+      if (elect_one()) {
+        uint32_t ss = s;
+        for (int k = 0; k < glen; ++k) {
+          const T2Job rc = c_t2jobs[j + k];
+          const uint32_t f = rc.flags;
+          if (k == glen - 1) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(turn_addr), "r"(g + 1u) : "memory");
+          const uint64_t bd0 = ring_desc0 + (uint64_t)(ss * (kTsStageBytes >> 4));
+          const uint64_t bd1 = bd0 + 1024u;
+          const uint32_t first = (f & T2_FIRST) ? 0u : 1u;
+          if (!(f & (T2_A_ENC | T2_A_DIR))) {
+            const uint32_t a_t = a_base + rc.a_col;
+            umma_bf16_ts(d, a_t, bd0, idesc, first);
+            umma_bf16_ts(d, a_t + 8, bd0 + 2, idesc, 1u);
+            umma_bf16_ts(d, a_t + 16, bd0 + 4, idesc, 1u);
+            umma_bf16_ts(d, a_t + 24, bd0 + 6, idesc, 1u);
+            umma_bf16_ts(d, a_t + 32, bd1, idesc, 1u);
+            umma_bf16_ts(d, a_t + 40, bd1 + 2, idesc, 1u);
+            umma_bf16_ts(d, a_t + 48, bd1 + 4, idesc, 1u);
+            umma_bf16_ts(d, a_t + 56, bd1 + 6, idesc, 1u);
+          } else {
+            const uint64_t adesc = (f & T2_A_DIR) ? adesc_dir : adesc_enc;
+            umma_bf16(d, adesc, bd0, idesc, first);
+            umma_bf16(d, adesc + 2, bd0 + 2, idesc, 1u);
+            if (rc.ksteps == 4) {
+              umma_bf16(d, adesc + 4, bd0 + 4, idesc, 1u);
+              umma_bf16(d, adesc + 6, bd0 + 6, idesc, 1u);
+            }
+          }
+          umma_commit(base + L::w_empty + 8 * ss);
+          if (f & T2_COMMIT_ACC) umma_commit(b_acc_full);
+          if (f & T2_COMMIT_ENC) umma_commit(b_enc_empty);
+          if (f & T2_COMMIT_DIR) umma_commit(b_dir_empty);
+          if (++ss == (uint32_t)L::NST) ss = 0;
+        }
+      }
+      __syncwarp();
+      if (tr) tr[3] = clock64();
+      for (int k = 0; k < glen; ++k)
+        if (++s == (uint32_t)L::NST) { s = 0; par ^= 1u; }
+      j += glen;
+      g += 2u;
+    }
+  }
+}
+
+// MODE 0: free-running issuers, one epilogue warpgroup per slot.  MODE 1: MMA groups issued in alternation (slot 0,
+// slot 1, ...), all eight epilogue warps serve whichever slot's accumulator comes next in that fixed order.
+template <int MODE>
 __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_t2_kernel(const T2Args a) {
   using L = T2Smem;
   extern __shared__ uint8_t smem_raw[];
@@ -197,14 +306,16 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_t2_kernel(const T2Args
     for (int i = 0; i < L::NST; ++i) { mbar_init(base + L::w_full + 8 * i, 1); mbar_init(base + L::w_empty + 8 * i, 2); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(base + L::acc_full + 8 * s, 1);
-      mbar_init(base + L::acc_empty + 8 * s, 128);
-      mbar_init(base + L::a_ready + 8 * s, 128);
+      mbar_init(base + L::acc_empty + 8 * s, MODE == 1 ? 256 : 128);
+      mbar_init(base + L::a_ready + 8 * s, MODE == 1 ? 256 : 128);
       mbar_init(base + L::enc_full + 8 * s, 128);
       mbar_init(base + L::enc_empty + 8 * s, 1);
       mbar_init(base + L::dir_full + 8 * s, 128);
       mbar_init(base + L::dir_empty + 8 * s, 1);
     }
     *reinterpret_cast<volatile uint32_t*>(gen + L::abort_flag) = 0;
+    *reinterpret_cast<volatile uint32_t*>(gen + L::lead) = 0;
+    *reinterpret_cast<volatile uint32_t*>(gen + L::lead + 4) = 0;
     mbar_init_fence();
   }
   if (warp == 2) tmem_alloc(base + L::tmem_ptr, kTmemCols);
@@ -254,9 +365,11 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_t2_kernel(const T2Args
         if (++s == (uint32_t)L::NST) { s = 0; par ^= 1u; }
       }
   } else if (warp == 1) {
-    t2_issue_loop<0>(a.err, a.njobs, base, abort_addr, tmem, my_pairs);
+    if constexpr (MODE == 1) t2_issue_groups<0>(a.err, a.njobs, base, abort_addr, tmem, my_pairs, a.trace, a.trace_it);
+    else t2_issue_loop<0>(a.err, a.njobs, base, abort_addr, tmem, my_pairs, a.trace, a.trace_it);
   } else if (warp == 3) {
-    t2_issue_loop<1>(a.err, a.njobs, base, abort_addr, tmem, my_pairs);
+    if constexpr (MODE == 1) t2_issue_groups<1>(a.err, a.njobs, base, abort_addr, tmem, my_pairs, a.trace, a.trace_it);
+    else t2_issue_loop<1>(a.err, a.njobs, base, abort_addr, tmem, my_pairs, a.trace, a.trace_it);
   } else if (warp >= 4 && warp < 8) {
     // =============================== per-tile input blocks of both slots: thread == row =============================
     const int row = threadIdx.x - 128;
@@ -350,6 +463,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_t2_kernel(const T2Args
       }
     }
   } else if (warp >= 8) {
+   if constexpr (MODE == 0) {
     // =============================== epilogue of one slot: thread == row, 128 channels per step ======================
     const int slot = (warp - 8) >> 2;
     const int row = ((warp & 3) << 5) | lane;
@@ -365,82 +479,259 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_t2_kernel(const T2Args
       const int64_t tile = 2 * ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) + slot;
       const int64_t p = tile * kTileRows + row;
       float sigma = 0.f;
-      uint32_t held[64];   // output half 0 of the current layer (bf16x2), waiting for half 1
-      for (int si = 0; si < a.nsteps; ++si) {
-        const T2Step st = c_t2steps[si];
-        ts_wait(b_acc_full, ph, abort_addr, a.err, 0x7a000000 | (slot << 16) | si);
-        ph ^= 1u;
-        tc_fence_after_sync();
+      const bool trace_on = kDiag && a.trace && blockIdx.x == 0 && it == a.trace_it && (threadIdx.x & 127) == 0;
+      // Steps come in pairs (one layer): HOLD converts output half 0 and keeps it in registers, FLUSH converts half 1 and
+      // stores both over A_s.  `held` lives inside the pair so that its 64 registers are free again for FLUSH's loads.
+      const int nlayers = (a.nsteps - 1) >> 1;
+      for (int li = 0; li < nlayers; ++li) {
+        const T2Step st = c_t2steps[2 * li];
         const float* bias = sbias + st.bias_off;
-        // One 32-column group in flight at a time: the 64 registers of the held half leave room for no more
-        // (512 threads x 128 registers is the whole register file).
+        unsigned long long* tr = trace_on ? a.trace + 512 + (slot * 24 + 2 * li) * 4 : nullptr;
+        uint32_t held[64];   // output half 0 of this layer (bf16x2), waiting for half 1
         uint32_t v[32];
-        if (st.mode == T2_HOLD) {
+        // ---- HOLD: one 32-column group in flight at a time (64 held + 32 in flight + conversion temporaries is what
+        // 128 registers per thread allow)
+        if (tr) tr[0] = clock64();
+        ts_wait(b_acc_full, ph, abort_addr, a.err, 0x7a000000 | (slot << 16) | (2 * li));
+        ph ^= 1u;
+        if (tr) tr[1] = clock64();
+        tc_fence_after_sync();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld32(acc + 32 * c, v);
+          tmem_ld_wait();
+          if (c == 3) {                      // ACC_s is in registers: the MMAs of half 1 may overwrite it
+            tc_fence_before_sync();
+            mbar_arrive(b_acc_empty);
+            if (tr) tr[2] = clock64();
+          }
+          if (st.relu) t2_convert<true>(v, bias + 32 * c, &held[16 * c]);
+          else t2_convert<false>(v, bias + 32 * c, &held[16 * c]);
+        }
+        if (st.dot) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) sigma = t2_dot32(&held[16 * c], walpha + 32 * c, sigma);
+        }
+        if (tr) tr[3] = clock64();
+        // ---- FLUSH: every MMA of this layer has completed (acc_full follows the last one): A_s is overwritten in place
+        if (tr) tr[4] = clock64();
+        ts_wait(b_acc_full, ph, abort_addr, a.err, 0x7a000000 | (slot << 16) | (2 * li + 1));
+        ph ^= 1u;
+        if (tr) tr[5] = clock64();
+        tc_fence_after_sync();
+        {
+          uint32_t w[16];
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) w[i] = held[16 * c + i];
+            tmem_st16(abuf + 16 * c, w);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t w[16];
+          tmem_ld32(acc + 32 * c, v);
+          tmem_ld_wait();
+          if (st.relu) t2_convert<true>(v, bias + 128 + 32 * c, w); else t2_convert<false>(v, bias + 128 + 32 * c, w);
+          tmem_st16(abuf + 64 + 16 * c, w);
+          if (st.dot) sigma = t2_dot32(w, walpha + 128 + 32 * c, sigma);
+        }
+        tmem_st_wait();
+        tc_fence_before_sync();
+        mbar_arrive(b_a_ready);              // next layer's input is in A_s (and ACC_s has been read out)
+        if (tr) { tr[6] = clock64(); tr[7] = tr[6]; }
+      }
+      {
+        // ---- OUT: views_linears.0 output (128 channels) -> ReLU -> rgb_linear on the CUDA cores -> (r, g, b, sigma)
+        const T2Step st = c_t2steps[a.nsteps - 1];
+        const float* bias = sbias + st.bias_off;
+        unsigned long long* tr = trace_on ? a.trace + 512 + (slot * 24 + a.nsteps - 1) * 4 : nullptr;
+        if (tr) tr[0] = clock64();
+        ts_wait(b_acc_full, ph, abort_addr, a.err, 0x7a000000 | (slot << 16) | (a.nsteps - 1));
+        ph ^= 1u;
+        if (tr) tr[1] = clock64();
+        tc_fence_after_sync();
+        float cr = 0.f, cg = 0.f, cb = 0.f;
+        uint32_t v[32], v2[32];
+        tmem_ld32(acc, v);
+        tmem_ld32(acc + 32, v2);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t w[16];
+          tmem_ld_wait();
+          if ((c & 1) == 0) {
+            t2_convert<true>(v, bias + 32 * c, w);
+            if (c == 0) tmem_ld32(acc + 64, v);
+          } else {
+            t2_convert<true>(v2, bias + 32 * c, w);
+            if (c == 1) tmem_ld32(acc + 96, v2);
+          }
+          if (c == 3) {                      // the next tile's layer 0 may start on ACC_s
+            tc_fence_before_sync();
+            mbar_arrive(b_acc_empty);
+            if (tr) tr[2] = clock64();
+          }
+          t2_rgb32(w, wrgb + 32 * c, cr, cg, cb);
+        }
+        if (p < a.P) {
+          float4 o;
+          o.x = cr + sbias[kBiasRgb + 0];
+          o.y = cg + sbias[kBiasRgb + 1];
+          o.z = cb + sbias[kBiasRgb + 2];
+          o.w = sigma + sbias[kBiasAlpha];
+          st_stream4(reinterpret_cast<float4*>(a.raw) + p, o);
+        }
+        if (tr) tr[3] = clock64();
+      }
+    }
+   } else {
+    // =============================== epilogue, both slots: thread == (row, 64-channel slice) =========================
+    // acc_full events arrive in the fixed order of the alternating issue: per layer  slot 0 half 0, slot 1 half 0,
+    // slot 0 half 1, slot 1 half 1.  All eight warps take each of them in turn: a step is two 32-column groups per
+    // thread instead of four, so a slot's hand-over comes back in about the time the other slot's MMA group runs.
+    const int wg = (warp - 8) >> 2;
+    const int row = ((warp & 3) << 5) | lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) << 5) << 16);
+    const float* sbias = reinterpret_cast<const float*>(gen + L::bias);
+    const float* walpha = reinterpret_cast<const float*>(gen + L::walpha);
+    const float4* wrgb = reinterpret_cast<const float4*>(gen + L::wrgb);
+    float4* red = reinterpret_cast<float4*>(gen + L::red);
+    uint32_t ph0 = 0, ph1 = 0;
+    for (int it = 0; it < my_pairs; ++it) {
+      const int64_t tile0 = 2 * ((int64_t)blockIdx.x + (int64_t)it * gridDim.x);
+      float sig0 = 0.f, sig1 = 0.f;
+      const bool trace_on = kDiag && a.trace && blockIdx.x == 0 && it == a.trace_it && (threadIdx.x & 255) == 0;
+      const int nlayers = (a.nsteps - 1) >> 1;
+      for (int li = 0; li < nlayers; ++li) {
+        const T2Step st = c_t2steps[2 * li];
+        const float* bias = sbias + st.bias_off + 64 * wg;
+        const float* wal = walpha + 64 * wg;
+        uint32_t heldA[32], heldB[32];   // this thread's 64 channels of output half 0, slot 0 / slot 1
+        unsigned long long* tr = trace_on ? a.trace + 512 + (2 * li) * 4 : nullptr;
+        // ---- half 0 of both slots: convert and keep
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          uint32_t* held = sl ? heldB : heldA;
+          const uint32_t acc = lane_addr + 256u * sl + 128u + 64u * wg;
+          unsigned long long* t4 = tr ? tr + sl * 24 * 4 : nullptr;
+          if (t4) t4[0] = clock64();
+          ts_wait(base + L::acc_full + 8 * sl, sl ? ph1 : ph0, abort_addr, a.err, 0x7a000000 | (sl << 16) | (2 * li));
+          if (sl) ph1 ^= 1u; else ph0 ^= 1u;
+          if (t4) t4[1] = clock64();
+          tc_fence_after_sync();
+          uint32_t v[32];
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
             tmem_ld32(acc + 32 * c, v);
             tmem_ld_wait();
-            if (c == 3) {                      // ACC_s is in registers: the MMAs of half 1 may overwrite it
+            if (c == 1) {                    // ACC is in registers: the MMAs of half 1 may overwrite it
               tc_fence_before_sync();
-              mbar_arrive(b_acc_empty);
+              mbar_arrive(base + L::acc_empty + 8 * sl);
+              if (t4) t4[2] = clock64();
             }
             if (st.relu) t2_convert<true>(v, bias + 32 * c, &held[16 * c]);
             else t2_convert<false>(v, bias + 32 * c, &held[16 * c]);
           }
           if (st.dot) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) sigma = t2_dot32(&held[16 * c], walpha + 32 * c, sigma);
+            float sg = sl ? sig1 : sig0;
+            sg = t2_dot32(&held[0], wal, sg);
+            sg = t2_dot32(&held[16], wal + 32, sg);
+            if (sl) sig1 = sg; else sig0 = sg;
           }
-        } else if (st.mode == T2_FLUSH) {
-          // every MMA of this layer has completed (acc_full follows the last one): A_s may be overwritten in place
+          if (t4) t4[3] = clock64();
+        }
+        // ---- half 1 of both slots: every MMA of the layer has completed, A is overwritten in place
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          const uint32_t* held = sl ? heldB : heldA;
+          const uint32_t acc = lane_addr + 256u * sl + 128u + 64u * wg;
+          const uint32_t abuf = lane_addr + 256u * sl + 32u * wg;
+          unsigned long long* t4 = tr ? tr + sl * 24 * 4 + 4 : nullptr;
+          if (t4) t4[0] = clock64();
+          ts_wait(base + L::acc_full + 8 * sl, sl ? ph1 : ph0, abort_addr, a.err, 0x7a000000 | (sl << 16) | (2 * li + 1));
+          if (sl) ph1 ^= 1u; else ph0 ^= 1u;
+          if (t4) t4[1] = clock64();
+          tc_fence_after_sync();
+          uint32_t v[32];
           tmem_ld32(acc, v);
           {
             uint32_t w[16];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) w[i] = held[16 * c + i];
               tmem_st16(abuf + 16 * c, w);
             }
           }
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 2; ++c) {
             uint32_t w[16];
             if (c > 0) tmem_ld32(acc + 32 * c, v);
             tmem_ld_wait();
             if (st.relu) t2_convert<true>(v, bias + 128 + 32 * c, w); else t2_convert<false>(v, bias + 128 + 32 * c, w);
             tmem_st16(abuf + 64 + 16 * c, w);
-            if (st.dot) sigma = t2_dot32(w, walpha + 128 + 32 * c, sigma);
+            if (st.dot) {
+              if (sl) sig1 = t2_dot32(w, wal + 128 + 32 * c, sig1); else sig0 = t2_dot32(w, wal + 128 + 32 * c, sig0);
+            }
           }
           tmem_st_wait();
           tc_fence_before_sync();
-          mbar_arrive(b_a_ready);              // next layer's input is in A_s (and ACC_s has been read out)
-        } else {
-          // views_linears.0 output (128 channels) -> ReLU -> rgb_linear on the CUDA cores -> (r, g, b, sigma)
-          float cr = 0.f, cg = 0.f, cb = 0.f;
+          mbar_arrive(base + L::a_ready + 8 * sl);   // next layer's input is in A (and ACC has been read out)
+          if (t4) { t4[2] = clock64(); t4[3] = t4[2]; }
+        }
+      }
+      // ---- views_linears.0 output (this thread's 64 of 128 channels) -> ReLU -> partial rgb_linear; the two slices of
+      // a row meet in shared memory
+      {
+        const T2Step st = c_t2steps[a.nsteps - 1];
+        const float* bias = sbias + st.bias_off + 64 * wg;
+        float4 part[2];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t w[16];
-            tmem_ld32(acc + 32 * c, v);
-            tmem_ld_wait();
-            if (c == 3) {                      // the next tile's layer 0 may start on ACC_s
-              tc_fence_before_sync();
-              mbar_arrive(b_acc_empty);
+        for (int sl = 0; sl < 2; ++sl) {
+          const uint32_t acc = lane_addr + 256u * sl + 128u + 64u * wg;
+          unsigned long long* t4 = trace_on ? a.trace + 512 + (sl * 24 + a.nsteps - 1) * 4 : nullptr;
+          if (t4) t4[0] = clock64();
+          ts_wait(base + L::acc_full + 8 * sl, sl ? ph1 : ph0, abort_addr, a.err, 0x7a000000 | (sl << 16) | (a.nsteps - 1));
+          if (sl) ph1 ^= 1u; else ph0 ^= 1u;
+          if (t4) t4[1] = clock64();
+          tc_fence_after_sync();
+          uint32_t v[32], w[32];
+          tmem_ld32(acc, v);
+          tmem_ld_wait();
+          t2_convert<true>(v, bias, &w[0]);
+          tmem_ld32(acc + 32, v);
+          tmem_ld_wait();
+          tc_fence_before_sync();
+          mbar_arrive(base + L::acc_empty + 8 * sl);   // the next tile's layer 0 may start on ACC
+          if (t4) t4[2] = clock64();
+          t2_convert<true>(v, bias + 32, &w[16]);
+          float cr = 0.f, cg = 0.f, cb = 0.f, cr2 = 0.f, cg2 = 0.f, cb2 = 0.f;
+          t2_rgb32(&w[0], wrgb + 64 * wg, cr, cg, cb);
+          t2_rgb32(&w[16], wrgb + 64 * wg + 32, cr2, cg2, cb2);
+          part[sl] = make_float4(cr + cr2, cg + cg2, cb + cb2, sl ? sig1 : sig0);
+          if (t4) t4[3] = clock64();
+        }
+        if (wg == 1) { red[row] = part[0]; red[128 + row] = part[1]; }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (wg == 0) {
+#pragma unroll
+          for (int sl = 0; sl < 2; ++sl) {
+            const int64_t p = (tile0 + sl) * kTileRows + row;
+            if (p < a.P) {
+              const float4 q = red[sl * 128 + row];
+              float4 o;
+              o.x = part[sl].x + q.x + sbias[kBiasRgb + 0];
+              o.y = part[sl].y + q.y + sbias[kBiasRgb + 1];
+              o.z = part[sl].z + q.z + sbias[kBiasRgb + 2];
+              o.w = part[sl].w + q.w + sbias[kBiasAlpha];
+              st_stream4(reinterpret_cast<float4*>(a.raw) + p, o);
             }
-            t2_convert<true>(v, bias + 32 * c, w);
-            t2_rgb32(w, wrgb + 32 * c, cr, cg, cb);
-          }
-          if (p < a.P) {
-            float4 o;
-            o.x = cr + sbias[kBiasRgb + 0];
-            o.y = cg + sbias[kBiasRgb + 1];
-            o.z = cb + sbias[kBiasRgb + 2];
-            o.w = sigma + sbias[kBiasAlpha];
-            st_stream4(reinterpret_cast<float4*>(a.raw) + p, o);
           }
         }
       }
     }
+   }
   }
 
   tc_fence_before_sync();
@@ -505,6 +796,19 @@ static T2Tables t2_build(const TsPlan& p) {
     if (q.layer == LIN_RGB && q.rows == 16 && q.nkb == 2) t.off_rgb = q.w_off;
   }
   if (!t.off_alpha[0] || !t.off_alpha[1] || !t.off_rgb) t.ok = false;
+  for (size_t i = 0; i < t.jobs.size();) {   // groups: from a T2_FIRST job up to and including the job that commits the accumulator
+    size_t e = i;
+    uint16_t gf = 0;
+    for (;; ++e) {
+      if (e >= t.jobs.size()) { t.ok = false; break; }
+      gf |= t.jobs[e].flags;
+      if (t.jobs[e].flags & T2_COMMIT_ACC) break;
+    }
+    if (!t.ok || !(t.jobs[i].flags & T2_FIRST)) { t.ok = false; break; }
+    t.jobs[i].glen = (uint8_t)(e - i + 1);
+    t.jobs[i].gflags = gf;
+    i = e + 1;
+  }
   if ((int)t.jobs.size() > kT2MaxJobs || (int)t.steps.size() > kT2MaxSteps) t.ok = false;
   return t;
 }
@@ -522,21 +826,26 @@ static int t2_upload() {   // called from ts_ensure_device (per device)
   GBN_REQUIRE(g_t2.ok, "T2 job table does not match the forward plan");
   GBN_CUDA(cudaMemcpyToSymbol(c_t2jobs, g_t2.jobs.data(), g_t2.jobs.size() * sizeof(T2Job), 0, cudaMemcpyHostToDevice));
   GBN_CUDA(cudaMemcpyToSymbol(c_t2steps, g_t2.steps.data(), g_t2.steps.size() * sizeof(T2Step), 0, cudaMemcpyHostToDevice));
-  GBN_CUDA(cudaFuncSetAttribute(nerf_mlp_t2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2Smem::alloc));
+  GBN_CUDA(cudaFuncSetAttribute(nerf_mlp_t2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2Smem::alloc));
+  GBN_CUDA(cudaFuncSetAttribute(nerf_mlp_t2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2Smem::alloc));
   return GBN_OK;
 }
 
 static int t2_forward(const void* packed, const float* ro, const float* rd, const float* vd, int64_t stride, const float* z,
-                      const float* pts, const float* emb, int64_t R, int S, float* raw, int* err, cudaStream_t stream) {
+                      const float* pts, const float* emb, int64_t R, int S, float* raw, int* err, cudaStream_t stream,
+                      unsigned long long* trace, int trace_it) {
   T2Args a{};
   a.packed = reinterpret_cast<const uint8_t*>(packed);
   a.ro = ro; a.rd = rd; a.z = z; a.pts = pts; a.emb = emb; a.vd = vd; a.raw = raw; a.err = err;
   a.stride = stride; a.P = R * S; a.S = S;
   a.njobs = (int)g_t2.jobs.size(); a.nsteps = (int)g_t2.steps.size();
+  a.trace = trace; a.trace_it = trace_it;
+  { const char* e = getenv("GBNERF_T2_MODE"); a.mode = e ? atoi(e) : 0; }
   a.off_alpha[0] = g_t2.off_alpha[0]; a.off_alpha[1] = g_t2.off_alpha[1]; a.off_rgb = g_t2.off_rgb;
   const int64_t ntiles = (a.P + kTileRows - 1) / kTileRows;
   const int64_t npairs = (ntiles + 1) / 2;
   const int grid = (int)(npairs < kNumSMs ? npairs : kNumSMs);
-  nerf_mlp_t2_kernel<<<grid, kTsThreads, T2Smem::alloc, stream>>>(a);
+  if (a.mode == 1) nerf_mlp_t2_kernel<1><<<grid, kTsThreads, T2Smem::alloc, stream>>>(a);
+  else nerf_mlp_t2_kernel<0><<<grid, kTsThreads, T2Smem::alloc, stream>>>(a);
   return check_launch("nerf_mlp_t2_kernel");
 }

@@ -1149,9 +1149,12 @@ int ts_forward(const void* packed, const float* ro, const float* rd, const float
   {
     unsigned long long* trace = nullptr; int trace_tile = 0;
     mlp_get_trace(&trace, &trace_tile);
-    // inference (no stash, no in-kernel trace requested): two tiles in flight per CTA
-    if (stash == nullptr && trace == nullptr && t2_enabled())
-      return t2_forward(packed, ro, rd, vd, stride, z, pts, emb, R, S, raw, err, stream);
+    // inference (no stash): two tiles in flight per CTA.  gbn_mlp_set_trace(buf, tile): tile = 0x40000000 | i traces pair
+    // iteration i of this kernel; any other tile (a tile index, or -1 for "no trace") keeps the launch on the one-tile
+    // kernel, which is how tools/t2_check.py runs both in one process
+    const bool t2_trace = trace != nullptr && trace_tile >= 0 && (trace_tile & 0x40000000);
+    if (stash == nullptr && (trace == nullptr || t2_trace) && t2_enabled())
+      return t2_forward(packed, ro, rd, vd, stride, z, pts, emb, R, S, raw, err, stream, trace, trace_tile & 0xffff);
   }
   TsArgs a{};
   a.packed = pk; a.ro = ro; a.rd = rd; a.z = z; a.pts = pts; a.emb = emb; a.vd = vd; a.raw = raw;

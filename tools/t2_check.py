@@ -35,7 +35,7 @@ trace = torch.zeros(4096, dtype=torch.int64, device=dev)
 
 
 def run(one_tile):
-    _lib.call("gbn_mlp_set_trace", C.c_void_p(trace.data_ptr()) if one_tile else None, 1 << 30)
+    _lib.call("gbn_mlp_set_trace", C.c_void_p(trace.data_ptr()) if one_tile else None, -1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     raw = ws = None
     for i in range(iters):
