@@ -653,8 +653,12 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_t2_kernel(const T2Args
           if (sl) ph1 ^= 1u; else ph0 ^= 1u;
           if (t4) t4[1] = clock64();
           tc_fence_after_sync();
-          uint32_t v[32];
+          // Loads are issued BEFORE the stores of the held half (measured: a tcgen05.st ahead of the tcgen05.ld delays it
+          // by more than the store takes).  Slot 1 is the last user of a held half in the layer, so both of its column
+          // groups fit in flight; slot 0 shares the registers with slot 1's held half and takes one group at a time.
+          uint32_t v[32], v2[32];
           tmem_ld32(acc, v);
+          if (sl == 1) tmem_ld32(acc + 32, v2);
           {
             uint32_t w[16];
 #pragma unroll
@@ -667,9 +671,10 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_t2_kernel(const T2Args
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             uint32_t w[16];
-            if (c > 0) tmem_ld32(acc + 32 * c, v);
-            tmem_ld_wait();
-            if (st.relu) t2_convert<true>(v, bias + 128 + 32 * c, w); else t2_convert<false>(v, bias + 128 + 32 * c, w);
+            if (c > 0 && sl == 0) tmem_ld32(acc + 32, v2);
+            if (c == 0 || sl == 0) tmem_ld_wait();
+            if (c == 0) { if (st.relu) t2_convert<true>(v, bias + 128, w); else t2_convert<false>(v, bias + 128, w); }
+            else { if (st.relu) t2_convert<true>(v2, bias + 160, w); else t2_convert<false>(v2, bias + 160, w); }
             tmem_st16(abuf + 64 + 16 * c, w);
             if (st.dot) {
               if (sl) sig1 = t2_dot32(w, wal + 128 + 32 * c, sig1); else sig0 = t2_dot32(w, wal + 128 + 32 * c, sig0);
@@ -840,7 +845,7 @@ static int t2_forward(const void* packed, const float* ro, const float* rd, cons
   a.stride = stride; a.P = R * S; a.S = S;
   a.njobs = (int)g_t2.jobs.size(); a.nsteps = (int)g_t2.steps.size();
   a.trace = trace; a.trace_it = trace_it;
-  { const char* e = getenv("GBNERF_T2_MODE"); a.mode = e ? atoi(e) : 0; }
+  { static const int m = [] { const char* e = getenv("GBNERF_T2_MODE"); return e ? atoi(e) : 1; }(); a.mode = m; }
   a.off_alpha[0] = g_t2.off_alpha[0]; a.off_alpha[1] = g_t2.off_alpha[1]; a.off_rgb = g_t2.off_rgb;
   const int64_t ntiles = (a.P + kTileRows - 1) / kTileRows;
   const int64_t npairs = (ntiles + 1) / 2;
