@@ -273,12 +273,17 @@ def run_ours(args, rank, world, local_rank):
         peak, peak_source = tf32_peaks["tf32_tflops_sustained"], "measured in this run: cuBLAS tf32 sustained"
     variant = os.environ.get("GBNERF_MLP", "ts") if args.precision == "bf16" else "ss"   # csrc/mlp_aux.cu mlp_variant()
     mlp_kernel_name = {"ts": "nerf_mlp_ts_kernel"}.get(variant, "nerf_mlp_kernel")
-    traffic = profile_traffic_bytes()
-    roofline = {"kernel": f"{mlp_kernel_name}<{args.precision}> (fused point generation + posenc + 8x256 MLP)",
+    t2 = variant == "ts" and os.environ.get("GBNERF_MLP_T2", "1") != "0"      # csrc/mlp_t2.cuh t2_enabled(): inference launches
+    if t2:
+        mlp_kernel_name = "nerf_mlp_t2_kernel"
+    traffic_file = "r2_mlp_t2_ncu_full.md" if t2 else "r2_mlp_ts_ncu_full.md"
+    traffic = profile_traffic_bytes(traffic_file)
+    roofline = {"kernel": f"{mlp_kernel_name}<{args.precision}> (fused point generation + posenc + 8x256 MLP"
+                          + (", two 128-point tiles in flight per CTA)" if t2 else ")"),
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak if achieved else None, "peak_source": peak_source, "tf32_peaks": tf32_peaks,
                 "traffic": traffic,
-                "traffic_source": "profiles/r2_mlp_ts_ncu_full.md (dram read+write of the 32768x128 fine-pass launch, ncu --set full; the 84 MB of algorithmic output + input mostly stay in L2 for the next kernel)"
+                "traffic_source": f"profiles/{traffic_file} (dram read+write of the 32768x128 fine-pass launch, ncu --set full; the 84 MB of algorithmic output + input mostly stay in L2 for the next kernel)"
                 if traffic else None, "launches_timed": len(mlp_ms), "avg_launch_ms": sum(mlp_ms) / max(1, len(mlp_ms)),
                 "share_of_step": sum(mlp_ms) / ms if mlp_ms else None,
                 "flop_per_launch": mlp_pts * FLOP_PER_POINT / max(1, len(mlp_ms))}
@@ -470,9 +475,9 @@ def stress_bench(G, ops, dev, kw_test, rank, world, timed, pk):
     return out
 
 
-def profile_traffic_bytes():
+def profile_traffic_bytes(name="r2_mlp_ts_ncu_full.md"):
     """dram__bytes_read.sum + dram__bytes_write.sum of the MLP kernel from the committed ncu --set full summary."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r2_mlp_ts_ncu_full.md")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", name)
     try:
         tot = 0.0
         for line in open(path):

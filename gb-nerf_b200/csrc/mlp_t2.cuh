@@ -826,6 +826,12 @@ static bool t2_enabled() {
   return on;
 }
 
+// GBNERF_T2_MODE: 1 (default) = alternating MMA groups + shared epilogue warps, 0 = free-running issuers
+static int t2_mode() {
+  static const int m = [] { const char* e = getenv("GBNERF_T2_MODE"); return (e && e[0] == '0') ? 0 : 1; }();
+  return m;
+}
+
 static int t2_upload() {   // called from ts_ensure_device (per device)
   if (g_t2.jobs.empty()) g_t2 = t2_build(ts_plan(0));
   GBN_REQUIRE(g_t2.ok, "T2 job table does not match the forward plan");
@@ -845,7 +851,7 @@ static int t2_forward(const void* packed, const float* ro, const float* rd, cons
   a.stride = stride; a.P = R * S; a.S = S;
   a.njobs = (int)g_t2.jobs.size(); a.nsteps = (int)g_t2.steps.size();
   a.trace = trace; a.trace_it = trace_it;
-  { static const int m = [] { const char* e = getenv("GBNERF_T2_MODE"); return e ? atoi(e) : 1; }(); a.mode = m; }
+  a.mode = t2_mode();
   a.off_alpha[0] = g_t2.off_alpha[0]; a.off_alpha[1] = g_t2.off_alpha[1]; a.off_rgb = g_t2.off_rgb;
   const int64_t ntiles = (a.P + kTileRows - 1) / kTileRows;
   const int64_t npairs = (ntiles + 1) / 2;

@@ -1206,6 +1206,18 @@ int ts_backward_data(const void* packed_bwd, const float* g_raw, int64_t P, cons
 
 // host only: the job / step tables the kernels run (for the protocol model of tests/test_ts_protocol_cpu.py)
 int ts_debug_plan(int bwd, void* jobs, int max_jobs, void* steps, int max_steps, int* meta) {
+  if (bwd == 2) {   // the two-tiles-in-flight inference kernel (mlp_t2.cuh): 16-byte T2Job / 8-byte T2Step records
+    if (g_t2.jobs.empty()) g_t2 = t2_build(ts_plan(0));
+    const int nj = (int)g_t2.jobs.size(), ns = (int)g_t2.steps.size();
+    if (!g_t2.ok || nj > max_jobs || ns > max_steps) return -1;
+    memcpy(jobs, g_t2.jobs.data(), nj * sizeof(T2Job));
+    memcpy(steps, g_t2.steps.data(), ns * sizeof(T2Step));
+    for (int i = 0; i < 10; ++i) meta[i] = 0;
+    meta[0] = nj; meta[1] = ns; meta[2] = T2Smem::NST; meta[3] = t2_mode();
+    meta[4] = (int)g_t2.off_alpha[0]; meta[5] = (int)g_t2.off_alpha[1]; meta[6] = (int)g_t2.off_rgb;
+    meta[7] = t2_enabled() ? 1 : 0;
+    return 0;
+  }
   const TsPlan& p = ts_plan(bwd);
   const int nj = (int)p.jobs.size(), ns = (int)p.steps.size();
   if (nj > max_jobs || ns > max_steps) return -1;
