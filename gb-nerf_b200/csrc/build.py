@@ -4,6 +4,8 @@
 
 --diag builds gb-nerf_b200/libgbnerf_diag.so instead: the same library with the diagnostic switches of the MLP
 kernels compiled in (-DGBN_TS_DIAG: GBNERF_TS_CHAOS, GBNERF_TS_GATE_DIRECT); select it with GBNERF_LIB=<path>.
+--exp builds gb-nerf_b200/libgbnerf_exp.so: the timing experiments of the two-tile MLP kernel (-DGBN_T2_EXP, see
+csrc/mlp_t2.cuh); results of its ablations are wrong by design - never load it outside tools/.
 
 The shared library lands next to the package (gb-nerf_b200/libgbnerf.so); it is git-ignored but travels to
 the GPU box with the gpurun snapshot.
@@ -32,18 +34,18 @@ def _digest():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False, diag=False):
+def build(force=False, verbose=False, diag=False, exp=False):
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(HERE, s))]
     dig = _digest()
-    target = OUT.replace("libgbnerf.so", "libgbnerf_diag.so") if diag else OUT
-    stamp = STAMP + (".diag" if diag else "")
+    target = OUT.replace("libgbnerf.so", "libgbnerf_diag.so") if diag else OUT.replace("libgbnerf.so", "libgbnerf_exp.so") if exp else OUT
+    stamp = STAMP + (".diag" if diag else ".exp" if exp else "")
     if not force and os.path.exists(target) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
         return target
     objs = []
     procs = []
     for s in srcs:
-        o = os.path.join(HERE, s.replace(".cu", ".diag.o" if diag else ".o"))
-        cmd = [NVCC, *FLAGS, *(["-DGBN_TS_DIAG"] if diag else []), "-c", os.path.join(HERE, s), "-o", o]
+        o = os.path.join(HERE, s.replace(".cu", ".diag.o" if diag else ".exp.o" if exp else ".o"))
+        cmd = [NVCC, *FLAGS, *(["-DGBN_TS_DIAG"] if diag else ["-DGBN_T2_EXP"] if exp else []), "-c", os.path.join(HERE, s), "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -65,4 +67,4 @@ def build(force=False, verbose=False, diag=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, diag="--diag" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, diag="--diag" in sys.argv, exp="--exp" in sys.argv))

@@ -22,6 +22,16 @@
 // removes their accumulator columns and two hand-overs per tile.
 
 constexpr int kT2MaxJobs = 48, kT2MaxSteps = 24;
+// -DGBN_T2_EXP (csrc/build.py --exp -> libgbnerf_exp.so, selected with GBNERF_LIB): timing experiments of DESIGN 3.1.1 -
+// GBNERF_T2_TURN_BACK (where inside a group the turn passes), GBNERF_T2_ABL (ablations that break the results: 1 = no rgb
+// head, 2 = no sin/cos in the input warps, 8 = OUT does nothing after reading the accumulator, 16 = FLUSH hands over
+// before it converts half 1), GBNERF_T2_DBG_EXTRA (repeat a wide layer n times).  The product build
+// carries none of it.
+#ifdef GBN_T2_EXP
+constexpr bool kT2Exp = true;
+#else
+constexpr bool kT2Exp = false;
+#endif
 enum : uint16_t {
   T2_WAIT_ENC = 1, T2_WAIT_DIR = 2, T2_WAIT_A = 4, T2_WAIT_EMPTY = 8, T2_FIRST = 16, T2_A_ENC = 32, T2_A_DIR = 64,
   T2_COMMIT_ACC = 128, T2_COMMIT_ENC = 256, T2_COMMIT_DIR = 512, T2_TILE_FIRST = 1024
@@ -40,9 +50,9 @@ struct T2Job {
 static_assert(sizeof(T2Job) == 16, "T2Job layout");
 enum : uint8_t { T2_HOLD = 0, T2_FLUSH = 1, T2_OUT = 2 };
 struct T2Step {
-  uint8_t mode, relu, dot, pad;   // dot: this layer's output feeds alpha_linear (sigma accumulates in the epilogue)
-  uint16_t bias_off, pad2;
-};
+  uint8_t mode, relu, dot, job0;  // dot: this layer's output feeds alpha_linear (sigma accumulates in the epilogue);
+  uint16_t bias_off, out_blk;     // job0: first job of the step's MMA group (= jobs of the tile before this group);
+};                                // out_blk: first H-stash block of the step's output (training forward, mlp_layout.h)
 static_assert(sizeof(T2Step) == 8, "T2Step layout");
 __constant__ T2Job c_t2jobs[kT2MaxJobs];
 __constant__ T2Step c_t2steps[kT2MaxSteps];
@@ -55,8 +65,8 @@ struct T2Smem {
   static constexpr uint32_t bias = ring + NST * kTsStageBytes;
   static constexpr uint32_t walpha = bias + kTsBiasFloats * 4;         // 256 floats
   static constexpr uint32_t wrgb = walpha + 256 * 4;                   // 128 x float4 (r, g, b, 0)
-  static constexpr uint32_t red = wrgb + 128 * 16;                     // [slot][row] float4: (r, g, b, sigma) partial sums of wg 1
-  static constexpr uint32_t bars = red + 2 * 128 * 16;
+  static constexpr uint32_t red = wrgb + 128 * 16;                     // [tile parity][slot][row] float4: (r, g, b, sigma) partial sums of wg 1
+  static constexpr uint32_t bars = red + 4 * 128 * 16;                 // (modes 0 / 1 use the first half)
   static constexpr uint32_t w_full = bars;
   static constexpr uint32_t w_empty = w_full + 8 * NST;
   static constexpr uint32_t acc_full = w_empty + 8 * NST;              // [slot]
@@ -87,7 +97,19 @@ struct T2Args {
   int mode;                    // kernel variant (GBNERF_T2_MODE): see the MODE template parameter
   int trace_it;                // [(slot*48 + job)*4 ..] issuer: start, operands ready, weights landed, issued |
                                // [512 + (slot*24 + step)*4 ..] epilogue: wait start, accumulator ready, handed over, step done
+  int turn_back, abl;          // GBN_T2_EXP builds only
+  int stagger;                 // MODE 2: MMA groups by which slot 1 runs behind slot 0
+  uint8_t* stash;              // STASH kernels: the H stash of the training forward (kStashTileBytes per tile)
+  int64_t ntiles;
 };
+
+// the 8 x 16-byte chunks a thread holds of one stash block (64 channels of its point): w = 32 bf16x2 words, or a part
+template <int NCHUNK>
+__device__ __forceinline__ void t2_stash_chunks(uint8_t* blk_row, int chunk0, const uint32_t* w) {
+#pragma unroll
+  for (int c = 0; c < NCHUNK; ++c)
+    ts_st_global16(blk_row + (uint32_t)(chunk0 + c) * 1024u, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+}
 
 __device__ __forceinline__ float t2_bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float t2_bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
@@ -202,7 +224,7 @@ __device__ __noinline__ void t2_issue_loop(int* err, int njobs, uint32_t base, u
 // slot 0 group 0, slot 1 group 0, slot 0 group 1, ...
 template <int SLOT>
 __device__ __noinline__ void t2_issue_groups(int* err, int njobs, uint32_t base, uint32_t abort_addr, uint32_t tmem, int my_pairs,
-                                             unsigned long long* trace, int trace_it) {
+                                             unsigned long long* trace, int trace_it, int turn_back) {
   using L = T2Smem;
   const uint64_t adesc_enc = smem_desc_sw128(base + L::enc + SLOT * kBlkBytes);
   const uint64_t adesc_dir = smem_desc_sw128(base + L::dir + SLOT * kBlkBytes);
@@ -245,10 +267,11 @@ __device__ __noinline__ void t2_issue_groups(int* err, int njobs, uint32_t base,
       tc_fence_after_sync();
       if (elect_one()) {
         uint32_t ss = s;
+        const int store_at = kT2Exp ? (2 * glen - turn_back > 0 ? 2 * glen - turn_back : 0) : 2 * (glen - 1);   // in half-jobs
         for (int k = 0; k < glen; ++k) {
           const T2Job rc = c_t2jobs[j + k];
           const uint32_t f = rc.flags;
-          if (k == glen - 1) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(turn_addr), "r"(g + 1u) : "memory");
+          if (2 * k == store_at) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(turn_addr), "r"(g + 1u) : "memory");
           const uint64_t bd0 = ring_desc0 + (uint64_t)(ss * (kTsStageBytes >> 4));
           const uint64_t bd1 = bd0 + 1024u;
           const uint32_t first = (f & T2_FIRST) ? 0u : 1u;
@@ -258,6 +281,7 @@ __device__ __noinline__ void t2_issue_groups(int* err, int njobs, uint32_t base,
             umma_bf16_ts(d, a_t + 8, bd0 + 2, idesc, 1u);
             umma_bf16_ts(d, a_t + 16, bd0 + 4, idesc, 1u);
             umma_bf16_ts(d, a_t + 24, bd0 + 6, idesc, 1u);
+            if (kT2Exp && 2 * k + 1 == store_at) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(turn_addr), "r"(g + 1u) : "memory");
             umma_bf16_ts(d, a_t + 32, bd1, idesc, 1u);
             umma_bf16_ts(d, a_t + 40, bd1 + 2, idesc, 1u);
             umma_bf16_ts(d, a_t + 48, bd1 + 4, idesc, 1u);
@@ -266,6 +290,7 @@ __device__ __noinline__ void t2_issue_groups(int* err, int njobs, uint32_t base,
             const uint64_t adesc = (f & T2_A_DIR) ? adesc_dir : adesc_enc;
             umma_bf16(d, adesc, bd0, idesc, first);
             umma_bf16(d, adesc + 2, bd0 + 2, idesc, 1u);
+            if (kT2Exp && 2 * k + 1 == store_at) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(turn_addr), "r"(g + 1u) : "memory");
             if (rc.ksteps == 4) {
               umma_bf16(d, adesc + 4, bd0 + 4, idesc, 1u);
               umma_bf16(d, adesc + 6, bd0 + 6, idesc, 1u);
@@ -288,10 +313,212 @@ __device__ __noinline__ void t2_issue_groups(int* err, int njobs, uint32_t base,
   }
 }
 
+// ---- MODE 2, "staggered": slot 1 runs D MMA groups (about half a network) behind slot 0 ------------------------------
+// With both slots in lock-step (MODE 1) they cross the tile boundary together: the view layer, OUT and layer 0 are short
+// MMA groups (18, 4 and 4 MMAs) that cannot hide an epilogue step, so the tensor pipe idles for ~16,000 of a pair's
+// ~59,000 cycles there (tools/t2_exp.py: 4,840 cycles per wide layer of both slots = 85 % busy, the rest is the boundary).
+// Staggered, one slot crosses the boundary while the other is in its wide layers.  The merged order of MMA groups -
+// issue turns, weight ring and epilogue service all follow it - is, for i = 0, 1, 2, ...:
+//     slot 0's group i (if it has one)      then      slot 1's group i - D (if i >= D)
+// Each slot fetches its own weights now (one consumer per ring stage, w_empty counts one commit): the ring position of a
+// group's first job is the number of jobs the producer emitted before it, which both sides compute from the same rule.
+// An issuer probes its weight stages AFTER it has the turn: every earlier group in the merged order has then finished
+// its own probes, so the previous fill of each stage has landed and the parity test cannot pass on a stale phase (the
+// two-consumer ring alias of DESIGN 3.1).
+struct T2Cnt { int q, r; };   // a group count n = q * G + r (q tiles, r groups)
+__device__ __forceinline__ void t2_cnt_inc(T2Cnt& c, int G) { if (++c.r == G) { c.r = 0; ++c.q; } }
+
+template <int SLOT>
+__device__ __noinline__ void t2_issue_stag(int* err, int njobs, int G, int D, uint32_t base, uint32_t abort_addr, uint32_t tmem,
+                                           int my_pairs, int abl) {
+  using L = T2Smem;
+  const uint64_t adesc_enc = smem_desc_sw128(base + L::enc + SLOT * kBlkBytes);
+  const uint64_t adesc_dir = smem_desc_sw128(base + L::dir + SLOT * kBlkBytes);
+  const uint64_t ring_desc0 = smem_desc_sw128(base + L::ring);
+  const uint32_t idesc = make_idesc(1, 128, 128);
+  const uint32_t d = tmem + 256u * SLOT + 128u, a_base = tmem + 256u * SLOT;
+  const uint32_t b_acc_full = base + L::acc_full + 8 * SLOT, b_acc_empty = base + L::acc_empty + 8 * SLOT;
+  const uint32_t b_a_ready = base + L::a_ready + 8 * SLOT;
+  const uint32_t b_enc_full = base + L::enc_full + 8 * SLOT, b_enc_empty = base + L::enc_empty + 8 * SLOT;
+  const uint32_t b_dir_full = base + L::dir_full + 8 * SLOT, b_dir_empty = base + L::dir_empty + 8 * SLOT;
+  const uint32_t turn_addr = base + L::lead + 4;
+  const int N0 = my_pairs * G;          // groups per slot
+  T2Cnt own{0, 0};
+  int m = SLOT == 0 ? 0 : (D + 1 < N0 ? D + 1 : N0);   // the other slot's groups that precede this one in the merged order
+  T2Cnt oth{m / G, m % G};
+  uint32_t ph_a = 0, ph_e = 0;
+  for (int n = 0; n < N0; ++n) {
+    const int tile = own.q;
+    const int j = c_t2steps[own.r].job0;
+    const T2Job r0 = c_t2jobs[j];
+    const uint32_t fl = r0.gflags;
+    const int glen = r0.glen;
+    const uint32_t pos = (uint32_t)(own.q + oth.q) * (uint32_t)njobs + (uint32_t)j + (uint32_t)c_t2steps[oth.r].job0;
+    const uint32_t t = SLOT == 0 ? 2u * (uint32_t)n : 2u * (uint32_t)(n + D) + 1u;
+    const uint32_t next = SLOT == 0 ? (n >= D ? t + 1u : t + 2u) : (n + D + 1 < N0 ? t + 1u : t + 2u);
+    if (fl & T2_WAIT_ENC) ts_wait(b_enc_full, (uint32_t)tile & 1u, abort_addr, err, 0x72000000 | (SLOT << 16) | j);
+    if (fl & T2_WAIT_DIR) ts_wait(b_dir_full, (uint32_t)tile & 1u, abort_addr, err, 0x73000000 | (SLOT << 16) | j);
+    if (fl & T2_WAIT_A) { ts_wait(b_a_ready, ph_a, abort_addr, err, 0x74000000 | (SLOT << 16) | j); ph_a ^= 1u; }
+    if ((fl & T2_WAIT_EMPTY) && !((fl & T2_TILE_FIRST) && tile == 0)) {
+      ts_wait(b_acc_empty, ph_e, abort_addr, err, 0x75000000 | (SLOT << 16) | j);
+      ph_e ^= 1u;
+    }
+    if (kT2Exp && (abl & 32)) {   // timing only: weight stages probed before the turn (not safe against the ring alias)
+      for (int k = 0; k < glen; ++k) {
+        const uint32_t pk = pos + (uint32_t)k;
+        ts_wait(base + L::w_full + 8 * (pk & (L::NST - 1)), (pk / L::NST) & 1u, abort_addr, err, 0x76000000 | (SLOT << 16) | (j + k));
+      }
+    }
+    ts_wait_progress(turn_addr, t, abort_addr, err, 0x77000000 | (SLOT << 16) | j);
+    if (!(kT2Exp && (abl & 32))) {
+    for (int k = 0; k < glen; ++k) {
+      const uint32_t pk = pos + (uint32_t)k;
+      ts_wait(base + L::w_full + 8 * (pk & (L::NST - 1)), (pk / L::NST) & 1u, abort_addr, err, 0x76000000 | (SLOT << 16) | (j + k));
+    }
+    }
+    tc_fence_after_sync();
+    if (elect_one()) {
+      for (int k = 0; k < glen; ++k) {
+        const T2Job rc = c_t2jobs[j + k];
+        const uint32_t f = rc.flags;
+        const uint32_t ss = (pos + (uint32_t)k) & (L::NST - 1);
+        if (k == glen - 1) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(turn_addr), "r"(next) : "memory");
+        const uint64_t bd0 = ring_desc0 + (uint64_t)(ss * (kTsStageBytes >> 4));
+        const uint64_t bd1 = bd0 + 1024u;
+        const uint32_t first = (f & T2_FIRST) ? 0u : 1u;
+        if (!(f & (T2_A_ENC | T2_A_DIR))) {
+          const uint32_t a_t = a_base + rc.a_col;
+          umma_bf16_ts(d, a_t, bd0, idesc, first);
+          umma_bf16_ts(d, a_t + 8, bd0 + 2, idesc, 1u);
+          umma_bf16_ts(d, a_t + 16, bd0 + 4, idesc, 1u);
+          umma_bf16_ts(d, a_t + 24, bd0 + 6, idesc, 1u);
+          umma_bf16_ts(d, a_t + 32, bd1, idesc, 1u);
+          umma_bf16_ts(d, a_t + 40, bd1 + 2, idesc, 1u);
+          umma_bf16_ts(d, a_t + 48, bd1 + 4, idesc, 1u);
+          umma_bf16_ts(d, a_t + 56, bd1 + 6, idesc, 1u);
+        } else {
+          const uint64_t adesc = (f & T2_A_DIR) ? adesc_dir : adesc_enc;
+          umma_bf16(d, adesc, bd0, idesc, first);
+          umma_bf16(d, adesc + 2, bd0 + 2, idesc, 1u);
+          if (rc.ksteps == 4) {
+            umma_bf16(d, adesc + 4, bd0 + 4, idesc, 1u);
+            umma_bf16(d, adesc + 6, bd0 + 6, idesc, 1u);
+          }
+        }
+        umma_commit(base + L::w_empty + 8 * ss);
+        if (f & T2_COMMIT_ACC) umma_commit(b_acc_full);
+        if (f & T2_COMMIT_ENC) umma_commit(b_enc_empty);
+        if (f & T2_COMMIT_DIR) umma_commit(b_dir_empty);
+      }
+    }
+    __syncwarp();
+    t2_cnt_inc(own, G);
+    if (SLOT == 0) { if (n >= D) t2_cnt_inc(oth, G); }
+    else if (m < N0) { ++m; t2_cnt_inc(oth, G); }
+  }
+}
+
+// One epilogue step of one slot in MODE 2 (all eight epilogue warps, thread == (row, 64-channel slice)).  `held` is the
+// slot's output half 0 between its HOLD and its FLUSH; the other slot's held half may be live at any step, so FLUSH keeps
+// one 32-column group in flight.
+struct T2Epi {
+  uint32_t base, abort_addr, lane_addr;
+  int wg, row;
+  const float* sbias; const float* walpha; const float4* wrgb; float4* red;
+};
+template <int SL>
+__device__ __forceinline__ void t2_epi_step(const T2Args& a, const T2Epi& e, int gi, int it, uint32_t (&held)[32], float& sig,
+                                            uint32_t& ph) {
+  using L = T2Smem;
+  const T2Step st = c_t2steps[gi];
+  const float* bias = e.sbias + st.bias_off + 64 * e.wg;
+  const float* wal = e.walpha + 64 * e.wg;
+  const uint32_t acc = e.lane_addr + 256u * SL + 128u + 64u * e.wg;
+  const uint32_t abuf = e.lane_addr + 256u * SL + 32u * e.wg;
+  ts_wait(e.base + L::acc_full + 8 * SL, ph, e.abort_addr, a.err, 0x7a000000 | (SL << 16) | gi);
+  ph ^= 1u;
+  tc_fence_after_sync();
+  if (st.mode == T2_HOLD) {
+    if (gi == 0) sig = 0.f;
+    uint32_t v[32];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      tmem_ld32(acc + 32 * c, v);
+      tmem_ld_wait();
+      if (c == 1) {                    // ACC is in registers: the MMAs of half 1 may overwrite it
+        tc_fence_before_sync();
+        mbar_arrive(e.base + L::acc_empty + 8 * SL);
+      }
+      if (st.relu) t2_convert<true>(v, bias + 32 * c, &held[16 * c]);
+      else t2_convert<false>(v, bias + 32 * c, &held[16 * c]);
+    }
+    if (st.dot) {
+      sig = t2_dot32(&held[0], wal, sig);
+      sig = t2_dot32(&held[16], wal + 32, sig);
+    }
+  } else if (st.mode == T2_FLUSH) {
+    uint32_t v[32];
+    tmem_ld32(acc, v);               // issued ahead of the stores of the held half (a tcgen05.st ahead of the ld delays it)
+    {
+      uint32_t w[16];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = held[16 * c + i];
+        tmem_st16(abuf + 16 * c, w);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t w[16];
+      if (c > 0) tmem_ld32(acc + 32, v);
+      tmem_ld_wait();
+      if (st.relu) t2_convert<true>(v, bias + 128 + 32 * c, w); else t2_convert<false>(v, bias + 128 + 32 * c, w);
+      tmem_st16(abuf + 64 + 16 * c, w);
+      if (st.dot) sig = t2_dot32(w, wal + 128 + 32 * c, sig);
+    }
+    tmem_st_wait();
+    tc_fence_before_sync();
+    mbar_arrive(e.base + L::a_ready + 8 * SL);   // next layer's input is in A (and ACC has been read out)
+  } else {
+    // OUT: views_linears.0 output (this thread's 64 of 128 channels) -> ReLU -> partial rgb_linear; the two slices of a
+    // row meet in shared memory (double-buffered by tile parity: the next write of a buffer is two barriers away)
+    uint32_t v[32], w[32];
+    tmem_ld32(acc, v);
+    tmem_ld_wait();
+    t2_convert<true>(v, bias, &w[0]);
+    tmem_ld32(acc + 32, v);
+    tmem_ld_wait();
+    tc_fence_before_sync();
+    mbar_arrive(e.base + L::acc_empty + 8 * SL);   // the next tile's layer 0 may start on ACC
+    t2_convert<true>(v, bias + 32, &w[16]);
+    float cr = 0.f, cg = 0.f, cb = 0.f, cr2 = 0.f, cg2 = 0.f, cb2 = 0.f;
+    t2_rgb32(&w[0], e.wrgb + 64 * e.wg, cr, cg, cb);
+    t2_rgb32(&w[16], e.wrgb + 64 * e.wg + 32, cr2, cg2, cb2);
+    float4* redp = e.red + ((it & 1) * 2 + SL) * 128;
+    if (e.wg == 1) redp[e.row] = make_float4(cr + cr2, cg + cg2, cb + cb2, sig);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (e.wg == 0) {
+      const int64_t p = (2 * ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) + SL) * kTileRows + e.row;
+      if (p < a.P) {
+        const float4 q = redp[e.row];
+        float4 o;
+        o.x = cr + cr2 + q.x + e.sbias[kBiasRgb + 0];
+        o.y = cg + cg2 + q.y + e.sbias[kBiasRgb + 1];
+        o.z = cb + cb2 + q.z + e.sbias[kBiasRgb + 2];
+        o.w = sig + q.w + e.sbias[kBiasAlpha];
+        st_stream4(reinterpret_cast<float4*>(a.raw) + p, o);
+      }
+    }
+  }
+}
+
 // MODE 0: free-running issuers, one epilogue warpgroup per slot.  MODE 1: MMA groups issued in alternation (slot 0,
-// slot 1, ...), all eight epilogue warps serve whichever slot's accumulator comes next in that fixed order.
-template <int MODE>
+// slot 1, ...), all eight epilogue warps serve whichever slot's accumulator comes next in that fixed order.  MODE 2: as
+// MODE 1 with slot 1 staggered by a.stagger groups (above).
+template <int MODE, bool STASH = false>
 __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_t2_kernel(const T2Args a) {
+  static_assert(!STASH || MODE == 1, "the stash-writing form exists for MODE 1 only");
   using L = T2Smem;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -303,11 +530,11 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_t2_kernel(const T2Args
   const uint32_t abort_addr = base + L::abort_flag;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < L::NST; ++i) { mbar_init(base + L::w_full + 8 * i, 1); mbar_init(base + L::w_empty + 8 * i, 2); }
+    for (int i = 0; i < L::NST; ++i) { mbar_init(base + L::w_full + 8 * i, 1); mbar_init(base + L::w_empty + 8 * i, MODE == 2 ? 1 : 2); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(base + L::acc_full + 8 * s, 1);
-      mbar_init(base + L::acc_empty + 8 * s, MODE == 1 ? 256 : 128);
-      mbar_init(base + L::a_ready + 8 * s, MODE == 1 ? 256 : 128);
+      mbar_init(base + L::acc_empty + 8 * s, MODE != 0 ? 256 : 128);
+      mbar_init(base + L::a_ready + 8 * s, MODE != 0 ? 256 : 128);
       mbar_init(base + L::enc_full + 8 * s, 128);
       mbar_init(base + L::enc_empty + 8 * s, 1);
       mbar_init(base + L::dir_full + 8 * s, 128);
@@ -347,11 +574,38 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_t2_kernel(const T2Args
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + L::tmem_ptr);
-
+  long long exp_t0 = 0;
+  if (kT2Exp) exp_t0 = clock64();
 
   if (warp == 0) {
     // =============================== weight producer: one fill per slab, consumed by both issuers ===================
     uint32_t s = 0, par = 0;
+    if constexpr (MODE == 2) {
+      // merged order: slot 0's group i, then slot 1's group i - D
+      const int G = a.nsteps, D = a.stagger, N0 = my_pairs * G;
+      int r0 = 0, r1 = 0;
+      for (int i = 0; i < N0 + D; ++i) {
+#pragma unroll 1
+        for (int sl = 0; sl < 2; ++sl) {
+          if (sl == 0 ? (i >= N0) : (i < D)) continue;
+          const int j0 = c_t2steps[sl ? r1 : r0].job0;
+          const int glen = c_t2jobs[j0].glen;
+          for (int j = j0; j < j0 + glen; ++j) {
+            ts_wait(base + L::w_empty + 8 * s, par ^ 1u, abort_addr, a.err, 0x71000000 | (sl << 16) | j);
+            const uint32_t bytes = (uint32_t)c_t2jobs[j].bytes16 * 16;
+            const uint8_t* src = a.packed + c_t2jobs[j].w_off;
+            if (elect_one()) {
+              mbar_expect_tx(base + L::w_full + 8 * s, bytes);
+              tma_bulk_g2s(base + L::ring + s * kTsStageBytes, src, bytes, base + L::w_full + 8 * s);
+            }
+            __syncwarp();
+            if (++s == (uint32_t)L::NST) { s = 0; par ^= 1u; }
+          }
+        }
+        if (i < N0 && ++r0 == G) r0 = 0;
+        if (i >= D && ++r1 == G) r1 = 0;
+      }
+    } else
     for (int it = 0; it < my_pairs; ++it)
       for (int j = 0; j < a.njobs; ++j) {
         ts_wait(base + L::w_empty + 8 * s, par ^ 1u, abort_addr, a.err, 0x71000000 | j);
@@ -365,10 +619,12 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_t2_kernel(const T2Args
         if (++s == (uint32_t)L::NST) { s = 0; par ^= 1u; }
       }
   } else if (warp == 1) {
-    if constexpr (MODE == 1) t2_issue_groups<0>(a.err, a.njobs, base, abort_addr, tmem, my_pairs, a.trace, a.trace_it);
+    if constexpr (MODE == 2) t2_issue_stag<0>(a.err, a.njobs, a.nsteps, a.stagger, base, abort_addr, tmem, my_pairs, a.abl);
+    else if constexpr (MODE == 1) t2_issue_groups<0>(a.err, a.njobs, base, abort_addr, tmem, my_pairs, a.trace, a.trace_it, a.turn_back);
     else t2_issue_loop<0>(a.err, a.njobs, base, abort_addr, tmem, my_pairs, a.trace, a.trace_it);
   } else if (warp == 3) {
-    if constexpr (MODE == 1) t2_issue_groups<1>(a.err, a.njobs, base, abort_addr, tmem, my_pairs, a.trace, a.trace_it);
+    if constexpr (MODE == 2) t2_issue_stag<1>(a.err, a.njobs, a.nsteps, a.stagger, base, abort_addr, tmem, my_pairs, a.abl);
+    else if constexpr (MODE == 1) t2_issue_groups<1>(a.err, a.njobs, base, abort_addr, tmem, my_pairs, a.trace, a.trace_it, a.turn_back);
     else t2_issue_loop<1>(a.err, a.njobs, base, abort_addr, tmem, my_pairs, a.trace, a.trace_it);
   } else if (warp >= 4 && warp < 8) {
     // =============================== per-tile input blocks of both slots: thread == row =============================
@@ -401,7 +657,11 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_t2_kernel(const T2Args
 #pragma unroll
               for (int i = 0; i < 3; ++i) {
                 float sc[20];
-                posenc_axis<10>(x[i], sc);
+                if (kT2Exp && (a.abl & 2)) {
+#pragma unroll
+                  for (int k = 0; k < 20; ++k) sc[k] = x[i] * (float)(k + 1);
+                } else
+                  posenc_axis<10>(x[i], sc);
                 e[i] = x[i];
 #pragma unroll
                 for (int k = 0; k < 10; ++k) { e[3 + 6 * k + i] = sc[2 * k]; e[6 + 6 * k + i] = sc[2 * k + 1]; }
@@ -420,6 +680,11 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_t2_kernel(const T2Args
         for (int c = 0; c < 8; ++c) {
           const uint32_t off = ((uint32_t)(c ^ (row & 7)) << 4);
           st_smem16(base + L::enc + sl * kBlkBytes + row_off + off, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+        }
+        if constexpr (STASH) {
+          if (tile0 + sl < a.ntiles)
+            t2_stash_chunks<8>(a.stash + (size_t)(tile0 + sl) * kStashTileBytes + (size_t)kHEnc * kBlkBytes +
+                                   stash_chunk_off((uint32_t)row, 0u), 0, w);
         }
         fence_proxy_async_smem();
         mbar_arrive(base + L::enc_full + 8 * sl);
@@ -457,6 +722,11 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_t2_kernel(const T2Args
           }
           const uint32_t off = ((uint32_t)(c ^ (row & 7)) << 4);
           st_smem16(base + L::dir + sl * kBlkBytes + row_off + off, q[0], q[1], q[2], q[3]);
+          if constexpr (STASH) {
+            if (tile0 + sl < a.ntiles)
+              t2_stash_chunks<1>(a.stash + (size_t)(tile0 + sl) * kStashTileBytes + (size_t)kHDir * kBlkBytes +
+                                     stash_chunk_off((uint32_t)row, 0u), c, q);
+          }
         }
         fence_proxy_async_smem();
         mbar_arrive(base + L::dir_full + 8 * sl);
@@ -585,6 +855,25 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_t2_kernel(const T2Args
         if (tr) tr[3] = clock64();
       }
     }
+   } else if constexpr (MODE == 2) {
+    // =============================== epilogue, both slots in the merged (staggered) order ============================
+    T2Epi e;
+    e.base = base; e.abort_addr = abort_addr;
+    e.lane_addr = tmem + ((uint32_t)((warp & 3) << 5) << 16);
+    e.wg = (warp - 8) >> 2; e.row = ((warp & 3) << 5) | lane;
+    e.sbias = reinterpret_cast<const float*>(gen + L::bias);
+    e.walpha = reinterpret_cast<const float*>(gen + L::walpha);
+    e.wrgb = reinterpret_cast<const float4*>(gen + L::wrgb);
+    e.red = reinterpret_cast<float4*>(gen + L::red);
+    const int G = a.nsteps, D = a.stagger, N0 = my_pairs * G;
+    uint32_t heldA[32], heldB[32];
+    float sigA = 0.f, sigB = 0.f;
+    uint32_t phA = 0, phB = 0;
+    T2Cnt cA{0, 0}, cB{0, 0};
+    for (int i = 0; i < N0 + D; ++i) {
+      if (i < N0) { t2_epi_step<0>(a, e, cA.r, cA.q, heldA, sigA, phA); t2_cnt_inc(cA, G); }
+      if (i >= D) { t2_epi_step<1>(a, e, cB.r, cB.q, heldB, sigB, phB); t2_cnt_inc(cB, G); }
+    }
    } else {
     // =============================== epilogue, both slots: thread == (row, 64-channel slice) =========================
     // acc_full events arrive in the fixed order of the alternating issue: per layer  slot 0 half 0, slot 1 half 0,
@@ -597,6 +886,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_t2_kernel(const T2Args
     const float* walpha = reinterpret_cast<const float*>(gen + L::walpha);
     const float4* wrgb = reinterpret_cast<const float4*>(gen + L::wrgb);
     float4* red = reinterpret_cast<float4*>(gen + L::red);
+    const uint32_t srow = stash_chunk_off((uint32_t)row, 0u);   // this point's place inside a stash block
+    (void)srow;
     uint32_t ph0 = 0, ph1 = 0;
     for (int it = 0; it < my_pairs; ++it) {
       const int64_t tile0 = 2 * ((int64_t)blockIdx.x + (int64_t)it * gridDim.x);
@@ -632,6 +923,11 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_t2_kernel(const T2Args
             }
             if (st.relu) t2_convert<true>(v, bias + 32 * c, &held[16 * c]);
             else t2_convert<false>(v, bias + 32 * c, &held[16 * c]);
+            if constexpr (STASH) {
+              if (tile0 + sl < a.ntiles)
+                t2_stash_chunks<4>(a.stash + (size_t)(tile0 + sl) * kStashTileBytes + (size_t)(st.out_blk + wg) * kBlkBytes + srow,
+                                   4 * c, &held[16 * c]);
+            }
           }
           if (st.dot) {
             float sg = sl ? sig1 : sig0;
@@ -668,6 +964,12 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_t2_kernel(const T2Args
               tmem_st16(abuf + 16 * c, w);
             }
           }
+          if (kT2Exp && (a.abl & 16)) {   // hand over as soon as the held half is stored and the first loads are back
+            tmem_ld_wait();
+            tmem_st_wait();
+            tc_fence_before_sync();
+            mbar_arrive(base + L::a_ready + 8 * sl);
+          }
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             uint32_t w[16];
@@ -676,13 +978,19 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_t2_kernel(const T2Args
             if (c == 0) { if (st.relu) t2_convert<true>(v, bias + 128, w); else t2_convert<false>(v, bias + 128, w); }
             else { if (st.relu) t2_convert<true>(v2, bias + 160, w); else t2_convert<false>(v2, bias + 160, w); }
             tmem_st16(abuf + 64 + 16 * c, w);
+            if constexpr (STASH) {
+              if (tile0 + sl < a.ntiles)
+                t2_stash_chunks<4>(a.stash + (size_t)(tile0 + sl) * kStashTileBytes + (size_t)(st.out_blk + 2 + wg) * kBlkBytes + srow,
+                                   4 * c, w);
+            }
             if (st.dot) {
               if (sl) sig1 = t2_dot32(w, wal + 128 + 32 * c, sig1); else sig0 = t2_dot32(w, wal + 128 + 32 * c, sig0);
             }
           }
           tmem_st_wait();
           tc_fence_before_sync();
-          mbar_arrive(base + L::a_ready + 8 * sl);   // next layer's input is in A (and ACC has been read out)
+          if (!(kT2Exp && (a.abl & 16)))
+            mbar_arrive(base + L::a_ready + 8 * sl);   // next layer's input is in A (and ACC has been read out)
           if (t4) { t4[2] = clock64(); t4[3] = t4[2]; }
         }
       }
@@ -710,10 +1018,18 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_t2_kernel(const T2Args
           tc_fence_before_sync();
           mbar_arrive(base + L::acc_empty + 8 * sl);   // the next tile's layer 0 may start on ACC
           if (t4) t4[2] = clock64();
-          t2_convert<true>(v, bias + 32, &w[16]);
+          if (!(kT2Exp && (a.abl & 8))) t2_convert<true>(v, bias + 32, &w[16]);
+          if constexpr (STASH) {
+            if (tile0 + sl < a.ntiles)
+              t2_stash_chunks<8>(a.stash + (size_t)(tile0 + sl) * kStashTileBytes + (size_t)(st.out_blk + wg) * kBlkBytes + srow, 0, w);
+          }
           float cr = 0.f, cg = 0.f, cb = 0.f, cr2 = 0.f, cg2 = 0.f, cb2 = 0.f;
-          t2_rgb32(&w[0], wrgb + 64 * wg, cr, cg, cb);
-          t2_rgb32(&w[16], wrgb + 64 * wg + 32, cr2, cg2, cb2);
+          if (kT2Exp && (a.abl & 9)) {
+            cr = __uint_as_float(w[0]); cr2 = __uint_as_float(w[31]);
+          } else {
+            t2_rgb32(&w[0], wrgb + 64 * wg, cr, cg, cb);
+            t2_rgb32(&w[16], wrgb + 64 * wg + 32, cr2, cg2, cb2);
+          }
           part[sl] = make_float4(cr + cr2, cg + cg2, cb + cb2, sl ? sig1 : sig0);
           if (t4) t4[3] = clock64();
         }
@@ -742,6 +1058,10 @@ __global__ void __launch_bounds__(kTsThreads, 1) nerf_mlp_t2_kernel(const T2Args
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem, kTmemCols);
+  if (kT2Exp && blockIdx.x == 0 && threadIdx.x == 0) {   // SM cycles of CTA 0 and its pair count: byte 64 of the workspace
+    *reinterpret_cast<long long*>(a.err + 16) = clock64() - exp_t0;
+    a.err[18] = my_pairs;
+  }
 }
 
 // ---- host: job / step tables from the forward plan's slab list -------------------------------------------------------
@@ -768,15 +1088,16 @@ static T2Tables t2_build(const TsPlan& p) {
     if (q->rows != 128) t.ok = false;
     t.jobs.push_back(j);
   };
-  auto step = [&](int mode, int relu, int dot, int bias_off) {
+  auto step = [&](int mode, int relu, int dot, int bias_off, int out_blk) {
     T2Step s{};
     s.mode = (uint8_t)mode; s.relu = (uint8_t)relu; s.dot = (uint8_t)dot; s.bias_off = (uint16_t)bias_off;
+    s.out_blk = (uint16_t)out_blk;
     t.steps.push_back(s);
   };
   // layer 0: A = the slot's encoding block
   job(slab(0, 0, 0, 1), T2_WAIT_ENC | T2_TILE_FIRST | T2_WAIT_EMPTY | T2_FIRST | T2_A_ENC | T2_COMMIT_ACC, 0, 4);
   job(slab(0, 128, 0, 1), T2_WAIT_EMPTY | T2_FIRST | T2_A_ENC | T2_COMMIT_ACC, 0, 4);
-  step(T2_HOLD, 1, 0, 0); step(T2_FLUSH, 1, 0, 0);
+  step(T2_HOLD, 1, 0, 0, 0); step(T2_FLUSH, 1, 0, 0, 2);
   auto wide = [&](int layer, int c0, bool skip) {
     for (int h = 0; h < 2; ++h) {
       job(slab(layer, 128 * h, c0, 2), (h == 0 ? T2_WAIT_A : T2_WAIT_EMPTY) | T2_FIRST, 0, 4);
@@ -786,14 +1107,18 @@ static T2Tables t2_build(const TsPlan& p) {
   };
   for (int l = 1; l <= 7; ++l) {
     wide(l, l == 5 ? 63 : 0, l == 5);
-    step(T2_HOLD, 1, l == 7, 256 * l); step(T2_FLUSH, 1, l == 7, 256 * l);
+    step(T2_HOLD, 1, l == 7, 256 * l, 4 * l); step(T2_FLUSH, 1, l == 7, 256 * l, 4 * l + 2);
+    if (kT2Exp && l == 2) {   // timing only: layer 2 again, n times (steady-state period of a wide layer = d time / d n)
+      const char* e = getenv("GBNERF_T2_DBG_EXTRA");
+      for (int n = e ? atoi(e) : 0; n > 0; --n) { wide(2, 0, false); step(T2_HOLD, 1, 0, 512, 8); step(T2_FLUSH, 1, 0, 512, 10); }
+    }
   }
   wide(LIN_FEATURE, 0, false);
-  step(T2_HOLD, 0, 0, kBiasFeat); step(T2_FLUSH, 0, 0, kBiasFeat);
+  step(T2_HOLD, 0, 0, kBiasFeat, kHFeat); step(T2_FLUSH, 0, 0, kBiasFeat, kHFeat + 2);
   job(slab(LIN_VIEWS, 0, 0, 2), T2_WAIT_A | T2_FIRST, 0, 4);
   job(slab(LIN_VIEWS, 0, 128, 2), 0, 64, 4);
   job(slab(LIN_VIEWS, 0, 256, 1), T2_WAIT_DIR | T2_A_DIR | T2_COMMIT_ACC | T2_COMMIT_DIR, 0, 2);
-  step(T2_OUT, 1, 0, kTsBiasViews);
+  step(T2_OUT, 1, 0, kTsBiasViews, kHHv);
   // alpha / rgb slabs (16 rows): decoded to fp32 in the kernel prologue
   t.off_alpha[0] = t.off_alpha[1] = t.off_rgb = 0;
   for (const TsPackJob& q : p.pack) {
@@ -814,6 +1139,15 @@ static T2Tables t2_build(const TsPlan& p) {
     t.jobs[i].gflags = gf;
     i = e + 1;
   }
+  {   // job0 of every step's group (steps and groups are one to one, in order)
+    size_t g = 0;
+    for (size_t i = 0; i < t.jobs.size(); ++i)
+      if (t.jobs[i].glen) {
+        if (g < t.steps.size()) t.steps[g].job0 = (uint8_t)i;
+        ++g;
+      }
+    if (g != t.steps.size()) t.ok = false;
+  }
   if ((int)t.jobs.size() > kT2MaxJobs || (int)t.steps.size() > kT2MaxSteps) t.ok = false;
   return t;
 }
@@ -826,10 +1160,23 @@ static bool t2_enabled() {
   return on;
 }
 
-// GBNERF_T2_MODE: 1 (default) = alternating MMA groups + shared epilogue warps, 0 = free-running issuers
+// GBNERF_T2_STASH=0 keeps the stash-writing (training) forward on the one-tile kernel
+static bool t2_stash_enabled() {
+  static const bool on = [] { const char* e = getenv("GBNERF_T2_STASH"); return !(e && e[0] == '0'); }();
+  return on && t2_enabled();
+}
+
+// GBNERF_T2_MODE: 1 (default) = alternating MMA groups + shared epilogue warps, 0 = free-running issuers; in the exp
+// build (-DGBN_T2_EXP) also 2 = as 1 with slot 1 staggered by GBNERF_T2_STAGGER groups (default 10)
 static int t2_mode() {
-  static const int m = [] { const char* e = getenv("GBNERF_T2_MODE"); return (e && e[0] == '0') ? 0 : 1; }();
+  static const int m = [] { const char* e = getenv("GBNERF_T2_MODE"); return (e && e[0] == '0') ? 0 : (kT2Exp && e && e[0] == '2') ? 2 : 1; }();
   return m;
+}
+static int t2_stagger(int nsteps) {
+  static const int d0 = [] { const char* e = getenv("GBNERF_T2_STAGGER"); return e ? atoi(e) : 10; }();
+  int d = d0;
+  if (kT2Exp) { const char* e = getenv("GBNERF_T2_STAGGER"); if (e) d = atoi(e); }   // per launch: tools/t2_exp.py sweeps it
+  return d < 1 ? 1 : d >= nsteps ? nsteps - 1 : d;
 }
 
 static int t2_upload() {   // called from ts_ensure_device (per device)
@@ -839,12 +1186,15 @@ static int t2_upload() {   // called from ts_ensure_device (per device)
   GBN_CUDA(cudaMemcpyToSymbol(c_t2steps, g_t2.steps.data(), g_t2.steps.size() * sizeof(T2Step), 0, cudaMemcpyHostToDevice));
   GBN_CUDA(cudaFuncSetAttribute(nerf_mlp_t2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2Smem::alloc));
   GBN_CUDA(cudaFuncSetAttribute(nerf_mlp_t2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2Smem::alloc));
+  GBN_CUDA(cudaFuncSetAttribute(nerf_mlp_t2_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2Smem::alloc));
+  if constexpr (kT2Exp)
+    GBN_CUDA(cudaFuncSetAttribute(nerf_mlp_t2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2Smem::alloc));
   return GBN_OK;
 }
 
 static int t2_forward(const void* packed, const float* ro, const float* rd, const float* vd, int64_t stride, const float* z,
                       const float* pts, const float* emb, int64_t R, int S, float* raw, int* err, cudaStream_t stream,
-                      unsigned long long* trace, int trace_it) {
+                      unsigned long long* trace, int trace_it, void* stash = nullptr) {
   T2Args a{};
   a.packed = reinterpret_cast<const uint8_t*>(packed);
   a.ro = ro; a.rd = rd; a.z = z; a.pts = pts; a.emb = emb; a.vd = vd; a.raw = raw; a.err = err;
@@ -852,11 +1202,29 @@ static int t2_forward(const void* packed, const float* ro, const float* rd, cons
   a.njobs = (int)g_t2.jobs.size(); a.nsteps = (int)g_t2.steps.size();
   a.trace = trace; a.trace_it = trace_it;
   a.mode = t2_mode();
+  if (kT2Exp) {
+    const char* e = getenv("GBNERF_T2_TURN_BACK");   // read per launch: tools/t2_exp.py sweeps them in one process
+    a.turn_back = e ? atoi(e) : 2;
+    e = getenv("GBNERF_T2_ABL");
+    a.abl = e ? atoi(e) : 0;
+  }
   a.off_alpha[0] = g_t2.off_alpha[0]; a.off_alpha[1] = g_t2.off_alpha[1]; a.off_rgb = g_t2.off_rgb;
   const int64_t ntiles = (a.P + kTileRows - 1) / kTileRows;
   const int64_t npairs = (ntiles + 1) / 2;
   const int grid = (int)(npairs < kNumSMs ? npairs : kNumSMs);
-  if (a.mode == 1) nerf_mlp_t2_kernel<1><<<grid, kTsThreads, T2Smem::alloc, stream>>>(a);
+  a.stagger = t2_stagger(a.nsteps);
+  a.stash = static_cast<uint8_t*>(stash); a.ntiles = ntiles;
+  if (stash != nullptr) {   // training forward: MODE 1 with the H stash written from the epilogue's registers
+    nerf_mlp_t2_kernel<1, true><<<grid, kTsThreads, T2Smem::alloc, stream>>>(a);
+    return check_launch("nerf_mlp_t2_kernel<stash>");
+  }
+  if constexpr (kT2Exp) {   // the staggered mode is an experiment (measured slower): exp build only
+    if (a.mode == 2) {
+      nerf_mlp_t2_kernel<2><<<grid, kTsThreads, T2Smem::alloc, stream>>>(a);
+      return check_launch("nerf_mlp_t2_kernel");
+    }
+  }
+  if (a.mode != 0) nerf_mlp_t2_kernel<1><<<grid, kTsThreads, T2Smem::alloc, stream>>>(a);
   else nerf_mlp_t2_kernel<0><<<grid, kTsThreads, T2Smem::alloc, stream>>>(a);
   return check_launch("nerf_mlp_t2_kernel");
 }

@@ -1155,6 +1155,9 @@ int ts_forward(const void* packed, const float* ro, const float* rd, const float
     const bool t2_trace = trace != nullptr && trace_tile >= 0 && (trace_tile & 0x40000000);
     if (stash == nullptr && (trace == nullptr || t2_trace) && t2_enabled())
       return t2_forward(packed, ro, rd, vd, stride, z, pts, emb, R, S, raw, err, stream, trace, trace_tile & 0xffff);
+    // training forward (writes the H stash): the same kernel with the stash stores compiled in
+    if (stash != nullptr && trace == nullptr && t2_stash_enabled())
+      return t2_forward(packed, ro, rd, vd, stride, z, pts, emb, R, S, raw, err, stream, nullptr, 0, stash);
   }
   TsArgs a{};
   a.packed = pk; a.ro = ro; a.rd = rd; a.z = z; a.pts = pts; a.emb = emb; a.vd = vd; a.raw = raw;

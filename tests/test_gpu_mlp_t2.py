@@ -84,3 +84,35 @@ def test_points_and_embedded_forms(G, net):
                      O.posenc(vd.cpu()[:, None, :].expand(R, S, 3).reshape(-1, 3), 4)], dim=-1).cuda()
     f_emb = lambda: G.ops.mlp_forward_embedded_raw(packed, "bf16", emb)
     torch.testing.assert_close(_run(G, False, f_emb), _run(G, True, f_emb), rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("R,S", [(1, 64), (3, 64), (37, 64), (300, 128), (4096, 64)])
+def test_training_stash_is_byte_identical_to_the_one_tile_kernel(G, net, R, S):
+    """The stash-writing (training) forward on the two-tile kernel: the H stash that dgrad and wgrad consume must be the
+    SAME BYTES the one-tile kernel writes (same MMAs, same bias / ReLU / bf16 rounding, same block layout), for partial
+    tiles and odd tile counts too (the idle slot of the last pair must not write); raw differs by the heads' summation
+    order only."""
+    o, d, vd, z = _rays(R, S, 100 + R)
+    packed = net.packed_weights()
+    out = {}
+    for one_tile in (True, False):
+        stash = G.ops._stash(R * S, o.device)
+        stash.fill_(0x5a)
+        fn = lambda: G.ops.mlp_forward_raw(packed, "bf16", vd, R, S, rays_o=o, rays_d=d, z=z, stash=stash)
+        out[one_tile] = (_run(G, one_tile, fn), stash)
+    torch.testing.assert_close(out[False][0], out[True][0], rtol=0, atol=1e-6)
+    a, b = out[False][1], out[True][1]
+    if not torch.equal(a, b):
+        bad = (a != b).nonzero().reshape(-1)
+        blk = (bad // 16384) % 40
+        raise AssertionError(f"{bad.numel()} stash bytes differ; tiles {sorted(set((bad // (40 * 16384)).tolist()))[:8]}, "
+                             f"blocks {sorted(set(blk.tolist()))}")
+    # the embedded-rows form writes the same stash through the same kernel
+    pts = (o[:, None, :] + d[:, None, :] * z[..., None]).contiguous()
+    res = {}
+    for one_tile in (True, False):
+        stash = G.ops._stash(R * S, o.device)
+        stash.fill_(0x5a)
+        fn = lambda: G.ops.mlp_forward_raw(packed, "bf16", vd, R, S, pts=pts, stash=stash)
+        res[one_tile] = (_run(G, one_tile, fn), stash)
+    assert torch.equal(res[False][1], res[True][1])
