@@ -34,18 +34,24 @@ def _digest():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False, diag=False, exp=False):
+def build(force=False, verbose=False, diag=False, exp=False, variant=""):
+    """variant (with exp): "NAME:MACRO[,MACRO...]" builds libgbnerf_exp_NAME.so with those extra -D flags (A/B of a code
+    change on one box in one gpurun call, tools/t2_exp.sh)."""
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(HERE, s))]
     dig = _digest()
-    target = OUT.replace("libgbnerf.so", "libgbnerf_diag.so") if diag else OUT.replace("libgbnerf.so", "libgbnerf_exp.so") if exp else OUT
-    stamp = STAMP + (".diag" if diag else ".exp" if exp else "")
+    vname, _, vdefs = variant.partition(":")
+    extra = ["-D" + d for d in vdefs.split(",") if d]
+    suffix = "_exp" + ("_" + vname if vname else "")
+    target = OUT.replace("libgbnerf.so", "libgbnerf_diag.so") if diag else OUT.replace("libgbnerf.so", f"libgbnerf{suffix}.so") if exp else OUT
+    stamp = STAMP + (".diag" if diag else "." + suffix[1:] if exp else "")
+    dig += "|" + variant
     if not force and os.path.exists(target) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
         return target
     objs = []
     procs = []
     for s in srcs:
-        o = os.path.join(HERE, s.replace(".cu", ".diag.o" if diag else ".exp.o" if exp else ".o"))
-        cmd = [NVCC, *FLAGS, *(["-DGBN_TS_DIAG"] if diag else ["-DGBN_T2_EXP"] if exp else []), "-c", os.path.join(HERE, s), "-o", o]
+        o = os.path.join(HERE, s.replace(".cu", ".diag.o" if diag else f".{suffix[1:]}.o" if exp else ".o"))
+        cmd = [NVCC, *FLAGS, *(["-DGBN_TS_DIAG"] if diag else ["-DGBN_T2_EXP", *extra] if exp else []), "-c", os.path.join(HERE, s), "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -67,4 +73,6 @@ def build(force=False, verbose=False, diag=False, exp=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, diag="--diag" in sys.argv, exp="--exp" in sys.argv))
+    var = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")), "")
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, diag="--diag" in sys.argv, exp="--exp" in sys.argv or bool(var),
+                variant=var))

@@ -269,7 +269,7 @@ __device__ __noinline__ void t2_issue_groups(int* err, int njobs, uint32_t base,
         uint32_t ss = s;
         const int store_at = kT2Exp ? (2 * glen - turn_back > 0 ? 2 * glen - turn_back : 0) : 2 * (glen - 1);   // in half-jobs
         for (int k = 0; k < glen; ++k) {
-          const T2Job rc = c_t2jobs[j + k];
+          const T2Job rc = c_t2jobs[j + k];   // (fetching the group's records ahead of the waits: +3.7 % cycles)
           const uint32_t f = rc.flags;
           if (2 * k == store_at) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(turn_addr), "r"(g + 1u) : "memory");
           const uint64_t bd0 = ring_desc0 + (uint64_t)(ss * (kTsStageBytes >> 4));

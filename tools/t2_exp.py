@@ -60,7 +60,9 @@ def run(label, **env):
 print(f"R={R} S={S} extra layers={extra} lib={os.environ.get('GBNERF_LIB', 'product')}", flush=True)
 run("warm-up")
 base = run("shipped (turn_back 2)")
-if os.environ.get("GBNERF_T2_MODE") == "2":
+if os.environ.get("T2_EXP_QUICK"):
+    run("shipped again")
+elif os.environ.get("GBNERF_T2_MODE") == "2":
     for D in (10, 2):
         run(f"staggered, D = {D}", GBNERF_T2_STAGGER=D)
         run(f"staggered, D = {D}, weights probed first", GBNERF_T2_STAGGER=D, GBNERF_T2_ABL=32)
