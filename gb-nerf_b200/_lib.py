@@ -41,8 +41,6 @@ SIGNATURES = {
     "gbn_mlp_set_trace": (_i, [_p, _i]),
     "gbn_watchdog_report": (_i, [_p, _i]),
     "gbn_debug_ts_plan": (_i, [_i, _p, _i, _p, _i, _p]),
-    "gbn_debug_ts_mma": (_i, [_p, _p, _p, _i, _i, _p]),
-    "gbn_debug_ts_mma_f16": (_i, [_p, _p, _p, _i, _i, _p]),
     "gbn_mlp_forward_embedded": (_i, [_p, _i, _p, _i64, _p, _p, _p, _p]),
     "gbn_mlp_variant": (_i, []),
     "gbn_normals_forward": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),

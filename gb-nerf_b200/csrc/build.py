@@ -19,7 +19,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libgbnerf.so")
 STAMP = os.path.join(PKG, ".libgbnerf.stamp")
-SOURCES = ["abi.cu", "render_ops.cu", "mlp_tc.cu", "mlp_aux.cu", "mlp_wgrad.cu", "render_staged.cu", "ray_setup.cu", "tcnn_model.cu", "normals.cu", "ts_probe.cu", "mlp_ts.cu"]
+SOURCES = ["abi.cu", "render_ops.cu", "mlp_tc.cu", "mlp_aux.cu", "mlp_wgrad.cu", "render_staged.cu", "ray_setup.cu", "tcnn_model.cu", "normals.cu", "mlp_ts.cu"]
+# probes that only the diag / exp builds carry (tools/ts_probe*.py bind them with ctypes themselves)
+TOOL_SOURCES = [os.path.join(os.path.dirname(PKG), "tools", "experiments", "ts_probe.cu")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC,-O2,-Wall", "--expt-relaxed-constexpr"]
@@ -28,7 +30,7 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
 def _digest():
     h = hashlib.sha256(" ".join(FLAGS).encode())
     names = sorted(f for f in os.listdir(HERE) if f.endswith((".cu", ".cuh", ".h")))
-    for n in names + ["../../include/gbnerf.h"]:
+    for n in names + ["../../include/gbnerf.h", "../../tools/experiments/ts_probe.cu"]:
         with open(os.path.join(HERE, n), "rb") as fh:
             h.update(n.encode() + b"\0" + fh.read())
     return h.hexdigest()
@@ -37,7 +39,9 @@ def _digest():
 def build(force=False, verbose=False, diag=False, exp=False, variant=""):
     """variant (with exp): "NAME:MACRO[,MACRO...]" builds libgbnerf_exp_NAME.so with those extra -D flags (A/B of a code
     change on one box in one gpurun call, tools/t2_exp.sh)."""
-    srcs = [s for s in SOURCES if os.path.exists(os.path.join(HERE, s))]
+    srcs = [os.path.join(HERE, s) for s in SOURCES if os.path.exists(os.path.join(HERE, s))]
+    if diag or exp:
+        srcs += [t for t in TOOL_SOURCES if os.path.exists(t)]
     dig = _digest()
     vname, _, vdefs = variant.partition(":")
     extra = ["-D" + d for d in vdefs.split(",") if d]
@@ -50,8 +54,8 @@ def build(force=False, verbose=False, diag=False, exp=False, variant=""):
     objs = []
     procs = []
     for s in srcs:
-        o = os.path.join(HERE, s.replace(".cu", ".diag.o" if diag else f".{suffix[1:]}.o" if exp else ".o"))
-        cmd = [NVCC, *FLAGS, *(["-DGBN_TS_DIAG"] if diag else ["-DGBN_T2_EXP", *extra] if exp else []), "-c", os.path.join(HERE, s), "-o", o]
+        o = os.path.join(HERE, os.path.basename(s).replace(".cu", ".diag.o" if diag else f".{suffix[1:]}.o" if exp else ".o"))
+        cmd = [NVCC, *FLAGS, "-I", HERE, *(["-DGBN_TS_DIAG"] if diag else ["-DGBN_T2_EXP", *extra] if exp else []), "-c", s, "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -224,14 +224,6 @@ int gbn_tcnn_backward(const void* table, const float* rays_o, const float* rays_
                       float loss_scale, float* g_enc, float* g_grid, float* g_sigma_params, float* g_color_params,
                       void* stream);
 
-/* Diagnostic: one 128x128x64 bf16 tcgen05.mma with the A operand in TMEM (A [128,64] bf16 row-major, Bimg a 16 KB
- * K-major 128B-swizzled tile image, D [128,128] fp32 out).  Used by tests/test_gpu_mlp_render.py to pin the TMEM
- * operand layout the MLP kernel relies on. */
-int gbn_debug_ts_mma(const void* A, const void* Bimg, float* D, int a_col, int col_per_kstep, void* stream);
-/* Same with fp16 operands and an fp16 accumulator; D_raw [128,128] uint32 receives the raw TMEM cells of accumulator
- * columns [0,128) (pins how 16-bit accumulators are packed). */
-int gbn_debug_ts_mma_f16(const void* A, const void* Bimg, void* D_raw, int a_col, int col_per_kstep, void* stream);
-
 /* Same network on pre-embedded rows (NeRF.forward's own signature): emb [P,90] fp32 -> raw [P,4]. */
 int gbn_mlp_forward_embedded(const void* packed, int precision, const float* emb, int64_t P, float* raw,
                              void* workspace, void* stash, void* stream);

@@ -1,6 +1,6 @@
 // Diagnostic: one tcgen05.mma with the A operand in TMEM (written with tcgen05.st, row == lane, two consecutive bf16
 // K-elements per 32-bit column) against a K-major 128B-swizzled B tile in shared memory.  D[128,128] = A[128,64] B^T.
-#include "common.cuh"
+#include "common.cuh"   // compiled with -I gb-nerf_b200/csrc by csrc/build.py --exp / --diag
 #include "tc_ptx.cuh"
 
 namespace gbn {

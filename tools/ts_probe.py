@@ -1,7 +1,13 @@
 import ctypes as C, os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from gbnerf_b200 import _lib
+# the probe lives in the exp / diag builds only (csrc/build.py --exp): bound here, not in the product's _lib table
+_dll = C.CDLL(os.environ.get("GBNERF_LIB") or os.path.join(ROOT, "gb-nerf_b200", "libgbnerf_exp.so"))
+class _lib:
+    @staticmethod
+    def call(name, *args):
+        rc = getattr(_dll, name)(*args)
+        assert rc == 0, (name, rc)
 torch.manual_seed(0)
 A = torch.randn(128, 64).bfloat16().cuda()
 B = torch.randn(128, 64).bfloat16().cuda()
