@@ -407,6 +407,9 @@ def train_step_bench(G, ops, dev, nets, kw_test, rank, world, timed):
             "tflops_fwd_bwd": R * 683.6e6 * steps / (ms * 1e-3) / 1e12 / world,
             "grad_allreduce_bytes": sum(f.numel() for f in ts.flat) * 4,
             "allreduce": "NCCL, one per network; the fine network's overlaps the coarse network's backward",
+            "mlp_forward_kernel": ("nerf_mlp_t2_kernel<1, stash> (two tiles in flight, H stash from the epilogue's registers)"
+                                   if os.environ.get("GBNERF_MLP_T2", "1") != "0" and os.environ.get("GBNERF_T2_STASH", "1") != "0"
+                                   and os.environ.get("GBNERF_MLP", "ts") == "ts" else "nerf_mlp_ts_kernel<fwd> (one tile)"),
             "eager_dropin": {"api": "render + loss.backward() + GradBucket.all_reduce() + FusedAdam.step()",
                              "ms_per_step": ms_e / steps, "value": R * steps / (ms_e * 1e-3), "gpu_launches": launches_e,
                              "mlp_kernels_ms_per_step": {k: v[0] / steps for k, v in per.items()},

@@ -31,7 +31,8 @@ class T2Job:
 
 class T2Step:
     def __init__(self, raw):
-        self.mode, self.relu, self.dot, _p, self.bias_off, _p2 = struct.unpack("<BBBBHH", raw)
+        # job0: first job of the step's MMA group; out_blk: first H-stash block of the step's output (training forward)
+        self.mode, self.relu, self.dot, self.job0, self.bias_off, self.out_blk = struct.unpack("<BBBBHH", raw)
 
 
 class T2Plan:

@@ -43,6 +43,9 @@ def test_tables_cover_the_forward_image(plans):
         groups += 1
         j += g.glen
     assert groups == len(t2.steps)
+    # steps and MMA groups are one to one: job0 of a step is the first job of its group
+    firsts = [i for i, jb in enumerate(t2.jobs) if jb.glen]
+    assert [s.job0 for s in t2.steps] == firsts
     assert [s.mode for s in t2.steps] == [M.HOLD, M.FLUSH] * 9 + [M.OUT]
     assert [i for i, s in enumerate(t2.steps) if s.dot] == [14, 15]       # layer 7 feeds alpha_linear
 
@@ -73,3 +76,19 @@ def test_model_catches_a_dropped_wait(plans, flag, what):
                 caught += 1
                 break
     assert caught == 3
+
+
+def test_stash_blocks_match_the_one_tile_forward(plans):
+    """The training form of the kernel writes the H stash that dgrad / wgrad read in the one-tile kernel's block numbering
+    (csrc/mlp_layout.h): every step's out_blk must be the block the one-tile plan gives the same layer half, and the
+    steps together must cover blocks 0 .. 37 exactly once (38 = encoding, 39 = directions: the input warps)."""
+    t2, fwd = plans
+    want = sorted(s.out_blk for s in fwd.steps if s.out_blk != 0xff)          # one 64-channel block pair per step
+    hold = [s.out_blk for s in t2.steps if s.mode == M.HOLD]
+    flush = [s.out_blk + 2 for s in t2.steps if s.mode == M.FLUSH]             # FLUSH writes the blocks after its HOLD's
+    out = [s.out_blk for s in t2.steps if s.mode == M.OUT]
+    assert [s.out_blk for s in t2.steps if s.mode == M.FLUSH] == [b + 2 for b in hold]
+    assert sorted(hold + [b + 2 for b in hold] + out) == want
+    covered = sorted(b + w for b in hold + [h + 2 for h in hold] + out for w in (0, 1))
+    assert covered == list(range(38))
+    del flush
