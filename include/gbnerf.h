@@ -158,8 +158,9 @@ int gbn_watchdog_report(unsigned int* out, int words);
  * 12-byte TsStep records (csrc/mlp_ts_layout.h); meta[0..9] = jobs, steps, a_ready completions per tile [4],
  * issue-order signals per tile, acc1_empty completions per tile, weight-ring stages, split hand-over in use.
  * tests/test_ts_protocol_cpu.py replays the barrier protocol of these tables under random latencies.
- * bwd = 2: the tables of the two-tiles-in-flight inference kernel (csrc/mlp_t2.cuh): 16-byte T2Job and 8-byte T2Step
- * records; meta[0..7] = jobs, steps, weight-ring stages, scheduling mode, slab offsets of alpha_linear (2) and rgb_linear,
+ * bwd = 2: the tables of the two-tiles-in-flight kernel (csrc/mlp_t2.cuh; inference and the stash-writing training
+ * forward): 16-byte T2Job and 8-byte T2Step records (a step names the first job of its MMA group and the first H-stash
+ * block of its output); meta[0..7] = jobs, steps, weight-ring stages, scheduling mode, slab offsets of alpha_linear (2) and rgb_linear,
  * kernel enabled (tests/test_t2_protocol_cpu.py). */
 int gbn_debug_ts_plan(int bwd, void* jobs, int max_jobs, void* steps, int max_steps, int* meta);
 
