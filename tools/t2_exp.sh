@@ -1,8 +1,20 @@
 #!/bin/bash
-# one gpurun call: cycle counts of build variants of the two-tile kernel (tools/t2_exp.py), ncu --set full of the stash-writing form
+# One gpurun call: SM cycles per tile pair of the two-tile MLP kernel (tools/t2_exp.py) for the exp build and for any
+# build variants given as arguments (csrc/build.py --variant=NAME:MACRO builds gb-nerf_b200/libgbnerf_exp_NAME.so):
+#     bash tools/t2_exp.sh [NAME ...]          e.g. after  python gb-nerf_b200/csrc/build.py --variant=foo:GBN_T2_FOO
+# Without arguments: the full sweep of the exp build (turn point, ablations), then a wide layer repeated twice, then the
+# staggered mode.
 mkdir -p gpurun_out
+L=gb-nerf_b200/libgbnerf_exp
 {
-for v in "" _preload _sincos1 _both ""; do echo "== variant '$v'"; GBNERF_LIB=gb-nerf_b200/libgbnerf_exp$v.so T2_EXP_QUICK=1 timeout 120 python tools/t2_exp.py | sed -n 2,4p; done
+if [ $# -gt 0 ]; then
+  for v in "" "$@" ""; do
+    echo "== variant '${v:-exp}'"
+    GBNERF_LIB=$L${v:+_$v}.so T2_EXP_QUICK=1 timeout 120 python tools/t2_exp.py | sed -n 2,4p
+  done
+else
+  for x in 0 2; do GBNERF_LIB=$L.so GBNERF_T2_DBG_EXTRA=$x timeout 120 python tools/t2_exp.py; done
+  for x in 0 2; do GBNERF_LIB=$L.so GBNERF_T2_MODE=2 GBNERF_T2_DBG_EXTRA=$x timeout 120 python tools/t2_exp.py; done
+fi
 } > gpurun_out/t2_exp.log 2>&1
-cat gpurun_out/t2_exp.log | cut -c1-200
-timeout 200 ncu --set full --clock-control none --import-source on -k regex:nerf_mlp_t2 -s 1 -c 1 -f -o gpurun_out/r2_mlp_t2_stash python tools/train_kernels_once.py > gpurun_out/ncu_stash.log 2>&1; echo "ncu rc=$?"; tail -3 gpurun_out/ncu_stash.log
+cut -c1-200 gpurun_out/t2_exp.log
