@@ -1,5 +1,7 @@
-// Two tiles in flight per CTA ("T2"): the inference form of the bf16 TMEM-operand MLP (included by mlp_ts.cu, inside
-// namespace gbn; same packed weight image, same inputs and outputs as nerf_mlp_ts_kernel<fwd> without a stash).
+// Two tiles in flight per CTA ("T2"): the forward of the bf16 TMEM-operand MLP (included by mlp_ts.cu, inside namespace
+// gbn; same packed weight image, same inputs and outputs as nerf_mlp_ts_kernel<fwd>).  nerf_mlp_t2_kernel<1> serves
+// inference, nerf_mlp_t2_kernel<1, true> the training forward: the same kernel with the H-stash stores compiled in
+// (byte-identical to the one-tile kernel's stash, tests/test_gpu_mlp_t2.py); dgrad stays the one-tile program.
 //
 // Why: one 128-point tile per SM leaves the tensor pipe idle while the epilogue converts an accumulator half and the
 // issuer waits for the hand-over - a ~2,700-cycle dependency chain per layer against 2,048 cycles of tensor work
