@@ -70,6 +70,20 @@ def test_sm100a_tensor_core_sass(lib):
             assert re.search(r"\bUTC[A-Z]*MMA\b", fn), f"{name} has no tcgen05.mma"
 
 
+def test_experiments_stay_out_of_the_product_build(lib):
+    """Timing experiments and probes live in the exp / diag builds only (csrc/build.py --exp): the product library has the
+    two shipped schedules of the two-tile MLP kernel (+ its stash-writing form), not the staggered mode, and no probe
+    entry points."""
+    syms = subprocess.check_output(["nm", lib.LIB_PATH], text=True)
+    t2 = sorted(set(re.findall(r"nerf_mlp_t2_kernelILi(\d)ELb(\d)E", syms)))
+    assert t2 == [("0", "0"), ("1", "0"), ("1", "1")], t2
+    assert "gbn_debug_ts_mma" not in syms and "ts_probe_kernel" not in syms
+    assert "mlp_tq" not in syms
+    src = open(os.path.join(ROOT, "gb-nerf_b200", "csrc", "build.py")).read()
+    sources = re.search(r"^SOURCES = \[(.*?)\]", src, flags=re.M).group(1)
+    assert "ts_probe" not in sources and "mlp_tq" not in sources
+
+
 def test_no_cpu_fallback(lib):
     """Operators refuse CPU tensors; without a GPU compute entry points report a CUDA error, never a result."""
     from gbnerf_b200 import ops
