@@ -1,7 +1,8 @@
-"""GPU parity of the two-tiles-in-flight inference MLP kernel (nerf_mlp_t2_kernel, csrc/mlp_t2.cuh) against the one-tile
-kernel it replaces for inference (same packed weights, same inputs) and against the CPU oracle, at ragged sizes: a single
-partial tile, an odd number of tiles (one slot of the last pair idles), pairs spread over many CTAs, and the three input
-forms of gbn_mlp_forward (rays + depths, points, embedded rows).
+"""GPU parity of the two-tiles-in-flight MLP forward kernel (nerf_mlp_t2_kernel, csrc/mlp_t2.cuh) against the one-tile
+kernel it replaces (same packed weights, same inputs) and against the CPU oracle, at ragged sizes: a single partial tile,
+an odd number of tiles (one slot of the last pair idles), pairs spread over many CTAs, and the three input forms of
+gbn_mlp_forward (rays + depths, points, embedded rows); and of its stash-writing (training) form: the H stash must be
+the one-tile kernel's, byte for byte.
 
 The one-tile kernel is selected in-process by handing the library a trace buffer with tile = -1 (ts_forward keeps such
 launches on it).  Tolerance: the two kernels run the same bf16 MMAs on the same operands; only the alpha / rgb heads are
